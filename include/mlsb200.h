@@ -1,0 +1,206 @@
+/*
+ * mlsb200 — C ABI of the B200-native mlsgpu reconstruction core.
+ *
+ * This is the drop-in boundary for the per-bin device path of bmerry/mlsgpu:
+ * octree build -> per-corner MLS -> marching tetrahedra + weld -> scale/bias.
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * upstream tree).  Plain pointers and sizes only; no C++/torch types; no exceptions cross
+ * this boundary — every call returns an mlsb_status and the message of the last failure on
+ * the calling thread is available from mlsb_last_error_string().
+ *
+ * Threading: one mlsb_worker <-> one host thread <-> one GPU, exactly like the reference's
+ * per-worker (SplatTreeCL, MlsFunctor, Marching, ScaleBiasFilter) set created in
+ * DeviceWorkerGroupBase::Worker::Worker (src/workers.cpp:207-225).  A worker owns all of its
+ * device scratch, allocated once at creation for the worst case and recycled per bin
+ * (src/splat_tree_cl.cpp:114-129, src/marching.cpp:380-405).
+ *
+ * There is no CPU fallback: every compute entry point fails with MLSB_ERR_CUDA when no
+ * CUDA device is usable.
+ */
+#ifndef MLSB200_H
+#define MLSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLSB_API __attribute__((visibility("default")))
+
+typedef enum
+{
+    MLSB_OK = 0,
+    MLSB_ERR_INVALID_ARGUMENT = 1,  /* std::invalid_argument in the reference (MLSGPU_ASSERT) */
+    MLSB_ERR_LENGTH = 2,            /* std::length_error: a size exceeds what the worker was built for */
+    MLSB_ERR_STATE = 3,             /* state_error: call sequence violated */
+    MLSB_ERR_CUDA = 4,              /* cl::Error equivalent: the CUDA runtime reported a failure */
+    MLSB_ERR_OVERFLOW = 5           /* mesh does not fit in mesh_bytes even one slice at a time */
+} mlsb_status;
+
+/* struct Splat, src/splat.h:40-45 (device view kernels/mls.cl:63-67).  32 bytes. */
+typedef struct
+{
+    float position[3];   /* grid units (full-grid vertex coordinates, src/bucket_loader.cpp:79-85) */
+    float radius;        /* grid units; the octree build overwrites it with 1/radius^2 */
+    float normal[3];
+    float quality;       /* 1/(smooth*r_world)^2, src/fast_ply.cpp:346-348 */
+} mlsb_splat;
+
+/* MlsShape, src/mls.h:45-49 */
+typedef enum { MLSB_SHAPE_SPHERE = 0, MLSB_SHAPE_PLANE = 1 } mlsb_shape;
+
+/* Marching::Swathe / ImageParams, src/marching.h:167-198: corner (x,y,z) lives at
+ * field[(y + z*zStride + zBias) * pitch + x]. */
+typedef struct
+{
+    uint32_t width, height;   /* corners carrying payload */
+    uint32_t zStride;
+    int32_t zBias;
+    uint32_t zFirst, zLast;   /* closed interval of corner slices */
+} mlsb_swathe;
+
+/* MeshSizes, src/mesh.h:40-81 */
+typedef struct
+{
+    uint64_t numVertices;
+    uint64_t numTriangles;
+    uint64_t numInternalVertices;
+} mlsb_mesh_sizes;
+
+/* What DeviceWorkerGroup hands to each Worker: --levels, --mem-bucket-splats / sizeof(Splat),
+ * maxCells (bin side), per-worker mesh memory, --fit-shape, --fit-boundary-limit
+ * (src/workers.h:214-350, src/mlsgpu_core.cpp:704-741). */
+typedef struct
+{
+    int32_t device;           /* CUDA ordinal (replaces --cl-device) */
+    uint32_t maxLevels;       /* SplatTreeCL maxLevels, 1..10 (src/splat_tree_cl.h:76) */
+    uint32_t subsampling;     /* --subsampling, >= 3 for the MLS kernel (src/mls.cpp:54) */
+    uint32_t maxSplats;       /* SplatTreeCL maxSplats: capacity of the device splat buffer */
+    uint32_t maxCells;        /* bin side in cells; Marching gets maxCells+1 corners per axis */
+    uint64_t meshBytes;       /* Marching meshMemory; vertex/index space = meshBytes/872 cells x 13 / x 36 */
+    int32_t shape;            /* mlsb_shape */
+    float boundaryLimit;      /* --fit-boundary-limit */
+} mlsb_worker_config;
+
+typedef struct mlsb_worker mlsb_worker;
+
+/* Receives one shipped-out block, the equivalent of Marching::OutputFunctor after
+ * enqueueReadMesh (src/marching.h:516-546, src/mesh.cpp:62-102).  hostBlob has the HostKeyMesh
+ * layout (src/mesh.cpp:51-60): [uint64 keys of external vertices][float[3] vertices]
+ * [uint32[3] triangles], 8-byte aligned, mlsb_mesh_host_bytes(sizes) bytes; it is owned by the
+ * worker and valid only during the callback.  Called zero or more times per generate,
+ * serialised, on the calling thread. */
+typedef void (*mlsb_mesh_sink)(const mlsb_mesh_sizes *sizes, const void *hostBlob, void *user);
+
+/* ---- library / device ------------------------------------------------------------------ */
+
+/* CLH::findDevices (src/clh.cpp:180-240): number of usable CUDA devices. */
+MLSB_API int mlsb_device_count(int *count);
+MLSB_API const char *mlsb_last_error_string(void);
+MLSB_API const char *mlsb_version(void);
+
+/* ---- worker lifetime -------------------------------------------------------------------- */
+
+/* DeviceWorkerGroupBase::Worker::Worker, src/workers.cpp:207-225. */
+MLSB_API int mlsb_worker_create(const mlsb_worker_config *config, mlsb_worker **out);
+MLSB_API void mlsb_worker_destroy(mlsb_worker *w);
+/* DeviceWorkerGroup::resourceUsage (src/workers.cpp:176-205): device bytes a worker allocates. */
+MLSB_API int mlsb_worker_resource_usage(const mlsb_worker_config *config, uint64_t *deviceBytes);
+/* The worker's own stream (the cl::CommandQueue of workers.cpp:215). */
+MLSB_API void *mlsb_worker_stream(mlsb_worker *w);
+MLSB_API int mlsb_worker_synchronize(mlsb_worker *w);
+
+/* ---- splat staging (CopyGroup, src/workers.cpp:354-373) --------------------------------- */
+
+/* Pinned host staging memory (CLH::PinnedMemory, src/clh.h). */
+MLSB_API int mlsb_host_alloc(void **ptr, size_t bytes);
+MLSB_API int mlsb_host_free(void *ptr);
+/* Asynchronous H2D of n splats into the worker's splat buffer at element dstFirst, on the
+ * worker's copy stream; the following octree build waits for it (copyEvent, workers.cpp:268). */
+MLSB_API int mlsb_splats_upload_async(mlsb_worker *w, const mlsb_splat *host, uint32_t dstFirst, uint32_t n);
+/* Device address of the worker's splat buffer (SplatTreeCL::getSplats). */
+MLSB_API int mlsb_splats_device(mlsb_worker *w, mlsb_splat **devicePtr);
+
+/* ---- octree: SplatTreeCL (src/splat_tree_cl.h:242-296) ---------------------------------- */
+
+/* SplatTreeCL::enqueueBuild (src/splat_tree_cl.cpp:269-335) on the worker's stream.
+ * size = corners of the region rounded up to 8; offset = bin low extent in the full grid. */
+MLSB_API int mlsb_octree_build(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats,
+                               const uint32_t size[3], const int32_t offset[3],
+                               uint32_t subsamplingShift);
+/* getStart/getCommands/getNumLevels (device pointers; test hook). numCommands = capacity. */
+MLSB_API int mlsb_octree_get(mlsb_worker *w, const int32_t **start, uint32_t *numStart,
+                             const int32_t **commands, uint32_t *numCommands, uint32_t *numLevels);
+
+/* ---- MLS: MlsFunctor (src/mls.h:79-170) -------------------------------------------------- */
+
+/* MlsFunctor::set(offset, tree, subsamplingShift), src/mls.cpp:90-94. */
+MLSB_API int mlsb_mls_set(mlsb_worker *w, const int32_t offset[3], uint32_t subsamplingShift);
+/* MlsFunctor::set(offset, splats, commands, start, shift), src/mls.cpp:76-88: explicit device
+ * buffers (the hand-built octree of test/test_mls.cpp:416-514). */
+MLSB_API int mlsb_mls_set_buffers(mlsb_worker *w, const int32_t offset[3], const mlsb_splat *splats,
+                                  const int32_t *commands, const int32_t *start,
+                                  uint32_t subsamplingShift);
+/* MlsFunctor::setBoundaryLimit, src/mls.cpp:137-144. */
+MLSB_API int mlsb_mls_set_boundary_limit(mlsb_worker *w, float limit);
+/* MlsFunctor::enqueue -> processCorners (src/mls.cpp:101-135, kernels/mls.cl:299-433): fills a
+ * device float image of row pitch `pitch` floats for the swathe, asynchronously. */
+MLSB_API int mlsb_mls_corners(mlsb_worker *w, float *deviceField, uint32_t pitch, const mlsb_swathe *swathe);
+
+/* ---- marching: Marching + ScaleBiasFilter (src/marching.h:564-608, src/mesh_filter.h) ---- */
+
+/* ScaleBiasFilter::setScaleBias(scale, x, y, z), src/mesh_filter.cpp:77-84. */
+MLSB_API int mlsb_set_scale_bias(mlsb_worker *w, float scale, const float bias[3]);
+/* Marching::generate with the MlsFunctor bound by mlsb_mls_set as generator
+ * (src/marching.cpp:745-824).  size = corners per axis of the bin, keyOffset = its low extent.
+ * BLOCKING.  Calls sink once per shipped-out block. */
+MLSB_API int mlsb_marching_generate(mlsb_worker *w, const uint32_t size[3], const uint32_t keyOffset[3],
+                                    mlsb_mesh_sink sink, void *user);
+/* Same with a host-supplied field ([depth][height][width] floats), the HostGenerator of
+ * test/test_marching.cpp:62-129: marching-only tests. */
+MLSB_API int mlsb_marching_generate_host_field(mlsb_worker *w, const float *hostField,
+                                               const uint32_t size[3], const uint32_t keyOffset[3],
+                                               mlsb_mesh_sink sink, void *user);
+/* Bytes of the HostKeyMesh blob, MeshSizes::getHostBytes (src/mesh.h:76-81). */
+MLSB_API uint64_t mlsb_mesh_host_bytes(const mlsb_mesh_sizes *sizes);
+/* The four lookup tables of Marching::makeTables (src/marching.cpp:109-252), host copies:
+ * count 256x2 u8, start 257x2 u16, data 8192 u8, key 2432x3 u32. */
+MLSB_API int mlsb_marching_tables(uint8_t *count, uint16_t *start, uint8_t *data, uint32_t *key);
+
+/* ---- one bin end to end: DeviceWorkerGroupBase::Worker::operator() ---------------------- */
+
+/* src/workers.cpp:232-286 for one SubItem: octree build on splats [firstSplat, firstSplat+n)
+ * of the worker's buffer (previously uploaded), MlsFunctor::set, Marching::generate.
+ * size = bin corners per axis (numVertices), offset = bin low extent (also the key offset). */
+MLSB_API int mlsb_worker_process_bin(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats,
+                                     const uint32_t size[3], const int32_t offset[3],
+                                     mlsb_mesh_sink sink, void *user);
+
+/* ---- statistics (--statistics-cl, src/statistics_cl.cpp) -------------------------------- */
+
+/* Enables CUDA-event timing of every kernel under the reference's statistic names
+ * (kernel.octree.*.time, kernel.mls.processCorners.time, kernel.marching.*.time). */
+MLSB_API int mlsb_worker_set_profiling(mlsb_worker *w, int enabled);
+/* Sum (seconds) and count of a named statistic since the last reset. */
+MLSB_API int mlsb_worker_get_statistic(mlsb_worker *w, const char *name, double *sum, uint64_t *count);
+MLSB_API int mlsb_worker_reset_statistics(mlsb_worker *w);
+/* Work counters of the last MLS launch when profiling is on: pair tests T and hits H of the
+ * SURVEY 8(d) work model, counted on the device. */
+MLSB_API int mlsb_worker_get_mls_work(mlsb_worker *w, uint64_t *pairTests, uint64_t *hits);
+/* Total kernels launched by this worker since creation. */
+MLSB_API uint64_t mlsb_worker_launch_count(mlsb_worker *w);
+
+/* ---- raw device memory helpers for tests and bindings ----------------------------------- */
+MLSB_API int mlsb_device_alloc(void **ptr, size_t bytes);
+MLSB_API int mlsb_device_free(void *ptr);
+MLSB_API int mlsb_memcpy_h2d(void *dst, const void *src, size_t bytes);
+MLSB_API int mlsb_memcpy_d2h(void *dst, const void *src, size_t bytes);
+MLSB_API int mlsb_device_memset(void *dst, int value, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MLSB200_H */

@@ -1,0 +1,362 @@
+"""ctypes binding of include/mlsb200.h.
+
+Method names follow the reference's classes: ``octree_build`` is SplatTreeCL::enqueueBuild,
+``mls_set`` / ``mls_corners`` are MlsFunctor::set / enqueue, ``marching_generate`` is
+Marching::generate (file:line citations are in the header).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+SPLAT_DTYPE = np.dtype([("position", np.float32, 3), ("radius", np.float32),
+                        ("normal", np.float32, 3), ("quality", np.float32)])
+
+STATUS_NAMES = {0: "MLSB_OK", 1: "MLSB_ERR_INVALID_ARGUMENT", 2: "MLSB_ERR_LENGTH", 3: "MLSB_ERR_STATE",
+                4: "MLSB_ERR_CUDA", 5: "MLSB_ERR_OVERFLOW"}
+
+
+class MlsbError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("%s: %s" % (STATUS_NAMES.get(status, status), message))
+        self.status = status
+
+
+class WorkerConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("maxLevels", C.c_uint32), ("subsampling", C.c_uint32),
+                ("maxSplats", C.c_uint32), ("maxCells", C.c_uint32), ("meshBytes", C.c_uint64),
+                ("shape", C.c_int32), ("boundaryLimit", C.c_float)]
+
+
+class Swathe(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("zStride", C.c_uint32), ("zBias", C.c_int32),
+                ("zFirst", C.c_uint32), ("zLast", C.c_uint32)]
+
+
+class MeshSizes(C.Structure):
+    _fields_ = [("numVertices", C.c_uint64), ("numTriangles", C.c_uint64), ("numInternalVertices", C.c_uint64)]
+
+
+MESH_SINK = C.CFUNCTYPE(None, C.POINTER(MeshSizes), C.c_void_p, C.c_void_p)
+
+# every symbol include/mlsb200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+API = {
+    "mlsb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "mlsb_last_error_string": (C.c_char_p, []),
+    "mlsb_version": (C.c_char_p, []),
+    "mlsb_worker_create": (C.c_int, [C.POINTER(WorkerConfig), C.POINTER(_P)]),
+    "mlsb_worker_destroy": (None, [_P]),
+    "mlsb_worker_resource_usage": (C.c_int, [C.POINTER(WorkerConfig), C.POINTER(C.c_uint64)]),
+    "mlsb_worker_stream": (_P, [_P]),
+    "mlsb_worker_synchronize": (C.c_int, [_P]),
+    "mlsb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "mlsb_host_free": (C.c_int, [_P]),
+    "mlsb_splats_upload_async": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32]),
+    "mlsb_splats_device": (C.c_int, [_P, C.POINTER(_P)]),
+    "mlsb_octree_build": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, C.c_uint32]),
+    "mlsb_octree_get": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P), C.POINTER(C.c_uint32),
+                                  C.POINTER(C.c_uint32)]),
+    "mlsb_mls_set": (C.c_int, [_P, _P, C.c_uint32]),
+    "mlsb_mls_set_buffers": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32]),
+    "mlsb_mls_set_boundary_limit": (C.c_int, [_P, C.c_float]),
+    "mlsb_mls_corners": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(Swathe)]),
+    "mlsb_set_scale_bias": (C.c_int, [_P, C.c_float, _P]),
+    "mlsb_marching_generate": (C.c_int, [_P, _P, _P, MESH_SINK, _P]),
+    "mlsb_marching_generate_host_field": (C.c_int, [_P, _P, _P, _P, MESH_SINK, _P]),
+    "mlsb_mesh_host_bytes": (C.c_uint64, [C.POINTER(MeshSizes)]),
+    "mlsb_marching_tables": (C.c_int, [_P, _P, _P, _P]),
+    "mlsb_worker_process_bin": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, MESH_SINK, _P]),
+    "mlsb_worker_set_profiling": (C.c_int, [_P, C.c_int]),
+    "mlsb_worker_get_statistic": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "mlsb_worker_reset_statistics": (C.c_int, [_P]),
+    "mlsb_worker_get_mls_work": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "mlsb_worker_launch_count": (C.c_uint64, [_P]),
+    "mlsb_device_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "mlsb_device_free": (C.c_int, [_P]),
+    "mlsb_memcpy_h2d": (C.c_int, [_P, _P, C.c_size_t]),
+    "mlsb_memcpy_d2h": (C.c_int, [_P, _P, C.c_size_t]),
+    "mlsb_device_memset": (C.c_int, [_P, C.c_int, C.c_size_t]),
+}
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(_HERE, "libmlsb200.so")
+
+
+def lib():
+    """Loads libmlsb200.so (fails loudly if it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise MlsbError(4, "%s is missing: run `make -C mlsgpu_b200` (or __graft_entry__.build())" % path)
+        handle = C.CDLL(path)
+        for name, (res, args) in API.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def _check(status):
+    if status != 0:
+        raise MlsbError(status, lib().mlsb_last_error_string().decode())
+
+
+def version():
+    return lib().mlsb_version().decode()
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(lib().mlsb_device_count(C.byref(n)))
+    return n.value
+
+
+def marching_tables():
+    count = np.zeros((256, 2), np.uint8)
+    start = np.zeros((257, 2), np.uint16)
+    data = np.zeros(8192, np.uint8)
+    key = np.zeros((2432, 3), np.uint32)
+    _check(lib().mlsb_marching_tables(count.ctypes.data, start.ctypes.data, data.ctypes.data, key.ctypes.data))
+    return dict(count=count, start=start, data=data, key=key)
+
+
+def _arr3(v, dtype):
+    a = np.ascontiguousarray(v, dtype)
+    assert a.shape == (3,)
+    return a
+
+
+class DeviceBuffer:
+    """Raw device allocation (tests and benchmarks only)."""
+
+    def __init__(self, nbytes):
+        self.ptr = _P()
+        self.nbytes = nbytes
+        _check(lib().mlsb_device_alloc(C.byref(self.ptr), nbytes))
+
+    @classmethod
+    def from_array(cls, a):
+        a = np.ascontiguousarray(a)
+        buf = cls(a.nbytes)
+        if a.nbytes:
+            _check(lib().mlsb_memcpy_h2d(buf.ptr, a.ctypes.data, a.nbytes))
+        return buf
+
+    def fill(self, byte):
+        _check(lib().mlsb_device_memset(self.ptr, byte, self.nbytes))
+
+    def to_array(self, dtype, shape):
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        if out.nbytes:
+            _check(lib().mlsb_memcpy_d2h(out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().mlsb_device_free(self.ptr)
+            self.ptr = _P()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Pinned host staging memory exposed as a numpy array (CLH::PinnedMemory)."""
+
+    def __init__(self, dtype, count):
+        self.ptr = _P()
+        dtype = np.dtype(dtype)
+        self.nbytes = dtype.itemsize * count
+        _check(lib().mlsb_host_alloc(C.byref(self.ptr), self.nbytes))
+        raw = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr.value)
+        self.array = np.frombuffer(raw, dtype=dtype, count=count)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().mlsb_host_free(self.ptr)
+            self.ptr = _P()
+
+
+class Worker:
+    """One worker = one GPU = one host thread (DeviceWorkerGroupBase::Worker)."""
+
+    def __init__(self, device=0, max_levels=6, subsampling=3, max_splats=1 << 20, max_cells=255,
+                 mesh_bytes=None, shape=0, boundary_limit=1.0):
+        if mesh_bytes is None:
+            mesh_bytes = max(64 << 20, max_cells * max_cells * 872)
+        self.cfg = WorkerConfig(device, max_levels, subsampling, max_splats, max_cells, mesh_bytes, shape,
+                                boundary_limit)
+        self.h = _P()
+        _check(lib().mlsb_worker_create(C.byref(self.cfg), C.byref(self.h)))
+        self._keep = []
+
+    # ---- lifetime --------------------------------------------------------------------------
+    def close(self):
+        if self.h:
+            lib().mlsb_worker_destroy(self.h)
+            self.h = _P()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(lib().mlsb_worker_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return lib().mlsb_worker_stream(self.h)
+
+    # ---- splats ----------------------------------------------------------------------------
+    def upload_splats(self, splats, dst_first=0):
+        """Async H2D from a host array (pinned or pageable); keep the array alive until the
+        next synchronize()."""
+        assert splats.dtype == SPLAT_DTYPE and splats.flags.c_contiguous
+        self._keep.append(splats)
+        _check(lib().mlsb_splats_upload_async(self.h, splats.ctypes.data, dst_first, len(splats)))
+
+    def download_splats(self, first, n):
+        self.synchronize()
+        ptr = _P()
+        _check(lib().mlsb_splats_device(self.h, C.byref(ptr)))
+        out = np.empty(n, SPLAT_DTYPE)
+        if n:
+            _check(lib().mlsb_memcpy_d2h(out.ctypes.data, ptr.value + 32 * first, out.nbytes))
+        return out
+
+    # ---- octree ----------------------------------------------------------------------------
+    def octree_build(self, first, n, size, offset, subsampling=None):
+        size = _arr3(size, np.uint32)
+        offset = _arr3(offset, np.int32)
+        sub = self.cfg.subsampling if subsampling is None else subsampling
+        _check(lib().mlsb_octree_build(self.h, first, n, size.ctypes.data, offset.ctypes.data, sub))
+
+    def octree_get(self, num_commands=None):
+        """Host copies of (start, commands)."""
+        self.synchronize()
+        start, commands = _P(), _P()
+        ns, nc, nl = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().mlsb_octree_get(self.h, C.byref(start), C.byref(ns), C.byref(commands), C.byref(nc), C.byref(nl)))
+        hs = np.empty(ns.value, np.int32)
+        _check(lib().mlsb_memcpy_d2h(hs.ctypes.data, start, hs.nbytes))
+        n = nc.value if num_commands is None else min(num_commands, nc.value)
+        hc = np.empty(n, np.int32)
+        if n:
+            _check(lib().mlsb_memcpy_d2h(hc.ctypes.data, commands, hc.nbytes))
+        return hs, hc
+
+    def octree_fill_commands(self, byte):
+        """Overwrites the command buffer (tests: detect slots the build does not write)."""
+        start, commands = _P(), _P()
+        ns, nc, nl = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().mlsb_octree_get(self.h, C.byref(start), C.byref(ns), C.byref(commands), C.byref(nc), C.byref(nl)))
+        _check(lib().mlsb_device_memset(commands, byte, 4 * nc.value))
+
+    # ---- MLS -------------------------------------------------------------------------------
+    def mls_set(self, offset, subsampling=None):
+        offset = _arr3(offset, np.int32)
+        sub = self.cfg.subsampling if subsampling is None else subsampling
+        _check(lib().mlsb_mls_set(self.h, offset.ctypes.data, sub))
+
+    def mls_set_buffers(self, offset, splats, commands, start, subsampling):
+        offset = _arr3(offset, np.int32)
+        _check(lib().mlsb_mls_set_buffers(self.h, offset.ctypes.data, splats.ptr, commands.ptr, start.ptr, subsampling))
+
+    def mls_set_boundary_limit(self, limit):
+        _check(lib().mlsb_mls_set_boundary_limit(self.h, limit))
+
+    def mls_corners(self, field, pitch, width, height, z_stride, z_bias, z_first, z_last):
+        sw = Swathe(width, height, z_stride, z_bias, z_first, z_last)
+        _check(lib().mlsb_mls_corners(self.h, field.ptr, pitch, C.byref(sw)))
+
+    # ---- marching --------------------------------------------------------------------------
+    def set_scale_bias(self, scale, bias):
+        bias = _arr3(bias, np.float32)
+        _check(lib().mlsb_set_scale_bias(self.h, scale, bias.ctypes.data))
+
+    @staticmethod
+    def _collector(blocks):
+        def sink(sizes_p, blob, _user):
+            s = sizes_p.contents
+            nv, nt, ni = int(s.numVertices), int(s.numTriangles), int(s.numInternalVertices)
+            ne = nv - ni
+            nbytes = 8 * ne + 12 * nv + 12 * nt
+            raw = np.frombuffer((C.c_char * max(nbytes, 1)).from_address(blob), np.uint8, nbytes).copy()
+            keys = raw[:8 * ne].view(np.uint64)
+            verts = raw[8 * ne:8 * ne + 12 * nv].view(np.float32).reshape(nv, 3)
+            tris = raw[8 * ne + 12 * nv:].view(np.uint32).reshape(nt, 3)
+            blocks.append(dict(vertices=verts, external_keys=keys, triangles=tris, num_internal=ni))
+        return MESH_SINK(sink)
+
+    def marching_generate(self, size, key_offset):
+        """Marching::generate with the bound MlsFunctor; returns the shipped-out blocks."""
+        blocks = []
+        cb = self._collector(blocks)
+        size = _arr3(size, np.uint32)
+        ko = _arr3(key_offset, np.uint32)
+        _check(lib().mlsb_marching_generate(self.h, size.ctypes.data, ko.ctypes.data, cb, None))
+        return blocks
+
+    def marching_generate_host_field(self, field, key_offset):
+        """field: [depth][height][width] float32 volume."""
+        field = np.ascontiguousarray(field, np.float32)
+        d, h, w = field.shape
+        blocks = []
+        cb = self._collector(blocks)
+        size = _arr3((w, h, d), np.uint32)
+        ko = _arr3(key_offset, np.uint32)
+        _check(lib().mlsb_marching_generate_host_field(self.h, field.ctypes.data, size.ctypes.data, ko.ctypes.data,
+                                                       cb, None))
+        return blocks
+
+    def process_bin(self, first, n, size, offset, collect=True):
+        """DeviceWorkerGroupBase::Worker::operator() for one bin."""
+        blocks = []
+        cb = self._collector(blocks) if collect else MESH_SINK(lambda a, b, c: None)
+        size = _arr3(size, np.uint32)
+        offset = _arr3(offset, np.int32)
+        _check(lib().mlsb_worker_process_bin(self.h, first, n, size.ctypes.data, offset.ctypes.data, cb, None))
+        self._keep.clear()
+        return blocks
+
+    # ---- statistics ------------------------------------------------------------------------
+    def set_profiling(self, enabled):
+        _check(lib().mlsb_worker_set_profiling(self.h, int(enabled)))
+
+    def statistic(self, name):
+        s, c = C.c_double(), C.c_uint64()
+        _check(lib().mlsb_worker_get_statistic(self.h, name.encode(), C.byref(s), C.byref(c)))
+        return s.value, c.value
+
+    def reset_statistics(self):
+        _check(lib().mlsb_worker_reset_statistics(self.h))
+
+    def mls_work(self):
+        t, h = C.c_uint64(), C.c_uint64()
+        _check(lib().mlsb_worker_get_mls_work(self.h, C.byref(t), C.byref(h)))
+        return t.value, h.value
+
+    @property
+    def launch_count(self):
+        return int(lib().mlsb_worker_launch_count(self.h))

@@ -1,0 +1,195 @@
+// Internal definitions shared by the CUDA translation units of libmlsb200.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mlsb200.h"
+
+namespace mlsb
+{
+
+void setError(const char *fmt, ...);
+
+#define MLSB_CUDA(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t err_ = (call);                                                            \
+        if (err_ != cudaSuccess) {                                                            \
+            mlsb::setError("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(err_)); \
+            return MLSB_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+#define MLSB_REQUIRE(cond, status, msg)                                                       \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            mlsb::setError("%s:%d: %s (%s)", __FILE__, __LINE__, msg, #cond);                 \
+            return status;                                                                    \
+        }                                                                                     \
+    } while (0)
+
+#define MLSB_TRY(expr)                                                                        \
+    do {                                                                                      \
+        int st_ = (expr);                                                                     \
+        if (st_ != MLSB_OK) return st_;                                                       \
+    } while (0)
+
+template <typename T> static inline T divUp(T a, T b) { return (a + b - 1) / b; }
+template <typename T> static inline T roundUp(T a, T b) { return divUp(a, b) * b; }
+
+constexpr int kMaxLevels = 10;             // SplatTreeCL::MAX_LEVELS, src/splat_tree_cl.h:76
+constexpr int kMlsWgs = 8;                 // MlsFunctor::wgs, src/mls.cpp:53
+constexpr unsigned kKeyAxisBits = 21;      // Marching::KEY_AXIS_BITS, src/marching.h:113
+constexpr unsigned kMaxCellVertices = 13;  // src/marching.h:88
+constexpr unsigned kMaxCellIndices = 36;   // src/marching.h:92
+constexpr unsigned kMaxCellBytes = 872;    // src/marching.h:97-100
+
+// One timed interval recorded with a pair of CUDA events on the worker's stream.
+struct TimedSpan
+{
+    cudaEvent_t begin, end;
+    int stat;   // index into Worker::statNames
+};
+
+struct StatAccum
+{
+    double sum = 0.0;
+    uint64_t count = 0;
+};
+
+// Device-side layout of the radix sort scratch (see sort.cu).
+struct SortScratch
+{
+    uint32_t *hist = nullptr;      // [passes][256] global digit histograms
+    uint32_t *status = nullptr;    // [passes][tiles][256] decoupled look-back words
+    uint32_t *tickets = nullptr;   // [passes] dynamic tile counters
+    size_t statusWordsPerPass = 0;
+    uint32_t maxPasses = 0;
+    size_t maxItems = 0;
+};
+
+}  // namespace mlsb
+
+struct mlsb_worker
+{
+    mlsb_worker_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;      // compute (the cl::CommandQueue of workers.cpp:215)
+    cudaStream_t copyStream = nullptr;  // H2D staging (CopyGroup's queue, workers.cpp:101)
+    cudaEvent_t copyEvent = nullptr;
+    bool copyPending = false;
+
+    // ---- splats (DeviceWorkerGroup::WorkItem::splats) ----
+    mlsb_splat *splats = nullptr;
+
+    // ---- octree (SplatTreeCL members, src/splat_tree_cl.cpp:114-129) ----
+    uint32_t numStartMax = 0;
+    uint32_t numStart = 0;
+    uint32_t numCommandsMax = 0;
+    int32_t *start = nullptr;
+    int32_t *runStart = nullptr;   // start slot of each non-empty key, else -1 (plays jumpPos' role too)
+    int32_t *jumpPos = nullptr;
+    int32_t *commands = nullptr;
+    uint32_t *entryKeys[2] = {nullptr, nullptr};
+    uint32_t *entryValues[2] = {nullptr, nullptr};
+    int32_t *runFirst = nullptr, *runLast = nullptr;
+    uint32_t *runIndex = nullptr;
+    uint64_t *scanStatus = nullptr;   // decoupled look-back words for device-wide scans
+    uint32_t scanStatusWords = 0;
+    uint32_t *scanTicket = nullptr;
+    mlsb::SortScratch sort;
+
+    // ---- MLS (MlsFunctor kernel arguments, src/mls.cpp:76-94) ----
+    const mlsb_splat *mlsSplats = nullptr;
+    const int32_t *mlsCommands = nullptr;
+    const int32_t *mlsStart = nullptr;
+    int32_t mlsOffset[3] = {0, 0, 0};
+    uint32_t mlsStartShift = 0;
+    float boundaryFactor = 0.0f;
+    bool mlsBound = false;
+    unsigned long long *mlsWork = nullptr;   // device: [0] pair tests, [1] hits (profiling only)
+
+    // ---- marching (Marching members, src/marching.cpp:380-405) ----
+    uint32_t fieldDim = 0;        // corners per axis the field was allocated for, rounded to 8
+    float *field = nullptr;       // [z][y][x], pitch fieldDim
+    uint64_t vertexSpace = 0, indexSpace = 0;
+    float4 *unwelded = nullptr;
+    uint32_t *vertKeys[2] = {nullptr, nullptr};
+    uint32_t *vertIdx[2] = {nullptr, nullptr};
+    uint32_t *indexRemap = nullptr;
+    uint32_t *indices = nullptr;
+    float *welded = nullptr;          // packed float3
+    uint64_t *weldedKeys = nullptr;
+    uint32_t *marchCounters = nullptr;   // device: see marching.cu
+    uint32_t *sliceHist = nullptr;       // per-slice (vertices, indices) histogram
+    float scale = 1.0f;
+    float bias[3] = {0.0f, 0.0f, 0.0f};
+    void *hostBlob = nullptr;     // pinned readback buffer
+    size_t hostBlobBytes = 0;
+    uint32_t *hostCounters = nullptr;   // pinned
+    uint8_t *tables = nullptr;          // device copy of the marching LUTs
+
+    // ---- statistics ----
+    bool profiling = false;
+    std::vector<std::string> statNames;
+    std::map<std::string, int> statIndex;
+    std::vector<mlsb::StatAccum> stats;
+    std::vector<mlsb::TimedSpan> pendingSpans;
+    std::vector<cudaEvent_t> eventPool;
+    uint64_t launches = 0;
+};
+
+namespace mlsb
+{
+
+// RAII helper: times everything enqueued on the worker stream during its lifetime under a
+// reference statistic name (Statistics::timeEvent, src/statistics_cl.cpp:62-160).
+class ScopedStat
+{
+public:
+    ScopedStat(mlsb_worker *w, const char *name, int kernels = 1);
+    ~ScopedStat();
+
+private:
+    mlsb_worker *w;
+    int idx;
+    cudaEvent_t begin;
+};
+
+int statId(mlsb_worker *w, const char *name);
+void collectStats(mlsb_worker *w);   // requires the stream to be idle
+
+// sort.cu
+int sortScratchAlloc(SortScratch &s, size_t maxItems, uint32_t maxPasses);
+void sortScratchFree(SortScratch &s);
+// Stable LSD radix sort of (key,value) u32 pairs on the low `bits` bits.  Input in keys[0] /
+// values[0]; returns in *result which of the two buffers holds the output.
+int radixSortPairs(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n, uint32_t bits,
+                   int *result, const char *statName);
+// Same, with the element count min(*nDev, n) read on the device (grids are sized for n).
+int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n,
+                              const uint32_t *nDev, uint32_t bits, int *result, const char *statName);
+
+// octree.cu
+int octreeAlloc(mlsb_worker *w);
+void octreeFree(mlsb_worker *w);
+int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const int32_t offset[3],
+                uint32_t subsamplingShift);
+
+// mls.cu
+int mlsAlloc(mlsb_worker *w);
+void mlsFree(mlsb_worker *w);
+int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &sw);
+
+// marching.cu
+int marchingAlloc(mlsb_worker *w);
+void marchingFree(mlsb_worker *w);
+int marchingGenerate(mlsb_worker *w, bool useMls, const float *hostField, const uint32_t size[3],
+                     const uint32_t keyOffset[3], mlsb_mesh_sink sink, void *user);
+int marchingTablesHost(uint8_t *count, uint16_t *start, uint8_t *data, uint32_t *key);
+
+}  // namespace mlsb

@@ -1,0 +1,321 @@
+// Per-corner MLS field: MlsFunctor::enqueue (src/mls.cpp:101-135) and processCorners
+// (kernels/mls.cl:299-433), sphere and plane fits.
+//
+// One CTA per 8x8x8 block of corners, as in the reference, but 128 threads that each own FOUR
+// corners sharing (y, z):  dot3(p,p) = fma(px,px, fma(py,py, pz*pz)) (kernels/mls.cl:105-108),
+// so the inner fma(py,py,pz*pz) — and py, pz themselves — are computed once per splat per
+// thread and reused by the four corners.  A pair test therefore costs 3 FP32 instructions
+// (+4 shared by four corners) instead of the 7 of one-thread-per-corner, with bit-identical
+// results.  For each of a thread's four slots the 32 lanes of a warp cover a compact 2x4x4
+// brick of corners, which keeps the warp-level "any lane hit" rate — what the accumulation
+// cost is proportional to — low.
+//
+// Rounding contract (shared with oracle/orc_mls.c): every operation is written with an
+// explicit round-to-nearest intrinsic, fused only where the oracle fuses; the translation
+// unit is also compiled with -fmad=false.  The field is bit-identical to the oracle's.
+#include "common.cuh"
+#include <cfloat>
+#include <climits>
+
+namespace mlsb
+{
+
+namespace
+{
+
+constexpr int kThreads = 128;
+constexpr int kChunk = 128;          // splats staged per batch
+constexpr float kRadiusCutoff = 0.99f;   // kernels/mls.cl:36
+constexpr int kHitsCutoff = 4;           // kernels/mls.cl:37
+
+struct MlsParams
+{
+    const mlsb_splat *splats;
+    const int32_t *commands;
+    const int32_t *start;
+    float *field;
+    uint32_t pitch;
+    uint32_t startShift;
+    int3 offset;
+    uint32_t zStride;
+    int32_t zBias;
+    uint32_t zFirst;
+    float boundaryFactor;
+    unsigned long long *work;   // [0] pair tests, [1] hits (COUNT builds only)
+};
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v)
+{
+    v &= 0x3FF;
+    v = (v | (v << 16)) & 0x030000FF;
+    v = (v | (v << 8)) & 0x0300F00F;
+    v = (v | (v << 4)) & 0x030C30C3;
+    v = (v | (v << 2)) & 0x09249249;
+    return v;
+}
+
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return __fmaf_rn(ax, bx, __fmaf_rn(ay, by, __fmul_rn(az, bz)));
+}
+
+__device__ __forceinline__ bool finite(float x) { return (__float_as_uint(x) & 0x7F800000u) != 0x7F800000u; }
+
+struct Accum
+{
+    float sumW, sumWpx, sumWpy, sumWpz, sumWnx, sumWny, sumWnz, sumWpp, sumWpn;
+    uint32_t hits;
+};
+
+// kernels/mls.cl:237-248
+__device__ __forceinline__ float solveQuadratic(float a, float b, float c)
+{
+    float det = __fsub_rn(__fmul_rn(b, b), __fmul_rn(__fmul_rn(4.0f, a), c));
+    float bdet = __fadd_rn(b, __fsqrt_rn(det));
+    float x = __fdiv_rn(__fmul_rn(-2.0f, c), bdet);
+    if (!finite(x)) x = __fdiv_rn(bdet, __fmul_rn(-2.0f, a));
+    return finite(x) ? x : __uint_as_float(0x7FC00000u);
+}
+
+// kernels/mls.cl:394-424 (+ fitSphere :210-229, projectOriginSphere :263-267, fitPlane :198-203)
+template <int SHAPE> __device__ __forceinline__ float finish(const Accum &f, float boundaryFactor)
+{
+    float result = __uint_as_float(0x7FC00000u);
+    if (f.hits < kHitsCutoff) return result;
+    if (SHAPE == MLSB_SHAPE_SPHERE)
+    {
+        float invSumW = __fdiv_rn(1.0f, f.sumW);
+        float mx = __fmul_rn(f.sumWpx, invSumW), my = __fmul_rn(f.sumWpy, invSumW), mz = __fmul_rn(f.sumWpz, invSumW);
+        float qNum = __fsub_rn(f.sumWpn, dot3(mx, my, mz, f.sumWnx, f.sumWny, f.sumWnz));
+        float qDen = __fsub_rn(f.sumWpp, dot3(mx, my, mz, f.sumWpx, f.sumWpy, f.sumWpz));
+        float q = __fdiv_rn(qNum, qDen);
+        float lim = __fmul_rn(__fmul_rn(4 * FLT_EPSILON, (float) f.hits), fabsf(f.sumWpp));
+        if (fabsf(qDen) < lim || !finite(q)) q = 0.0f;
+        float a = __fmul_rn(0.5f, q);
+        float bx = __fmul_rn(__fsub_rn(f.sumWnx, __fmul_rn(q, f.sumWpx)), invSumW);
+        float by = __fmul_rn(__fsub_rn(f.sumWny, __fmul_rn(q, f.sumWpy)), invSumW);
+        float bz = __fmul_rn(__fsub_rn(f.sumWnz, __fmul_rn(q, f.sumWpz)), invSumW);
+        float c = __fmul_rn(__fsub_rn(__fmul_rn(-a, f.sumWpp), dot3(bx, by, bz, f.sumWpx, f.sumWpy, f.sumWpz)), invSumW);
+        float b2 = dot3(bx, by, bz, bx, by, bz);
+        float l = solveQuadratic(__fmul_rn(a, b2), b2, c);
+        float ax = __fmul_rn(l, bx), ay = __fmul_rn(l, by), az = __fmul_rn(l, bz);
+        float aa = dot3(ax, ay, az, ax, ay, az);
+        if (aa < 3.0f)
+        {
+            float rhs = __fadd_rn(__fsub_rn(f.sumWpp, __fmul_rn(2.0f, dot3(f.sumWpx, f.sumWpy, f.sumWpz, ax, ay, az))),
+                                  __fmul_rn(f.sumW, aa));
+            if (qDen > __fmul_rn(boundaryFactor, rhs))
+                result = __fmul_rn(-dot3(bx, by, bz, ax, ay, az), __fdiv_rn(1.0f, __fsqrt_rn(b2)));
+        }
+    }
+    else
+    {
+        float mx = __fdiv_rn(f.sumWpx, f.sumW), my = __fdiv_rn(f.sumWpy, f.sumW), mz = __fdiv_rn(f.sumWpz, f.sumW);
+        float rl = __fdiv_rn(1.0f, __fsqrt_rn(dot3(f.sumWnx, f.sumWny, f.sumWnz, f.sumWnx, f.sumWny, f.sumWnz)));
+        float nx = __fmul_rn(f.sumWnx, rl), ny = __fmul_rn(f.sumWny, rl), nz = __fmul_rn(f.sumWnz, rl);
+        float dist = -dot3(nx, ny, nz, mx, my, mz);
+        float ax = __fmul_rn(nx, -dist), ay = __fmul_rn(ny, -dist), az = __fmul_rn(nz, -dist);
+        float aa = dot3(ax, ay, az, ax, ay, az);
+        if (aa < 3.0f)
+        {
+            float qDen = __fsub_rn(f.sumWpp, dot3(mx, my, mz, f.sumWpx, f.sumWpy, f.sumWpz));
+            float rhs = __fadd_rn(__fsub_rn(f.sumWpp, __fmul_rn(2.0f, dot3(f.sumWpx, f.sumWpy, f.sumWpz, ax, ay, az))),
+                                  __fmul_rn(f.sumW, aa));
+            if (qDen > __fmul_rn(boundaryFactor, rhs)) result = dist;
+        }
+    }
+    return result;
+}
+
+template <int SHAPE, bool COUNT>
+__global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
+{
+    __shared__ float4 sPosR[kChunk];
+    __shared__ float4 sNormQ[kChunk];
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31, quad = tid >> 5;
+    // corner layout inside the block: x = xi + 2j (j = slot 0..3), y, z fixed per thread
+    const int xi = lane & 1;
+    const int ly = (int) ((lane >> 1) & 3) + 4 * (int) (quad & 1);
+    const int lz = (int) ((lane >> 3) & 3) + 4 * (int) (quad >> 1);
+    const int wx = blockIdx.x * kMlsWgs, wy = blockIdx.y * kMlsWgs, wz = blockIdx.z * kMlsWgs + (int) P.zFirst;
+
+    const uint32_t code = (spread3(wx) | (spread3(wy) << 1) | (spread3(wz) << 2)) >> P.startShift;
+    int32_t pos = P.start[code];
+
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[j] = __uint_as_float(0x7FC00000u);
+
+    if (pos >= 0)
+    {
+        const float cy = (float) (wy + ly + P.offset.y);
+        const float cz = (float) (wz + lz + P.offset.z);
+        float cx[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) cx[j] = (float) (wx + xi + 2 * j + P.offset.x);
+
+        Accum acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            acc[j].sumW = acc[j].sumWpx = acc[j].sumWpy = acc[j].sumWpz = 0.0f;
+            acc[j].sumWnx = acc[j].sumWny = acc[j].sumWnz = acc[j].sumWpp = acc[j].sumWpn = 0.0f;
+            acc[j].hits = 0;
+        }
+        unsigned long long tests = 0;
+
+        int32_t end = P.commands[pos++];
+        while (pos < end)
+        {
+            // stage one batch; as in the reference a batch never spans two ranges (:336-358)
+            int32_t lpos = pos + (int32_t) tid;
+            if (lpos < end)
+            {
+                int32_t id = P.commands[lpos];
+                const float4 *sp = reinterpret_cast<const float4 *>(P.splats + id);
+                sPosR[tid] = __ldg(sp);
+                sNormQ[tid] = __ldg(sp + 1);
+            }
+            const int count = min(end - pos, kChunk);
+            pos += kChunk;
+            if (pos >= end)
+            {
+                pos = P.commands[end];
+                end = pos >= 0 ? P.commands[pos++] : INT_MIN;
+            }
+            __syncthreads();
+            if (COUNT) tests += 4ull * count;
+
+            for (int i = 0; i < count; i++)
+            {
+                const float4 s = sPosR[i];
+                const float pz = __fsub_rn(s.z, cz);
+                const float py = __fsub_rn(s.y, cy);
+                const float t = __fmaf_rn(py, py, __fmul_rn(pz, pz));
+                float px[4], pp[4], d[4];
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    px[j] = __fsub_rn(s.x, cx[j]);
+                    pp[j] = __fmaf_rn(px[j], px[j], t);
+                    d[j] = __fmul_rn(pp[j], s.w);
+                    any |= d[j] < kRadiusCutoff;
+                }
+                if (__any_sync(0xFFFFFFFFu, any))
+                {
+                    const float4 nq = sNormQ[i];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        if (d[j] < kRadiusCutoff)
+                        {
+                            float w = __fsub_rn(1.0f, d[j]);
+                            w = __fmul_rn(w, w);
+                            w = __fmul_rn(w, w);
+                            w = __fmul_rn(w, nq.w);
+                            Accum &a = acc[j];
+                            a.sumW = __fadd_rn(a.sumW, w);
+                            a.sumWpx = __fmaf_rn(w, px[j], a.sumWpx);
+                            a.sumWpy = __fmaf_rn(w, py, a.sumWpy);
+                            a.sumWpz = __fmaf_rn(w, pz, a.sumWpz);
+                            a.sumWnx = __fmaf_rn(w, nq.x, a.sumWnx);
+                            a.sumWny = __fmaf_rn(w, nq.y, a.sumWny);
+                            a.sumWnz = __fmaf_rn(w, nq.z, a.sumWnz);
+                            a.sumWpp = __fmaf_rn(w, pp[j], a.sumWpp);
+                            a.sumWpn = __fmaf_rn(w, dot3(nq.x, nq.y, nq.z, px[j], py, pz), a.sumWpn);
+                            a.hits++;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        unsigned long long hits = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            out[j] = finish<SHAPE>(acc[j], P.boundaryFactor);
+            if (COUNT) hits += acc[j].hits;
+        }
+        if (COUNT)
+        {
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                tests += __shfl_xor_sync(0xFFFFFFFFu, tests, o);
+                hits += __shfl_xor_sync(0xFFFFFFFFu, hits, o);
+            }
+            if (lane == 0)
+            {
+                atomicAdd(&P.work[0], tests);
+                atomicAdd(&P.work[1], hits);
+            }
+        }
+    }
+
+    // write_imagef(corners, (x, y + z*zStride + zBias)), kernels/mls.cl:429-432
+    const long row = (long) (wy + ly) + (long) (wz + lz) * P.zStride + P.zBias;
+    float *dst = P.field + row * P.pitch + wx + xi;
+#pragma unroll
+    for (int j = 0; j < 4; j++) dst[2 * j] = out[j];
+}
+
+}  // namespace
+
+int mlsAlloc(mlsb_worker *w)
+{
+    MLSB_CUDA(cudaMalloc(&w->mlsWork, 2 * sizeof(unsigned long long)));
+    MLSB_CUDA(cudaMemset(w->mlsWork, 0, 2 * sizeof(unsigned long long)));
+    return MLSB_OK;
+}
+
+void mlsFree(mlsb_worker *w) { cudaFree(w->mlsWork); }
+
+int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &sw)
+{
+    MLSB_REQUIRE(w->mlsBound, MLSB_ERR_STATE, "mlsb_mls_set has not been called");
+    // src/mls.cpp:108-117
+    uint32_t width = roundUp(sw.width, (uint32_t) kMlsWgs);
+    uint32_t height = roundUp(sw.height, (uint32_t) kMlsWgs);
+    MLSB_REQUIRE(sw.zStride >= height, MLSB_ERR_INVALID_ARGUMENT, "zStride smaller than the padded height");
+    MLSB_REQUIRE(sw.zFirst <= sw.zLast, MLSB_ERR_INVALID_ARGUMENT, "empty swathe");
+    MLSB_REQUIRE(sw.zFirst % kMlsWgs == 0, MLSB_ERR_INVALID_ARGUMENT, "zFirst must be a multiple of 8");
+    MLSB_REQUIRE(pitch >= width, MLSB_ERR_LENGTH, "field pitch smaller than the padded width");
+    MLSB_REQUIRE((long) sw.zFirst * sw.zStride + sw.zBias >= 0, MLSB_ERR_INVALID_ARGUMENT, "swathe starts before the image");
+
+    MlsParams P;
+    P.splats = w->mlsSplats;
+    P.commands = w->mlsCommands;
+    P.start = w->mlsStart;
+    P.field = field;
+    P.pitch = pitch;
+    P.startShift = w->mlsStartShift;
+    P.offset = make_int3(w->mlsOffset[0], w->mlsOffset[1], w->mlsOffset[2]);
+    P.zStride = sw.zStride;
+    P.zBias = sw.zBias;
+    P.zFirst = sw.zFirst;
+    P.boundaryFactor = w->boundaryFactor;
+    P.work = w->mlsWork;
+    dim3 grid(width / kMlsWgs, height / kMlsWgs, divUp(sw.zLast - sw.zFirst + 1, (uint32_t) kMlsWgs));
+    ScopedStat st(w, "kernel.mls.processCorners.time");
+    const bool count = w->profiling;
+    if (count) MLSB_CUDA(cudaMemsetAsync(w->mlsWork, 0, 2 * sizeof(unsigned long long), w->stream));
+    if (w->cfg.shape == MLSB_SHAPE_SPHERE)
+    {
+        if (count) processCornersKernel<MLSB_SHAPE_SPHERE, true><<<grid, kThreads, 0, w->stream>>>(P);
+        else processCornersKernel<MLSB_SHAPE_SPHERE, false><<<grid, kThreads, 0, w->stream>>>(P);
+    }
+    else
+    {
+        if (count) processCornersKernel<MLSB_SHAPE_PLANE, true><<<grid, kThreads, 0, w->stream>>>(P);
+        else processCornersKernel<MLSB_SHAPE_PLANE, false><<<grid, kThreads, 0, w->stream>>>(P);
+    }
+    w->launches++;
+    MLSB_CUDA(cudaGetLastError());
+    return MLSB_OK;
+}
+
+}  // namespace mlsb

@@ -1,0 +1,228 @@
+// Stable LSD radix sort of (u32 key, u32 value) pairs — the role of clogs::Radixsort in the
+// reference (src/splat_tree_cl.cpp:308, src/marching.cpp:572) — written as a one-sweep sort:
+// one histogram kernel for all digits, then one kernel per 8-bit digit that ranks a
+// 4096-element tile in shared memory and obtains its global offsets with a decoupled
+// look-back over the tiles' digit counts.  Per pass every key/value is read once and written
+// once (16 B per pair), against 3 reads + 1 write for a histogram/scan/scatter pipeline.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace mlsb
+{
+
+namespace
+{
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;   // 4096
+constexpr int kRadix = 256;
+constexpr uint32_t kStFlagAggregate = 1u << 30;
+constexpr uint32_t kStFlagPrefix = 2u << 30;
+constexpr uint32_t kStFlagMask = 3u << 30;
+
+__global__ void __launch_bounds__(256) sortHistogramKernel(const uint32_t *__restrict__ keys, uint32_t nHost,
+                                                           const uint32_t *__restrict__ nDev,
+                                                           uint32_t *__restrict__ hist, uint32_t passes,
+                                                           uint32_t bits)
+{
+    const uint32_t n = nDev ? min(*nDev, nHost) : nHost;
+    __shared__ uint32_t sHist[4 * kRadix];
+    for (uint32_t i = threadIdx.x; i < passes * kRadix; i += blockDim.x) sHist[i] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        uint32_t k = keys[i];
+        for (uint32_t p = 0; p < passes; p++)
+        {
+            uint32_t w = min(8u, bits - 8 * p);
+            uint32_t d = (k >> (8 * p)) & ((1u << w) - 1);
+            atomicAdd(&sHist[p * kRadix + d], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < passes * kRadix; i += blockDim.x)
+        if (sHist[i]) atomicAdd(&hist[i], sHist[i]);
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+sortOnesweepKernel(const uint32_t *__restrict__ keysIn, const uint32_t *__restrict__ valsIn,
+                   uint32_t *__restrict__ keysOut, uint32_t *__restrict__ valsOut, uint32_t nHost,
+                   const uint32_t *__restrict__ nDev, uint32_t shift, uint32_t mask, const uint32_t *__restrict__ hist,
+                   volatile uint32_t *status, uint32_t *ticket)
+{
+    __shared__ uint32_t sWarpCnt[kSortThreads / 32][kRadix];
+    __shared__ uint32_t sKeys[kSortTile];
+    __shared__ uint32_t sVals[kSortTile];
+    __shared__ uint32_t sDigitStart[kRadix];
+    __shared__ uint32_t sGlobalBase[kRadix];
+    __shared__ uint32_t sScan[33];
+    __shared__ uint32_t sTile;
+
+    const uint32_t n = nDev ? min(*nDev, nHost) : nHost;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sTile = atomicAdd(ticket, 1u);
+    for (uint32_t i = tid; i < (kSortThreads / 32) * kRadix; i += kSortThreads) (&sWarpCnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = sTile;
+    const uint32_t base = tile * kSortTile;
+    if (base >= n) return;
+
+    // ---- load (warp-striped: ascending index order inside a warp's 512-element span) ----
+    uint32_t key[kSortItems];
+    uint16_t rank[kSortItems];
+    const uint32_t warpBase = base + warp * (32 * kSortItems);
+#pragma unroll
+    for (int k = 0; k < kSortItems; k++)
+    {
+        uint32_t idx = warpBase + k * 32 + lane;
+        key[k] = idx < n ? keysIn[idx] : 0xFFFFFFFFu;
+    }
+
+    // ---- stable rank inside the warp: match lanes with equal digits ----
+#pragma unroll
+    for (int k = 0; k < kSortItems; k++)
+    {
+        uint32_t idx = warpBase + k * 32 + lane;
+        bool valid = idx < n;
+        unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        if (valid)
+        {
+            uint32_t d = (key[k] >> shift) & mask;
+            unsigned peers = __match_any_sync(vmask, d);
+            int leader = __ffs(peers) - 1;
+            uint32_t b = 0;
+            if ((int) lane == leader)
+            {
+                b = sWarpCnt[warp][d];
+                sWarpCnt[warp][d] = b + __popc(peers);
+            }
+            b = __shfl_sync(peers, b, leader);
+            rank[k] = (uint16_t) (b + __popc(peers & ((1u << lane) - 1)));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per-digit totals of the tile (thread d owns digit d) ----
+    const uint32_t d = tid;
+    uint32_t tileCount = 0;
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; w++)
+    {
+        uint32_t t = sWarpCnt[w][d];
+        sWarpCnt[w][d] = tileCount;
+        tileCount += t;
+    }
+
+    // ---- decoupled look-back on this digit's chain ----
+    uint32_t exclusive = 0;
+    volatile uint32_t *st = status + (size_t) tile * kRadix + d;
+    if (tile == 0)
+        *st = kStFlagPrefix | tileCount;
+    else
+    {
+        *st = kStFlagAggregate | tileCount;
+        int t = (int) tile - 1;
+        while (true)
+        {
+            uint32_t v;
+            do { v = status[(size_t) t * kRadix + d]; } while ((v & kStFlagMask) == 0);
+            exclusive += v & ~kStFlagMask;
+            if ((v & kStFlagMask) == kStFlagPrefix) break;
+            t--;
+        }
+        *st = kStFlagPrefix | (exclusive + tileCount);
+    }
+
+    uint32_t digitStart = blockExclusiveScan(tileCount, sScan, (uint32_t *) nullptr);
+    uint32_t histPrefix = blockExclusiveScan(hist[d], sScan, (uint32_t *) nullptr);
+    sDigitStart[d] = digitStart;
+    sGlobalBase[d] = histPrefix + exclusive - digitStart;
+    __syncthreads();
+
+    // ---- scatter into shared memory in sorted order, then stream out coalesced runs ----
+#pragma unroll
+    for (int k = 0; k < kSortItems; k++)
+    {
+        uint32_t idx = warpBase + k * 32 + lane;
+        if (idx < n)
+        {
+            uint32_t dd = (key[k] >> shift) & mask;
+            uint32_t pos = sDigitStart[dd] + sWarpCnt[warp][dd] + rank[k];
+            sKeys[pos] = key[k];
+            sVals[pos] = valsIn[idx];
+        }
+    }
+    __syncthreads();
+    const uint32_t count = min((uint32_t) kSortTile, n - base);
+    for (uint32_t i = tid; i < count; i += kSortThreads)
+    {
+        uint32_t k = sKeys[i];
+        uint32_t dst = sGlobalBase[(k >> shift) & mask] + i;
+        keysOut[dst] = k;
+        valsOut[dst] = sVals[i];
+    }
+}
+
+}  // namespace
+
+int sortScratchAlloc(SortScratch &s, size_t maxItems, uint32_t maxPasses)
+{
+    s.maxItems = maxItems;
+    s.maxPasses = maxPasses;
+    size_t tiles = divUp(maxItems, (size_t) kSortTile) + 1;
+    s.statusWordsPerPass = tiles * kRadix;
+    MLSB_CUDA(cudaMalloc(&s.hist, (size_t) maxPasses * kRadix * sizeof(uint32_t)));
+    MLSB_CUDA(cudaMalloc(&s.status, (size_t) maxPasses * s.statusWordsPerPass * sizeof(uint32_t)));
+    MLSB_CUDA(cudaMalloc(&s.tickets, maxPasses * sizeof(uint32_t)));
+    return MLSB_OK;
+}
+
+void sortScratchFree(SortScratch &s)
+{
+    cudaFree(s.hist);
+    cudaFree(s.status);
+    cudaFree(s.tickets);
+    s = SortScratch();
+}
+
+int radixSortPairs(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n, uint32_t bits,
+                   int *result, const char *statName)
+{
+    return radixSortPairsDeviceCount(w, keys, values, n, nullptr, bits, result, statName);
+}
+
+int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n,
+                              const uint32_t *nDev, uint32_t bits, int *result, const char *statName)
+{
+    *result = 0;
+    if (n == 0 || bits == 0) return MLSB_OK;
+    SortScratch &s = w->sort;
+    uint32_t passes = divUp(bits, 8u);
+    MLSB_REQUIRE(n <= s.maxItems && passes <= s.maxPasses && passes <= 4, MLSB_ERR_LENGTH, "sort scratch too small");
+    ScopedStat stat(w, statName, 1 + passes);
+    uint32_t tiles = divUp(n, (uint32_t) kSortTile);
+    MLSB_CUDA(cudaMemsetAsync(s.hist, 0, (size_t) passes * kRadix * sizeof(uint32_t), w->stream));
+    MLSB_CUDA(cudaMemsetAsync(s.tickets, 0, passes * sizeof(uint32_t), w->stream));
+    for (uint32_t p = 0; p < passes; p++)
+        MLSB_CUDA(cudaMemsetAsync(s.status + p * s.statusWordsPerPass, 0, (size_t) tiles * kRadix * sizeof(uint32_t), w->stream));
+    uint32_t histBlocks = min(divUp(n, 256u * 8u), 148u * 8u);
+    sortHistogramKernel<<<histBlocks, 256, 0, w->stream>>>(keys[0], n, nDev, s.hist, passes, bits);
+    int cur = 0;
+    for (uint32_t p = 0; p < passes; p++)
+    {
+        uint32_t wbits = bits - 8 * p < 8 ? bits - 8 * p : 8;
+        sortOnesweepKernel<<<tiles, kSortThreads, 0, w->stream>>>(
+            keys[cur], values[cur], keys[cur ^ 1], values[cur ^ 1], n, nDev, 8 * p, (1u << wbits) - 1,
+            s.hist + p * kRadix, s.status + p * s.statusWordsPerPass, s.tickets + p);
+        cur ^= 1;
+    }
+    w->launches += 1 + passes;
+    MLSB_CUDA(cudaGetLastError());
+    *result = cur;
+    return MLSB_OK;
+}
+
+}  // namespace mlsb

@@ -1,0 +1,162 @@
+"""Host-side input conditioning and binning that sits just in front of the device path.
+
+Mirrors what the reference does between a PLY vertex and the splat buffer of a bin:
+FastPly::Reader::decode (src/fast_ply.cpp:334-350), the bounding grid of
+SplatSet::FastBlobSet::getBoundingGrid (src/splat_set_impl.h:771-810), and
+BucketLoader::operator() (src/bucket_loader.cpp:56-128).  The spatial partition here is a
+plain recursive halving of the grid (the reference's histogram-driven Bucket::bucket,
+src/bucket_impl.h:439-561, is out of scope for this round); bins have the same contract:
+at most ``max_cells`` cells per side, at most ``max_splats`` splats, and every splat whose
+ball reaches the bin is included.
+"""
+import numpy as np
+
+from .capi import SPLAT_DTYPE
+
+
+def condition_splats(splats, smooth=4.0, max_radius=np.inf):
+    """radius <- min(radius, maxRadius) * smooth; quality <- 1/radius^2 (double division)."""
+    r = np.minimum(splats["radius"], np.float32(max_radius)) * np.float32(smooth)
+    splats["radius"] = r
+    splats["quality"] = (1.0 / (r * r).astype(np.float64)).astype(np.float32)
+    return splats
+
+
+def bounding_grid(splats, spacing, bucket_size=63):
+    """Vertex-index extents [lo, hi] per axis of the full grid (reference point = origin)."""
+    pos = splats["position"].astype(np.float64)
+    r = splats["radius"].astype(np.float64)[:, None]
+    lo = np.floor((pos - r).min(axis=0) / spacing).astype(np.int64)
+    hi = np.ceil((pos + r).max(axis=0) / spacing).astype(np.int64)
+    lo = (lo // bucket_size) * bucket_size   # rounded down to a multiple of the blob bucket
+    return lo, hi
+
+
+def world_to_grid(splats, spacing, lo):
+    """Grid::worldToVertex + radius rescale, in float32 exactly as src/grid.cpp:99-106."""
+    inv = np.float32(1.0) / np.float32(spacing)
+    out = splats.copy()
+    out["position"] = splats["position"] * inv - lo.astype(np.float32)[None, :]
+    out["radius"] = splats["radius"] * inv
+    return out
+
+
+def make_bins(grid_splats, num_cells, max_cells=255, max_splats=1 << 21):
+    """Partition cells [0, num_cells) into bins.  Returns a list of dicts with
+    offset (int32[3]), size = corners per axis (uint32[3]) and ids (indices into grid_splats,
+    ascending)."""
+    pos = grid_splats["position"]
+    r = grid_splats["radius"]
+    lo_all = pos - r[:, None]
+    hi_all = pos + r[:, None]
+    bins = []
+
+    def recurse(lo, hi, ids):
+        # splats whose ball reaches the closed corner box [lo, hi]
+        m = np.ones(len(ids), bool)
+        for a in range(3):
+            m &= (hi_all[ids, a] >= lo[a]) & (lo_all[ids, a] <= hi[a])
+        ids = ids[m]
+        if len(ids) == 0:
+            return
+        ext = hi - lo
+        if ext.max() <= max_cells and len(ids) <= max_splats:
+            bins.append(dict(offset=lo.astype(np.int32), size=(ext + 1).astype(np.uint32), ids=ids))
+            return
+        a = int(np.argmax(ext))
+        if ext[a] <= 1:
+            raise ValueError("too many splats over a single cell (DensityError in the reference)")
+        mid = lo[a] + ext[a] // 2
+        hi0 = hi.copy()
+        hi0[a] = mid
+        lo1 = lo.copy()
+        lo1[a] = mid
+        recurse(lo, hi0, ids)
+        recurse(lo1, hi, ids)
+
+    # first cut the grid into max_cells-sized blocks so that bins are as cubic as possible
+    n = np.asarray(num_cells, np.int64)
+    counts = -(-n // max_cells)
+    all_ids = np.arange(len(grid_splats))
+    for bz in range(counts[2]):
+        for by in range(counts[1]):
+            for bx in range(counts[0]):
+                b = np.array([bx, by, bz])
+                lo = b * n // counts
+                hi = (b + 1) * n // counts
+                recurse(lo, hi, all_ids)
+    return bins
+
+
+# ---- synthetic inputs ---------------------------------------------------
+
+def morton_order(pos, bits=10):
+    """Indices that sort points along a Morton curve of their quantised position (the manual's
+    coherence advice, doc/mlsgpu-user-manual.xml:211-216)."""
+    p = pos - pos.min(axis=0)
+    p = (p / (p.max() + 1e-30) * ((1 << bits) - 1)).astype(np.uint64)
+    code = np.zeros(len(pos), np.uint64)
+    for b in range(bits):
+        for a in range(3):
+            code |= ((p[:, a] >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b + a)
+    return np.argsort(code, kind="stable")
+
+
+def sphere_splats(n, seed=1, radius=0.005, noise=0.002, R=1.0):
+    """C1: noisy unit sphere, uniform area sampling, exact radial normals, constant radius."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    z = rng.uniform(-1.0, 1.0, n)
+    t = rng.uniform(-np.pi, np.pi, n)
+    xy = np.sqrt(1.0 - z * z)
+    nrm = np.stack([np.cos(t) * xy, np.sin(t) * xy, z], axis=1)
+    rad = R + rng.normal(0.0, noise, n)
+    out = np.zeros(n, SPLAT_DTYPE)
+    out["position"] = (nrm * rad[:, None]).astype(np.float32)
+    out["normal"] = nrm.astype(np.float32)
+    out["radius"] = np.float32(radius)
+    out = out[morton_order(out["position"])]
+    return np.ascontiguousarray(out)
+
+
+def torus_splats(n, seed=2, R=1.0, r=0.4, bump=0.02, freq=20.0):
+    """C2: bumpy torus with analytic normals and per-splat radii = local spacing x U(1,2)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    # area-uniform sampling of the torus: density in v proportional to (R + r cos v)
+    u = rng.uniform(0.0, 2 * np.pi, n)
+    v = rng.uniform(0.0, 2 * np.pi, int(n * 1.6) + 16)
+    keep = rng.uniform(0.0, 1.0, len(v)) < (R + r * np.cos(v)) / (R + r)
+    v = v[keep][:n]
+    if len(v) < n:
+        v = np.concatenate([v, rng.uniform(0.0, 2 * np.pi, n - len(v))])
+    rr = r + bump * np.sin(freq * u) * np.sin(freq * v)
+
+    def point(u, v, rr):
+        return np.stack([(R + rr * np.cos(v)) * np.cos(u), (R + rr * np.cos(v)) * np.sin(u), rr * np.sin(v)], axis=1)
+
+    p = point(u, v, rr)
+    # analytic normal = dP/du x dP/dv
+    drr_du = bump * freq * np.cos(freq * u) * np.sin(freq * v)
+    drr_dv = bump * freq * np.sin(freq * u) * np.cos(freq * v)
+    cu, su, cv, sv = np.cos(u), np.sin(u), np.cos(v), np.sin(v)
+    dpu = np.stack([-(R + rr * cv) * su + drr_du * cv * cu, (R + rr * cv) * cu + drr_du * cv * su, drr_du * sv], axis=1)
+    dpv = np.stack([(drr_dv * cv - rr * sv) * cu, (drr_dv * cv - rr * sv) * su, drr_dv * sv + rr * cv], axis=1)
+    nrm = np.cross(dpu, dpv)
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    area = 4 * np.pi * np.pi * R * r
+    spacing = np.sqrt(area / n)
+    out = np.zeros(n, SPLAT_DTYPE)
+    out["position"] = p.astype(np.float32)
+    out["normal"] = nrm.astype(np.float32)
+    out["radius"] = (spacing * rng.uniform(1.0, 2.0, n)).astype(np.float32)
+    out = out[morton_order(out["position"])]
+    return np.ascontiguousarray(out)
+
+
+def prepare(splats, fit_grid, smooth=4.0, max_cells=255, max_splats=1 << 21, bucket_size=63):
+    """World-space splats -> (grid_splats, bins, lo, spacing): everything the reference does on
+    the host before DeviceWorkerGroup sees a bin."""
+    s = condition_splats(splats.copy(), smooth)
+    lo, hi = bounding_grid(s, fit_grid, bucket_size)
+    g = world_to_grid(s, fit_grid, lo)
+    bins = make_bins(g, hi - lo, max_cells, max_splats)
+    return g, bins, lo, np.float32(fit_grid)

@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""Benchmark of the per-bin reconstruction hot path (octree build -> MLS -> marching + weld).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): a 10M-splat synthetic bumpy torus with
+per-splat normals and radii, --fit-grid 0.002, sphere fit, CLI defaults (smooth 4, levels 6,
+subsampling 3, bins of <=255 cells).  One "step" = one pass of the hot path over all bins.
+Under torchrun every rank meshes its own torus (seed 2 + rank): weak scaling, no collective on
+the data path; rank 0 prints one JSON line.
+
+value   = splats/s with the bins' splats resident in HBM at the start of the timed region
+e2e     = splats/s through the C ABI from pinned HOST buffers (H2D of every bin and D2H of every
+          mesh inside the timed region)
+roofline= processCorners against the FP32 pipe: (7 T + 16 H) pipe instructions over
+          the kernel's CUDA-event time, against a measured dependent-free FFMA stream
+cpu_baseline = the CPU oracle (port of the reference kernels) on a bounded sample of the bins
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FIT_GRID = 0.002
+SMOOTH = 4.0
+MLS_STAT = "kernel.mls.processCorners.time"
+OCTREE_STATS = ["kernel.octree.writeEntries.time", "kernel.octree.sort.time", "kernel.octree.fill.time",
+                "kernel.octree.countCommands.time", "kernel.octree.scan.time", "kernel.octree.writeSplatIds.time",
+                "kernel.octree.writeStart.time"]
+MARCHING_STATS = ["kernel.marching.zero.time", "kernel.marching.generateElements.time",
+                  "kernel.marching.sortVertices.time", "kernel.marching.compactVertices.time",
+                  "kernel.marching.reindex.time", "kernel.marching.readback.time"]
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_workload(num_splats, seed):
+    from mlsgpu_b200 import host
+    t0 = time.time()
+    s = host.torus_splats(num_splats, seed=seed)
+    g, bins, lo, spacing = host.prepare(s, FIT_GRID, smooth=SMOOTH)
+    # concatenate the bins' splats: this is what the loader hands to the copy stage
+    firsts, total = [], 0
+    for b in bins:
+        firsts.append(total)
+        total += len(b["ids"])
+    packed = np.empty(total, g.dtype)
+    for b, f in zip(bins, firsts):
+        packed[f:f + len(b["ids"])] = g[b["ids"]]
+        b["first"] = f
+        b["n"] = len(b["ids"])
+    log("workload: %d splats, %d bins, %d splat instances, prepared in %.1fs" % (num_splats, len(bins), total, time.time() - t0))
+    return dict(splats=packed, bins=bins, lo=lo, spacing=spacing, num_splats=num_splats)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = self.proc.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower() == "active":
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class Runner:
+    """`threads` workers on one GPU (the reference's --device-threads), bins handed out
+    round-robin; each worker thread uploads its bin and runs mlsb_worker_process_bin."""
+
+    def __init__(self, wl, device, threads):
+        import mlsgpu_b200 as m
+        from mlsgpu_b200.capi import DeviceBuffer, PinnedBuffer, MESH_SINK
+        self.m = m
+        self.wl = wl
+        self.bins = wl["bins"]
+        total = len(wl["splats"])
+        self.max_bin = max(b["n"] for b in self.bins)
+        self.workers = [m.Worker(device=device, max_splats=self.max_bin, max_cells=255, mesh_bytes=256 << 20)
+                        for _ in range(threads)]
+        bias = wl["lo"].astype(np.float32) * wl["spacing"]
+        for w in self.workers:
+            w.set_scale_bias(float(wl["spacing"]), bias)
+        self.pinned = PinnedBuffer(m.SPLAT_DTYPE, total)
+        self.pinned.array[:] = wl["splats"]
+        self.resident = DeviceBuffer.from_array(wl["splats"])
+        self.mesh_bytes = 0
+        self.mesh_vertices = 0
+        self.mesh_triangles = 0
+        self.lock = threading.Lock()
+
+        def sink(sizes_p, blob, user):
+            s = sizes_p.contents
+            with self.lock:
+                self.mesh_vertices += int(s.numVertices)
+                self.mesh_triangles += int(s.numTriangles)
+                self.mesh_bytes += 12 * int(s.numVertices) + 12 * int(s.numTriangles) + 8 * int(s.numVertices - s.numInternalVertices)
+        self.sink = MESH_SINK(sink)
+
+    def _work(self, wi, from_host):
+        import ctypes as C
+        from mlsgpu_b200.capi import lib, _check
+        w = self.workers[wi]
+        L = lib()
+        for b in self.bins[wi::len(self.workers)]:
+            if from_host:
+                src = self.pinned.ptr.value + 32 * b["first"]
+            else:
+                src = self.resident.ptr.value + 32 * b["first"]
+            _check(L.mlsb_splats_upload_async(w.h, src, 0, b["n"]))
+            _check(L.mlsb_worker_process_bin(w.h, 0, b["n"], b["size"].ctypes.data, b["offset"].ctypes.data, self.sink, None))
+
+    def step(self, from_host):
+        if len(self.workers) == 1:
+            self._work(0, from_host)
+            return
+        ts = [threading.Thread(target=self._work, args=(i, from_host)) for i in range(len(self.workers))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    def sync(self):
+        for w in self.workers:
+            w.synchronize()
+
+    def stat_sum(self, names):
+        tot, cnt = 0.0, 0
+        for w in self.workers:
+            for n in names:
+                s, c = w.statistic(n)
+                tot += s
+                cnt += c
+        return tot, cnt
+
+    def close(self):
+        for w in self.workers:
+            w.close()
+        self.resident.free()
+        self.pinned.free()
+
+
+def oracle_bin(orc, wl, b):
+    """The reference path for one bin on the CPU oracle: build -> processCorners -> marching."""
+    s = wl["splats"][b["first"]:b["first"] + b["n"]].copy()
+    tree = orc.octree_build(s, 0, len(s), b["offset"], 3, 6)
+    size = [int(v) for v in b["size"]]
+    pitch, zs, depth = (-(-v // 8) * 8 for v in size)
+    img = np.zeros((zs * depth, pitch), np.float32)
+    orc.mls_process_corners(img, s, tree["commands"], tree["start"], 9, b["offset"], size[0], size[1], zs, 0, 0,
+                            size[2] - 1, orc.boundary_factor(1.0), 0)
+    mesh = orc.marching_generate(img, size[0], size[1], zs, 0, 0, size[2] - 1, [int(v) for v in b["offset"]],
+                                 vcap=4 << 20, icap=24 << 20)
+    return len(mesh["vertices"])
+
+
+def cpu_baseline(wl, budget_s=15.0, max_bins=None):
+    from oracle.oracle import Oracle
+    orc = Oracle()
+    done, splats, t0 = 0, 0, time.time()
+    order = sorted(range(len(wl["bins"])), key=lambda i: -wl["bins"][i]["n"])   # typical (large) bins first
+    for i in order:
+        b = wl["bins"][i]
+        oracle_bin(orc, wl, b)
+        done += 1
+        splats += b["n"]
+        if time.time() - t0 > budget_s or (max_bins and done >= max_bins):
+            break
+    dt = time.time() - t0
+    return splats / dt, done, splats, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU port of the reference kernels (the reference itself cannot be
+    built here: Boost/clogs/OpenCL/cppunit absent), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    wl = make_workload(args.splats, 2)
+    cores = os.cpu_count()
+    rate, _, _, dt1 = cpu_baseline(wl, budget_s=0.0, max_bins=1)     # calibration: one bin
+    per_step = max(1, int(120.0 / max(dt1, 1e-3) / (args.steps + args.warmup)))
+    per_step = min(per_step, len(wl["bins"]))
+    times, splats = [], 0
+    for it in range(args.warmup + args.steps):
+        r, done, ns, dt = cpu_baseline(wl, budget_s=1e9, max_bins=per_step)
+        if it >= args.warmup:
+            times.append(dt)
+            splats = ns
+    ms = 1e3 * float(np.mean(times))
+    value = splats / (ms * 1e-3) / 1e6
+    line = {"impl": "reference", "metric": "Msplats/s", "value": value, "unit": "Msplats/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(wl, args),
+            "cpu_baseline": {"value": value, "unit": "Msplats/s", "cores": cores, "kind": "port",
+                             "sample": "%d largest bins (%d splat instances) per step; MLS stage OpenMP over %d threads, "
+                                       "octree and marching stages single-threaded" % (per_step, splats, cores)},
+            "e2e": {"value": value, "unit": "Msplats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl, args):
+    return {"workload": "C2: %d-splat synthetic bumpy torus, fit-grid %.3g, sphere fit, smooth %.0f, levels 6, "
+                        "subsampling 3, %d bins <=255 cells" % (wl["num_splats"], FIT_GRID, SMOOTH, len(wl["bins"])),
+            "splats": wl["num_splats"], "bins": len(wl["bins"]), "splat_instances": int(len(wl["splats"])),
+            "device_threads": args.threads,
+            "l2": "inputs larger than L2: %.0f MB of splats and a 64 MiB field per bin cycle through a 126 MB L2"
+                  % (len(wl["splats"]) * 32 / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--splats", type=int, default=10_000_000)
+    ap.add_argument("--threads", type=int, default=2, help="workers per GPU (--device-threads)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: mlsgpu_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import mlsgpu_b200 as m
+    wl = make_workload(args.splats, 2 + rank)
+    peak_inst = m.measure_fp32_peak(local)
+    runner = Runner(wl, local, args.threads)
+
+    def barrier():
+        runner.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(from_host, steps, profile):
+        for w in runner.workers:
+            w.set_profiling(1 if profile else 0)
+            w.reset_statistics()
+        runner.mesh_bytes = 0
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = sum(w.launch_count for w in runner.workers)
+        e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            runner.step(from_host)
+        runner.sync()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        launches = sum(w.launch_count for w in runner.workers) - l0
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, wall * 1e3, launches
+
+    # ---- work model (untimed): T pair tests and H hits of one step ----
+    for w in runner.workers:
+        w.set_work_counting(True)
+        w.reset_statistics()
+    runner.step(False)
+    runner.sync()
+    T = sum(w.mls_work()[0] for w in runner.workers)
+    H = sum(w.mls_work()[1] for w in runner.workers)
+    for w in runner.workers:
+        w.set_work_counting(False)
+    corners = sum(int(np.prod([-(-int(v) // 8) * 8 for v in b["size"]])) for b in wl["bins"])
+
+    # ---- warm-up, then the two timed regions ----
+    for _ in range(args.warmup):
+        runner.step(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, wall_dev, launches = timed(False, args.steps, profile=True)
+    mls_s, mls_n = runner.stat_sum([MLS_STAT])
+    clocks = sampler.stop()
+    runner.step(True)   # warm the host path
+    ms_e2e, wall_e2e, _ = timed(True, args.steps, profile=False)
+    d2h = runner.mesh_bytes // args.steps
+
+    # ---- per-stage breakdown (untimed pass with every kernel timed) ----
+    for w in runner.workers:
+        w.set_profiling(2)
+        w.reset_statistics()
+    runner.step(False)
+    runner.sync()
+    oct_s, _ = runner.stat_sum(OCTREE_STATS)
+    mar_s, _ = runner.stat_sum(MARCHING_STATS)
+    mls2_s, _ = runner.stat_sum([MLS_STAT])
+    for w in runner.workers:
+        w.set_profiling(0)
+
+    total_splats = args.splats * world
+    value = total_splats * args.steps / (ms_dev * 1e-3) / 1e6
+    e2e = total_splats * args.steps / (ms_e2e * 1e-3) / 1e6
+    inst = 7.0 * T + 16.0 * H                        # FP32 pipe lane-instructions per step
+    mls_per_step = mls_s / args.steps
+    achieved = 2.0 * inst / mls_per_step / 1e12      # TFLOP/s at 2 flop per lane-instruction
+    peak = 2.0 * peak_inst / 1e12
+    inst_bytes = len(wl["splats"])
+    line = {
+        "metric": "Msplats/s", "value": value, "unit": "Msplats/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl, args),
+        "e2e": {"value": e2e, "unit": "Msplats/s", "h2d_bytes_per_step": int(len(wl["splats"]) * 32),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "mls_corners_per_s": corners * args.steps / mls_s if mls_s > 0 else None,
+        "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "processCornersKernel",
+                     "model": "7*T + 16*H FP32 pipe instructions per step (SURVEY 8d), 2 flop each",
+                     "pair_tests": int(T), "hits": int(H), "kernel_ms_per_step": 1e3 * mls_per_step,
+                     "launches_per_step": mls_n // args.steps,
+                     "peak_source": "measured here: dependent-free FFMA stream, %.2f T lane-inst/s "
+                                    "(MEASURED_PEAKS.json has no FP32 figure)" % (peak_inst / 1e12)},
+        "stages_ms_per_step": {"octree": 1e3 * oct_s, "mls": 1e3 * mls2_s, "marching": 1e3 * mar_s,
+                               "wall": wall_dev / args.steps},
+        "rooflines_hbm": {
+            "octree": {"model_bytes": 472 * inst_bytes, "achieved_gbs": 472 * inst_bytes / oct_s / 1e9 if oct_s else None,
+                       "peak_gbs": 6541.1, "note": "472 B/splat model of SURVEY 8d, measured copy peak"}},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, done, ns, dt = cpu_baseline(wl)
+        line["cpu_baseline"] = {"value": rate / 1e6, "unit": "Msplats/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": "%d largest bins (%d splat instances) in %.1f s; MLS stage OpenMP over all cores, "
+                                          "octree and marching stages single-threaded" % (done, ns, dt)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    runner.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

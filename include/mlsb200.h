@@ -180,15 +180,21 @@ MLSB_API int mlsb_worker_process_bin(mlsb_worker *w, uint32_t firstSplat, uint32
 
 /* ---- statistics (--statistics-cl, src/statistics_cl.cpp) -------------------------------- */
 
-/* Enables CUDA-event timing of every kernel under the reference's statistic names
- * (kernel.octree.*.time, kernel.mls.processCorners.time, kernel.marching.*.time). */
-MLSB_API int mlsb_worker_set_profiling(mlsb_worker *w, int enabled);
+/* CUDA-event timing under the reference's statistic names (kernel.octree.*.time,
+ * kernel.mls.processCorners.time, kernel.marching.*.time): level 0 off, 1 processCorners
+ * only, 2 every kernel. */
+MLSB_API int mlsb_worker_set_profiling(mlsb_worker *w, int level);
 /* Sum (seconds) and count of a named statistic since the last reset. */
 MLSB_API int mlsb_worker_get_statistic(mlsb_worker *w, const char *name, double *sum, uint64_t *count);
 MLSB_API int mlsb_worker_reset_statistics(mlsb_worker *w);
-/* Work counters of the last MLS launch when profiling is on: pair tests T and hits H of the
- * SURVEY 8(d) work model, counted on the device. */
+/* Work model of SURVEY 8(d): while counting is enabled every MLS launch also accumulates its
+ * pair tests T and hits H on the device (slower kernel variant: enable only for an untimed
+ * pass).  Counters are cleared by mlsb_worker_reset_statistics. */
+MLSB_API int mlsb_worker_set_work_counting(mlsb_worker *w, int enabled);
 MLSB_API int mlsb_worker_get_mls_work(mlsb_worker *w, uint64_t *pairTests, uint64_t *hits);
+/* FP32 pipe peak of a device in lane-instructions per second, measured with a dependent-free
+ * FFMA stream (the roofline denominator of processCorners). */
+MLSB_API int mlsb_measure_fp32_peak(int device, double *laneInstPerSecond);
 /* Total kernels launched by this worker since creation. */
 MLSB_API uint64_t mlsb_worker_launch_count(mlsb_worker *w);
 

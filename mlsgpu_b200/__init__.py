@@ -8,7 +8,7 @@ There is no CPU fallback: importing works anywhere, but every compute call needs
 library and a CUDA device and raises :class:`MlsbError` otherwise.
 """
 from .capi import (MlsbError, SPLAT_DTYPE, Worker, WorkerConfig, device_count, lib, library_path,
-                   marching_tables, version)
+                   marching_tables, measure_fp32_peak, version)
 
 __all__ = ["MlsbError", "SPLAT_DTYPE", "Worker", "WorkerConfig", "device_count", "lib", "library_path",
-           "marching_tables", "version"]
+           "marching_tables", "measure_fp32_peak", "version"]

@@ -72,6 +72,8 @@ API = {
     "mlsb_worker_set_profiling": (C.c_int, [_P, C.c_int]),
     "mlsb_worker_get_statistic": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "mlsb_worker_reset_statistics": (C.c_int, [_P]),
+    "mlsb_worker_set_work_counting": (C.c_int, [_P, C.c_int]),
+    "mlsb_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "mlsb_worker_get_mls_work": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "mlsb_worker_launch_count": (C.c_uint64, [_P]),
     "mlsb_device_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
@@ -117,6 +119,13 @@ def device_count():
     n = C.c_int(0)
     _check(lib().mlsb_device_count(C.byref(n)))
     return n.value
+
+
+def measure_fp32_peak(device=0):
+    """FP32 lane-instructions per second of a dependent-free FFMA stream."""
+    v = C.c_double()
+    _check(lib().mlsb_measure_fp32_peak(device, C.byref(v)))
+    return v.value
 
 
 def marching_tables():
@@ -236,6 +245,10 @@ class Worker:
         self._keep.append(splats)
         _check(lib().mlsb_splats_upload_async(self.h, splats.ctypes.data, dst_first, len(splats)))
 
+    def upload_splats_from_device(self, src, src_first, n, dst_first=0):
+        """Device-to-device refill of the splat buffer (benchmarks with HBM-resident inputs)."""
+        _check(lib().mlsb_splats_upload_async(self.h, src.ptr.value + 32 * src_first, dst_first, n))
+
     def download_splats(self, first, n):
         self.synchronize()
         ptr = _P()
@@ -341,8 +354,9 @@ class Worker:
         return blocks
 
     # ---- statistics ------------------------------------------------------------------------
-    def set_profiling(self, enabled):
-        _check(lib().mlsb_worker_set_profiling(self.h, int(enabled)))
+    def set_profiling(self, level):
+        """0 off, 1 processCorners only, 2 (or True) every kernel."""
+        _check(lib().mlsb_worker_set_profiling(self.h, 2 if level is True else int(level)))
 
     def statistic(self, name):
         s, c = C.c_double(), C.c_uint64()
@@ -351,6 +365,9 @@ class Worker:
 
     def reset_statistics(self):
         _check(lib().mlsb_worker_reset_statistics(self.h))
+
+    def set_work_counting(self, enabled):
+        _check(lib().mlsb_worker_set_work_counting(self.h, int(enabled)))
 
     def mls_work(self):
         t, h = C.c_uint64(), C.c_uint64()

@@ -43,9 +43,9 @@ static cudaEvent_t takeEvent(mlsb_worker *w)
     return e;
 }
 
-ScopedStat::ScopedStat(mlsb_worker *w, const char *name, int) : w(w), idx(-1), begin(nullptr)
+ScopedStat::ScopedStat(mlsb_worker *w, const char *name, int, int level) : w(w), idx(-1), begin(nullptr)
 {
-    if (!w->profiling) return;
+    if (w->profiling < level) return;
     idx = statId(w, name);
     begin = takeEvent(w);
     cudaEventRecord(begin, w->stream);
@@ -234,7 +234,7 @@ int mlsb_splats_upload_async(mlsb_worker *w, const mlsb_splat *host, uint32_t ds
     MLSB_REQUIRE((uint64_t) dstFirst + n <= w->cfg.maxSplats, MLSB_ERR_LENGTH, "more splats than the worker's buffer holds");
     MLSB_CUDA(cudaSetDevice(w->device));
     if (n)
-        MLSB_CUDA(cudaMemcpyAsync(w->splats + dstFirst, host, (size_t) n * sizeof(mlsb_splat), cudaMemcpyHostToDevice,
+        MLSB_CUDA(cudaMemcpyAsync(w->splats + dstFirst, host, (size_t) n * sizeof(mlsb_splat), cudaMemcpyDefault,
                                   w->copyStream));
     MLSB_CUDA(cudaEventRecord(w->copyEvent, w->copyStream));
     w->copyPending = true;
@@ -377,7 +377,7 @@ int mlsb_worker_set_profiling(mlsb_worker *w, int enabled)
     MLSB_REQUIRE(w != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null worker");
     MLSB_CUDA(cudaStreamSynchronize(w->stream));
     collectStats(w);
-    w->profiling = enabled != 0;
+    w->profiling = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
     return MLSB_OK;
 }
 
@@ -405,6 +405,14 @@ int mlsb_worker_reset_statistics(mlsb_worker *w)
     MLSB_CUDA(cudaStreamSynchronize(w->stream));
     collectStats(w);
     for (StatAccum &a : w->stats) a = StatAccum();
+    MLSB_CUDA(cudaMemset(w->mlsWork, 0, 2 * sizeof(unsigned long long)));
+    return MLSB_OK;
+}
+
+int mlsb_worker_set_work_counting(mlsb_worker *w, int enabled)
+{
+    MLSB_REQUIRE(w != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null worker");
+    w->countWork = enabled != 0;
     return MLSB_OK;
 }
 
@@ -417,6 +425,13 @@ int mlsb_worker_get_mls_work(mlsb_worker *w, uint64_t *pairTests, uint64_t *hits
     if (pairTests) *pairTests = h[0];
     if (hits) *hits = h[1];
     return MLSB_OK;
+}
+
+int mlsb_measure_fp32_peak(int device, double *laneInstPerSecond)
+{
+    MLSB_REQUIRE(laneInstPerSecond != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
+    MLSB_CUDA(cudaSetDevice(device));
+    return measureFp32Peak(laneInstPerSecond, nullptr);
 }
 
 uint64_t mlsb_worker_launch_count(mlsb_worker *w) { return w ? w->launches : 0; }

@@ -134,7 +134,8 @@ struct mlsb_worker
     uint8_t *tables = nullptr;          // device copy of the marching LUTs
 
     // ---- statistics ----
-    bool profiling = false;
+    int profiling = 0;        // 0 off, 1 processCorners only, 2 every kernel
+    bool countWork = false;   // MLS kernels also count pair tests / hits (slower; never timed)
     std::vector<std::string> statNames;
     std::map<std::string, int> statIndex;
     std::vector<mlsb::StatAccum> stats;
@@ -151,7 +152,7 @@ namespace mlsb
 class ScopedStat
 {
 public:
-    ScopedStat(mlsb_worker *w, const char *name, int kernels = 1);
+    ScopedStat(mlsb_worker *w, const char *name, int kernels = 1, int level = 2);
     ~ScopedStat();
 
 private:
@@ -181,6 +182,7 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
                 uint32_t subsamplingShift);
 
 // mls.cu
+int measureFp32Peak(double *laneInstPerSecond, double *seconds);
 int mlsAlloc(mlsb_worker *w);
 void mlsFree(mlsb_worker *w);
 int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &sw);

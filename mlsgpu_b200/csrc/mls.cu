@@ -263,7 +263,62 @@ __global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
     for (int j = 0; j < 4; j++) dst[2 * j] = out[j];
 }
 
+// Dependent-free FFMA stream: 8 independent accumulators per thread, every issue slot an FFMA.
+__global__ void __launch_bounds__(256) fp32PeakKernel(float *out, float a, float b, int iters)
+{
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = a + (float) (threadIdx.x + i);
+    for (int it = 0; it < iters; it++)
+    {
+#pragma unroll
+        for (int r = 0; r < 16; r++)
+        {
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = __fmaf_rn(x[i], a, b);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i];
+    if (s == 12345.678f) out[0] = s;   // never true; keeps the loop alive
+}
+
 }  // namespace
+
+// FP32 pipe peak of the current device in lane-instructions per second (one FFMA = one
+// lane-instruction = 2 flop): the roofline denominator for processCorners, which
+// MEASURED_PEAKS.json does not contain.
+int measureFp32Peak(double *laneInstPerSecond, double *seconds)
+{
+    float *out = nullptr;
+    MLSB_CUDA(cudaMalloc(&out, sizeof(float)));
+    cudaEvent_t e0, e1;
+    MLSB_CUDA(cudaEventCreate(&e0));
+    MLSB_CUDA(cudaEventCreate(&e1));
+    int sms = 0;
+    MLSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    const int blocks = sms * 8, iters = 4096;
+    double best = 0.0, bestT = 0.0;
+    for (int rep = 0; rep < 6; rep++)
+    {
+        MLSB_CUDA(cudaEventRecord(e0, 0));
+        fp32PeakKernel<<<blocks, 256>>>(out, 0.999f, 0.001f, iters);
+        MLSB_CUDA(cudaEventRecord(e1, 0));
+        MLSB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        MLSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double inst = (double) blocks * 256 * iters * 16 * 8;
+        double rate = inst / (ms * 1e-3);
+        if (rep > 0 && rate > best) { best = rate; bestT = ms * 1e-3; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *laneInstPerSecond = best;
+    if (seconds) *seconds = bestT;
+    return MLSB_OK;
+}
 
 int mlsAlloc(mlsb_worker *w)
 {
@@ -300,9 +355,8 @@ int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &
     P.boundaryFactor = w->boundaryFactor;
     P.work = w->mlsWork;
     dim3 grid(width / kMlsWgs, height / kMlsWgs, divUp(sw.zLast - sw.zFirst + 1, (uint32_t) kMlsWgs));
-    ScopedStat st(w, "kernel.mls.processCorners.time");
-    const bool count = w->profiling;
-    if (count) MLSB_CUDA(cudaMemsetAsync(w->mlsWork, 0, 2 * sizeof(unsigned long long), w->stream));
+    ScopedStat st(w, "kernel.mls.processCorners.time", 1, 1);
+    const bool count = w->countWork;
     if (w->cfg.shape == MLSB_SHAPE_SPHERE)
     {
         if (count) processCornersKernel<MLSB_SHAPE_SPHERE, true><<<grid, kThreads, 0, w->stream>>>(P);

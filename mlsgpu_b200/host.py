@@ -74,17 +74,33 @@ def make_bins(grid_splats, num_cells, max_cells=255, max_splats=1 << 21):
         recurse(lo, hi0, ids)
         recurse(lo1, hi, ids)
 
-    # first cut the grid into max_cells-sized blocks so that bins are as cubic as possible
+    # first cut the grid into max_cells-sized blocks so that bins are as cubic as possible;
+    # candidate (splat, block) pairs come from each splat's bounding box in block units
     n = np.asarray(num_cells, np.int64)
     counts = -(-n // max_cells)
-    all_ids = np.arange(len(grid_splats))
-    for bz in range(counts[2]):
-        for by in range(counts[1]):
-            for bx in range(counts[0]):
-                b = np.array([bx, by, bz])
-                lo = b * n // counts
-                hi = (b + 1) * n // counts
-                recurse(lo, hi, all_ids)
+    edges = [np.arange(counts[a] + 1) * n[a] // counts[a] for a in range(3)]
+    first = [np.clip(np.searchsorted(edges[a], lo_all[:, a], side="left") - 1, 0, counts[a] - 1) for a in range(3)]
+    last = [np.clip(np.searchsorted(edges[a], hi_all[:, a], side="right") - 1, 0, counts[a] - 1) for a in range(3)]
+    span = [last[a] - first[a] + 1 for a in range(3)]
+    per = span[0] * span[1] * span[2]
+    sid = np.repeat(np.arange(len(grid_splats)), per)
+    k = np.arange(len(sid)) - np.repeat(np.cumsum(per) - per, per)
+    sx, sy = span[0][sid], span[1][sid]
+    bx = first[0][sid] + k % sx
+    by = first[1][sid] + (k // sx) % sy
+    bz = first[2][sid] + k // (sx * sy)
+    block = (bz * counts[1] + by) * counts[0] + bx
+    order = np.argsort(block, kind="stable")
+    block, sid = block[order], sid[order]
+    bounds = np.searchsorted(block, np.arange(counts.prod() + 1))
+    for bi in range(int(counts.prod())):
+        ids = sid[bounds[bi]:bounds[bi + 1]]
+        if len(ids) == 0:
+            continue
+        b = np.array([bi % counts[0], (bi // counts[0]) % counts[1], bi // (counts[0] * counts[1])])
+        lo = np.array([edges[a][b[a]] for a in range(3)])
+        hi = np.array([edges[a][b[a] + 1] for a in range(3)])
+        recurse(lo, hi, ids)
     return bins
 
 

@@ -63,6 +63,7 @@ def test_field_matches_oracle_on_sphere_bin(orc, shape, limit):
     size = b["size"]
     with m.Worker(max_splats=len(splats), max_cells=int(size.max()) - 1, shape=shape, boundary_limit=limit) as w:
         w.set_profiling(True)
+        w.set_work_counting(True)
         w.upload_splats(splats)
         w.octree_build(0, len(splats), [-(-int(v) // 8) * 8 for v in size], b["offset"])
         w.mls_set(b["offset"])

@@ -348,6 +348,10 @@ def main():
     oct_s, _ = runner.stat_sum(OCTREE_STATS)
     mar_s, _ = runner.stat_sum(MARCHING_STATS)
     mls2_s, _ = runner.stat_sum([MLS_STAT])
+    if rank == 0:
+        for name in OCTREE_STATS + [MLS_STAT] + MARCHING_STATS:
+            s_, c_ = runner.stat_sum([name])
+            log("  %-44s %9.3f ms/step  %5d launches" % (name, 1e3 * s_, c_))
     for w in runner.workers:
         w.set_profiling(0)
 

@@ -176,106 +176,181 @@ struct GenParams
 
 __device__ __forceinline__ bool finiteF(float x) { return (__float_as_uint(x) & 0x7F800000u) != 0x7F800000u; }
 
+// Tile = kGenRows rows of cells of one z slab (x-fastest linear order is preserved because tiles
+// are numbered z-major, then by row group).  The 2 x (rows+1) corner rows the tile needs are
+// staged in shared memory with coalesced float4 loads, so every field value is read from HBM
+// about 2.25 times per bin instead of 8, and a tile takes ONE ticket / look-back for up to
+// 8 x 511 cells.  Occupied cells (a few percent) are then emitted warp-cooperatively: one lane
+// per vertex / index, so the stores of a cell are contiguous.
+constexpr int kGenRows = 8;
+constexpr int kGenMaxVRows = 16;   // rows x ceil(cellsX / 256) virtual rows per tile
+
+__device__ __forceinline__ uint32_t cellCode(const float *s0, const float *s1, uint32_t ps, uint32_t x, bool *valid)
+{
+    // s0 / s1: corner row y of slices z / z+1 in shared memory; ps = row pitch
+    const float iso[8] = {s0[x], s0[x + 1], s0[ps + x], s0[ps + x + 1], s1[x], s1[x + 1], s1[ps + x], s1[ps + x + 1]};
+    uint32_t code = 0;
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        code |= (iso[i] >= 0.0f ? 1u : 0u) << i;
+        ok = ok && finiteF(iso[i]);
+    }
+    *valid = ok;
+    return code;
+}
+
 __global__ void __launch_bounds__(kGenThreads) generateCellsKernel(GenParams P)
 {
+    extern __shared__ float sField[];   // [2 slices][kGenRows + 1 rows][ps]
+    __shared__ uint64_t sWarpTot[kGenMaxVRows * (kGenThreads / 32)];
     __shared__ uint64_t sScan[33];
     __shared__ uint32_t sTile;
     __shared__ uint64_t sPrefix;
-    if (threadIdx.x == 0) sTile = atomicAdd(&P.counters[CTR_GEN_TICKET], 1u);
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sTile = atomicAdd(&P.counters[CTR_GEN_TICKET], 1u);
     __syncthreads();
     const uint32_t tile = sTile;
-    const uint32_t c = tile * kGenThreads + threadIdx.x;
+    const uint32_t rowGroups = (P.cellsY + kGenRows - 1) / kGenRows;
+    const uint32_t z = P.zFirst + tile / rowGroups;
+    const uint32_t y0 = (tile % rowGroups) * kGenRows;
+    const uint32_t nRows = min((uint32_t) kGenRows, P.cellsY - y0);
+    const uint32_t ps = (P.cellsX + 1 + 3) & ~3u;          // staged row pitch (floats), <= P.pitch
+    const uint32_t chunks = (P.cellsX + kGenThreads - 1) / kGenThreads;
+    const uint32_t vRows = nRows * chunks;
 
-    // ---- genOccupied (kernels/marching.cl:84-120) ----
-    float iso[8];
-    uint32_t code = 0;
-    bool occupied = false;
-    uint32_t x = 0, y = 0, z = 0;
-    if (c < P.numCells)
+    // ---- stage the corner rows (float4, coalesced) ----
     {
-        x = c % P.cellsX;
-        uint32_t r = c / P.cellsX;
-        y = r % P.cellsY;
-        z = r / P.cellsY + P.zFirst;
-        const float *p0 = P.field + ((size_t) z * P.zStride + y) * P.pitch + x;
-        const float *p1 = p0 + (size_t) P.zStride * P.pitch;
-        iso[0] = __ldg(p0);
-        iso[1] = __ldg(p0 + 1);
-        iso[2] = __ldg(p0 + P.pitch);
-        iso[3] = __ldg(p0 + P.pitch + 1);
-        iso[4] = __ldg(p1);
-        iso[5] = __ldg(p1 + 1);
-        iso[6] = __ldg(p1 + P.pitch);
-        iso[7] = __ldg(p1 + P.pitch + 1);
-        bool valid = true;
-#pragma unroll
-        for (int i = 0; i < 8; i++)
+        const uint32_t ps4 = ps / 4, rowsPerSlice = nRows + 1;
+        const uint32_t total4 = 2 * rowsPerSlice * ps4;
+        for (uint32_t i = tid; i < total4; i += kGenThreads)
         {
-            code |= (iso[i] >= 0.0f ? 1u : 0u) << i;
-            valid = valid && finiteF(iso[i]);
+            uint32_t col4 = i % ps4, r = i / ps4;
+            uint32_t slice = r / rowsPerSlice, row = r % rowsPerSlice;
+            const float4 *src = reinterpret_cast<const float4 *>(P.field + ((size_t) (z + slice) * P.zStride + y0 + row) * P.pitch) + col4;
+            reinterpret_cast<float4 *>(sField + (slice * (kGenRows + 1) + row) * ps)[col4] = __ldg(src);
         }
-        occupied = valid && code != 0 && code != 255;
-    }
-    uint32_t nv = 0, ni = 0;
-    if (occupied)
-    {
-        nv = P.tables->count[code][0];
-        ni = P.tables->count[code][1];
-    }
-
-    // ---- scanElements: packed (vertices | indices << 31) ----
-    uint64_t packed = (uint64_t) nv | ((uint64_t) ni << 31);
-    uint64_t total;
-    uint64_t excl = blockExclusiveScan(packed, sScan, &total);
-    if (threadIdx.x < 32)
-    {
-        uint64_t p = lookbackExclusive(P.status, tile, total);
-        if (threadIdx.x == 0) sPrefix = p;
     }
     __syncthreads();
-    const uint64_t basePacked = sPrefix + excl;
-    const uint32_t vNext = (uint32_t) (basePacked & 0x7FFFFFFFu);
-    const uint32_t iNext = (uint32_t) (basePacked >> 31);
-    if (tile == gridDim.x - 1 && threadIdx.x == kGenThreads - 1)
-    {
-        uint64_t end = sPrefix + total;
-        P.counters[CTR_VERTS] = (uint32_t) (end & 0x7FFFFFFFu);
-        P.counters[CTR_INDICES] = (uint32_t) (end >> 31);
-    }
-    if (!occupied) return;
-    if (vNext + nv > P.vertexSpace || iNext + ni > P.indexSpace)
-    {
-        P.counters[CTR_OVERFLOW] = 1;
-        return;
-    }
+    const float *sl0 = sField, *sl1 = sField + (kGenRows + 1) * ps;
 
-    // ---- generateElements (kernels/marching.cl:184-258) ----
-    const Tables &T = *P.tables;
-    const uint32_t sx = T.start[code][0], sy = T.start[code][1];
-    const uint32_t gx = x + P.gridOffset.x, gy = y + P.gridOffset.y, gz = z + P.gridOffset.z;
-    for (uint32_t i = 0; i < nv; i++)
+    // ---- genOccupied + tile-local scan (fields: vertices | indices << 21 | cells << 42) ----
+    // inside a warp the three counts fit 10 + 12 + 6 bits of one 32-bit word
+    uint32_t excl[kGenMaxVRows];
+#pragma unroll
+    for (int v = 0; v < kGenMaxVRows; v++)
     {
-        const uint32_t e = T.data[sx + i];
-        const uint32_t a = T.edge[e][0], b = T.edge[e][1];
-        const uint32_t oax = a & 1, oay = (a >> 1) & 1, oaz = a >> 2;
-        const uint32_t dx = (b & 1) - oax, dy = ((b >> 1) & 1) - oay, dz = (b >> 2) - oaz;
-        // interp(), kernels/marching.cl:130-138: no contraction, explicit fma
-        const float inv = __fdiv_rn(1.0f, __fsub_rn(iso[a], iso[b]));
-        const float t = __fmul_rn(iso[a], inv);
-        float4 v;
-        v.x = __fmaf_rn(t, (float) dx, (float) (gx + oax));
-        v.y = __fmaf_rn(t, (float) dy, (float) (gy + oay));
-        v.z = __fmaf_rn(t, (float) dz, (float) (gz + oaz));
-        v.w = 0.0f;
-        // computeKey(), :148-154, on the compact layout (flag | z | y | x)
-        const uint32_t kx = 2 * x + 2 * oax + dx, ky = 2 * y + 2 * oay + dy, kz = 2 * z + 2 * oaz + dz;
-        uint32_t key = (kz << (2 * P.keyBits)) | (ky << P.keyBits) | kx;
-        if (kx == 0 || ky == 0 || kx == P.top.x || ky == P.top.y || kz == P.top.z) key |= 1u << (3 * P.keyBits);
-        P.unwelded[vNext + i] = v;
-        P.keys[vNext + i] = key;
-        P.vidx[vNext + i] = vNext + i;
+        excl[v] = 0;
+        if ((uint32_t) v < vRows)
+        {
+            const uint32_t r = v / chunks, x = (v % chunks) * kGenThreads + tid;
+            uint32_t packed = 0;
+            if (x < P.cellsX)
+            {
+                bool valid;
+                uint32_t code = cellCode(sl0 + r * ps, sl1 + r * ps, ps, x, &valid);
+                if (valid && code != 0 && code != 255)
+                    packed = (uint32_t) P.tables->count[code][0] | ((uint32_t) P.tables->count[code][1] << 10) | (1u << 22);
+            }
+            uint32_t inc = warpInclusiveScan(packed);
+            excl[v] = inc - packed;
+            if (lane == 31)
+                sWarpTot[v * (kGenThreads / 32) + warp] =
+                    (uint64_t) (inc & 0x3FF) | ((uint64_t) ((inc >> 10) & 0xFFF) << 21) | ((uint64_t) (inc >> 22) << 42);
+        }
     }
-    for (uint32_t i = 0; i < ni; i++) P.indices[iNext + i] = vNext + T.data[sy + i];
+    __syncthreads();
+    {
+        uint64_t t = tid < vRows * (kGenThreads / 32) ? sWarpTot[tid] : 0ull;
+        uint64_t total;
+        uint64_t e = blockExclusiveScan(t, sScan, &total);
+        if (tid < vRows * (kGenThreads / 32)) sWarpTot[tid] = e;
+        if (tid < 32)
+        {
+            const uint64_t agg = (total & 0x1FFFFF) | (((total >> 21) & 0x1FFFFF) << 31);
+            uint64_t p = lookbackExclusive(P.status, tile, agg);
+            if (tid == 0)
+            {
+                sPrefix = p;
+                if (tile == gridDim.x - 1)
+                {
+                    P.counters[CTR_VERTS] = (uint32_t) ((p + agg) & 0x7FFFFFFFu);
+                    P.counters[CTR_INDICES] = (uint32_t) ((p + agg) >> 31);
+                }
+                if (total >> 42) atomicAdd(&P.counters[CTR_CELLS], (uint32_t) (total >> 42));
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t vBase = (uint32_t) (sPrefix & 0x7FFFFFFFu), iBase = (uint32_t) (sPrefix >> 31);
+
+    // ---- generateElements for the occupied cells, one warp per cell ----
+    const Tables &T = *P.tables;
+#pragma unroll
+    for (int v = 0; v < kGenMaxVRows; v++)
+    {
+        if ((uint32_t) v >= vRows) break;
+        const uint32_t r = v / chunks, x = (v % chunks) * kGenThreads + tid;
+        const float *s0 = sl0 + r * ps, *s1 = sl1 + r * ps;
+        uint32_t code = 0;
+        bool occupied = false;
+        if (x < P.cellsX)
+        {
+            bool valid;
+            code = cellCode(s0, s1, ps, x, &valid);
+            occupied = valid && code != 0 && code != 255;
+        }
+        unsigned mask = __ballot_sync(0xFFFFFFFFu, occupied);
+        if (mask == 0) continue;
+        const uint64_t wbase = sWarpTot[v * (kGenThreads / 32) + warp];
+        const uint32_t myV = vBase + (uint32_t) (wbase & 0x1FFFFF) + (excl[v] & 0x3FF);
+        const uint32_t myI = iBase + (uint32_t) ((wbase >> 21) & 0x1FFFFF) + ((excl[v] >> 10) & 0xFFF);
+        while (mask)
+        {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t cx = __shfl_sync(0xFFFFFFFFu, x, src);
+            const uint32_t cc = __shfl_sync(0xFFFFFFFFu, code, src);
+            const uint32_t vNext = __shfl_sync(0xFFFFFFFFu, myV, src);
+            const uint32_t iNext = __shfl_sync(0xFFFFFFFFu, myI, src);
+            const uint32_t nv = T.count[cc][0], ni = T.count[cc][1];
+            if (vNext + nv > P.vertexSpace || iNext + ni > P.indexSpace)
+            {
+                if (lane == 0) P.counters[CTR_OVERFLOW] = 1;
+                continue;
+            }
+            const uint32_t sx = T.start[cc][0], sy = T.start[cc][1];
+            const uint32_t y = y0 + r;
+            if (lane < nv)
+            {
+                const uint32_t e = T.data[sx + lane];
+                const uint32_t a = T.edge[e][0], b = T.edge[e][1];
+                const uint32_t oax = a & 1, oay = (a >> 1) & 1, oaz = a >> 2;
+                const uint32_t obx = b & 1, oby = (b >> 1) & 1, obz = b >> 2;
+                const uint32_t dx = obx - oax, dy = oby - oay, dz = obz - oaz;
+                const float isoA = (oaz ? s1 : s0)[oay * ps + cx + oax];
+                const float isoB = (obz ? s1 : s0)[oby * ps + cx + obx];
+                // interp(), kernels/marching.cl:130-138: no contraction, explicit fma
+                const float inv = __fdiv_rn(1.0f, __fsub_rn(isoA, isoB));
+                const float t = __fmul_rn(isoA, inv);
+                float4 pos;
+                pos.x = __fmaf_rn(t, (float) dx, (float) (cx + P.gridOffset.x + oax));
+                pos.y = __fmaf_rn(t, (float) dy, (float) (y + P.gridOffset.y + oay));
+                pos.z = __fmaf_rn(t, (float) dz, (float) (z + P.gridOffset.z + oaz));
+                pos.w = 0.0f;
+                // computeKey(), :148-154, on the compact layout (flag | z | y | x)
+                const uint32_t kx = 2 * cx + 2 * oax + dx, ky = 2 * y + 2 * oay + dy, kz = 2 * z + 2 * oaz + dz;
+                uint32_t key = (kz << (2 * P.keyBits)) | (ky << P.keyBits) | kx;
+                if (kx == 0 || ky == 0 || kx == P.top.x || ky == P.top.y || kz == P.top.z) key |= 1u << (3 * P.keyBits);
+                P.unwelded[vNext + lane] = pos;
+                P.keys[vNext + lane] = key;
+                P.vidx[vNext + lane] = vNext + lane;
+            }
+            for (uint32_t i = lane; i < ni; i += 32) P.indices[iNext + i] = vNext + T.data[sy + i];
+        }
+    }
 }
 
 struct WeldParams
@@ -462,7 +537,10 @@ int shipBlock(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t s
     if (numCells64 == 0) return MLSB_OK;
     MLSB_REQUIRE(numCells64 < (1ull << 32) - kGenThreads, MLSB_ERR_LENGTH, "too many cells");
     const uint32_t numCells = (uint32_t) numCells64;
-    const uint32_t tiles = divUp(numCells, (uint32_t) kGenThreads);
+    const uint32_t tiles = (zLast - zFirst) * divUp(cellsY, (uint32_t) kGenRows);
+    const uint32_t stagedPitch = (cellsX + 1 + 3) & ~3u;
+    const size_t genSmem = 2 * (kGenRows + 1) * (size_t) stagedPitch * sizeof(float);
+    MLSB_REQUIRE(divUp(cellsX, (uint32_t) kGenThreads) * kGenRows <= (uint32_t) kGenMaxVRows, MLSB_ERR_LENGTH, "bin too wide");
     const uint32_t weldTilesMax = (uint32_t) divUp(w->vertexSpace, (uint64_t) (kWeldThreads * kWeldItems)) + 1;
     MLSB_REQUIRE(std::max(tiles, weldTilesMax) <= w->scanStatusWords, MLSB_ERR_LENGTH, "scan status too small");
 
@@ -496,7 +574,7 @@ int shipBlock(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t s
     }
     {
         ScopedStat st(w, "kernel.marching.generateElements.time");
-        generateCellsKernel<<<tiles, kGenThreads, 0, s>>>(G);
+        generateCellsKernel<<<tiles, kGenThreads, genSmem, s>>>(G);
         w->launches++;
     }
     MLSB_CUDA(cudaGetLastError());

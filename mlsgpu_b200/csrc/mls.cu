@@ -127,11 +127,33 @@ template <int SHAPE> __device__ __forceinline__ float finish(const Accum &f, flo
     return result;
 }
 
+// The hit test of kernels/mls.cl:373-374 is  d = pp * invr2;  d < 0.99f.  x -> RN(x * w) is
+// monotone for w > 0, so the set of pp >= 0 that pass is exactly { pp < T } for one float T per
+// splat: the smallest T with RN(T * w) >= 0.99f.  Comparing against T saves the multiply in the
+// pair test (d itself is only needed for a hit) without changing a single decision.
+// w = +0 (infinite radius) passes every finite pp: T = +inf.  w = +inf or NaN passes nothing: T = 0.
+__device__ __forceinline__ float hitThreshold(float w)
+{
+    if (!(w > 0.0f)) return w == 0.0f ? __uint_as_float(0x7F800000u) : 0.0f;
+    if (__float_as_uint(w) == 0x7F800000u) return 0.0f;
+    float t = __fdiv_rn(kRadiusCutoff, w);
+    if (!finite(t)) t = __uint_as_float(0x7F7FFFFFu);
+    for (int k = 0; k < 8 && t > 0.0f && __fmul_rn(t, w) >= kRadiusCutoff; k++) t = __uint_as_float(__float_as_uint(t) - 1);
+    for (int k = 0; k < 8 && __fmul_rn(t, w) < kRadiusCutoff; k++)
+    {
+        if (__float_as_uint(t) >= 0x7F7FFFFFu) return __uint_as_float(0x7F800000u);
+        t = __uint_as_float(__float_as_uint(t) + 1);
+    }
+    return t;
+}
+
 template <int SHAPE, bool COUNT>
 __global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
 {
-    __shared__ float4 sPosR[kChunk];
-    __shared__ float4 sNormQ[kChunk];
+    __shared__ float4 sPosT[2][kChunk];    // x, y, z, hit threshold on |p|^2
+    __shared__ float4 sNormQ[2][kChunk];   // normal, quality
+    __shared__ float sInvR[2][kChunk];     // 1/r^2
+    __shared__ uint8_t sList[kThreads / 32][kChunk];
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31, quad = tid >> 5;
@@ -166,72 +188,146 @@ __global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
         }
         unsigned long long tests = 0;
 
+        // bounding box of this warp's 8x4x4 brick of corners (exact small integers)
+        const float bx0 = (float) (wx + P.offset.x), bx1 = (float) (wx + 7 + P.offset.x);
+        const float by0 = (float) (wy + 4 * (int) (quad & 1) + P.offset.y), by1 = by0 + 3.0f;
+        const float bz0 = (float) (wz + 4 * (int) (quad >> 1) + P.offset.z), bz1 = bz0 + 3.0f;
+        uint8_t *const list = sList[quad];
+
+        // ---- chain walker (uniform across the CTA).  Unlike the reference (:336-358) a chunk may
+        // span several ranges; the per-corner visit order is still the chain order. ----
         int32_t end = P.commands[pos++];
-        while (pos < end)
-        {
-            // stage one batch; as in the reference a batch never spans two ranges (:336-358)
-            int32_t lpos = pos + (int32_t) tid;
-            if (lpos < end)
+        float4 rPos = make_float4(0.f, 0.f, 0.f, 0.f), rNq = rPos;
+        bool rHave = false;
+        int nextCount = 0;
+        auto fetch = [&]() {
+            int filled = 0;
+            int32_t id = -1;
+            while (filled < kChunk && pos >= 0)
             {
-                int32_t id = P.commands[lpos];
+                const int take = min(end - pos, kChunk - filled);
+                const int s = (int) tid - filled;
+                if (s >= 0 && s < take) id = P.commands[pos + s];
+                filled += take;
+                pos += take;
+                if (pos >= end)
+                {
+                    pos = P.commands[end];
+                    end = pos >= 0 ? P.commands[pos++] : INT_MIN;
+                }
+            }
+            nextCount = filled;
+            rHave = id >= 0;
+            if (rHave)
+            {
                 const float4 *sp = reinterpret_cast<const float4 *>(P.splats + id);
-                sPosR[tid] = __ldg(sp);
-                sNormQ[tid] = __ldg(sp + 1);
+                rPos = __ldg(sp);
+                rNq = __ldg(sp + 1);
             }
-            const int count = min(end - pos, kChunk);
-            pos += kChunk;
-            if (pos >= end)
+        };
+        auto store = [&](int b) {
+            if (rHave)
             {
-                pos = P.commands[end];
-                end = pos >= 0 ? P.commands[pos++] : INT_MIN;
+                sPosT[b][tid] = make_float4(rPos.x, rPos.y, rPos.z, hitThreshold(rPos.w));
+                sNormQ[b][tid] = rNq;
+                sInvR[b][tid] = rPos.w;
             }
-            __syncthreads();
+        };
+
+        fetch();
+        store(0);
+        int count = nextCount, buf = 0;
+        __syncthreads();
+        while (count > 0)
+        {
+            fetch();   // next chunk: global loads stay in flight while this one is processed
             if (COUNT) tests += 4ull * count;
 
-            for (int i = 0; i < count; i++)
+            // ---- per-warp cull: keep the splats whose ball can reach this warp's brick ----
+            int n = 0;
+            for (int k = 0; k < count; k += 32)
             {
-                const float4 s = sPosR[i];
+                const int i = k + (int) lane;
+                bool keep = false;
+                if (i < count)
+                {
+                    const float4 s = sPosT[buf][i];
+                    const float dx = fmaxf(fmaxf(bx0 - s.x, s.x - bx1), 0.0f);
+                    const float dy = fmaxf(fmaxf(by0 - s.y, s.y - by1), 0.0f);
+                    const float dz = fmaxf(fmaxf(bz0 - s.z, s.z - bz1), 0.0f);
+                    // |p|^2 >= dist^2 to the box for every corner of the brick; 1e-5 of slack
+                    // covers the few-ulp rounding of both sides
+                    keep = (dx * dx + dy * dy + dz * dz) * 0.99999f < s.w;
+                }
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) list[n + __popc(m & ((1u << lane) - 1))] = (uint8_t) i;
+                n += __popc(m);
+            }
+            __syncwarp();
+
+            // ---- pair tests over the kept splats, in list (= chain) order ----
+            int iNext = n > 0 ? list[0] : 0;
+            float4 sNext = sPosT[buf][iNext];
+            for (int idx = 0; idx < n; idx++)
+            {
+                const int i = iNext;
+                const float4 s = sNext;
+                if (idx + 1 < n)
+                {
+                    iNext = list[idx + 1];
+                    sNext = sPosT[buf][iNext];
+                }
                 const float pz = __fsub_rn(s.z, cz);
                 const float py = __fsub_rn(s.y, cy);
                 const float t = __fmaf_rn(py, py, __fmul_rn(pz, pz));
-                float px[4], pp[4], d[4];
-                bool any = false;
+                float px[4], pp[4];
+                bool hit[4], any = false;
 #pragma unroll
                 for (int j = 0; j < 4; j++)
                 {
                     px[j] = __fsub_rn(s.x, cx[j]);
                     pp[j] = __fmaf_rn(px[j], px[j], t);
-                    d[j] = __fmul_rn(pp[j], s.w);
-                    any |= d[j] < kRadiusCutoff;
+                    hit[j] = pp[j] < s.w;   // <=> pp * invr2 < 0.99f, see hitThreshold()
+                    any |= hit[j];
                 }
                 if (__any_sync(0xFFFFFFFFu, any))
                 {
-                    const float4 nq = sNormQ[i];
+                    const float4 nq = sNormQ[buf][i];
+                    const float invr2 = sInvR[buf][i];
+                    const float u = __fmaf_rn(nq.y, py, __fmul_rn(nq.z, pz));   // shared part of dot3(n, p)
 #pragma unroll
                     for (int j = 0; j < 4; j++)
                     {
-                        if (d[j] < kRadiusCutoff)
+                        if (__any_sync(0xFFFFFFFFu, hit[j]))
                         {
-                            float w = __fsub_rn(1.0f, d[j]);
-                            w = __fmul_rn(w, w);
-                            w = __fmul_rn(w, w);
-                            w = __fmul_rn(w, nq.w);
-                            Accum &a = acc[j];
-                            a.sumW = __fadd_rn(a.sumW, w);
-                            a.sumWpx = __fmaf_rn(w, px[j], a.sumWpx);
-                            a.sumWpy = __fmaf_rn(w, py, a.sumWpy);
-                            a.sumWpz = __fmaf_rn(w, pz, a.sumWpz);
-                            a.sumWnx = __fmaf_rn(w, nq.x, a.sumWnx);
-                            a.sumWny = __fmaf_rn(w, nq.y, a.sumWny);
-                            a.sumWnz = __fmaf_rn(w, nq.z, a.sumWnz);
-                            a.sumWpp = __fmaf_rn(w, pp[j], a.sumWpp);
-                            a.sumWpn = __fmaf_rn(w, dot3(nq.x, nq.y, nq.z, px[j], py, pz), a.sumWpn);
-                            a.hits++;
+                            if (hit[j])
+                            {
+                                const float d = __fmul_rn(pp[j], invr2);
+                                float w = __fsub_rn(1.0f, d);
+                                w = __fmul_rn(w, w);
+                                w = __fmul_rn(w, w);
+                                w = __fmul_rn(w, nq.w);
+                                Accum &a = acc[j];
+                                a.sumW = __fadd_rn(a.sumW, w);
+                                a.sumWpx = __fmaf_rn(w, px[j], a.sumWpx);
+                                a.sumWpy = __fmaf_rn(w, py, a.sumWpy);
+                                a.sumWpz = __fmaf_rn(w, pz, a.sumWpz);
+                                a.sumWnx = __fmaf_rn(w, nq.x, a.sumWnx);
+                                a.sumWny = __fmaf_rn(w, nq.y, a.sumWny);
+                                a.sumWnz = __fmaf_rn(w, nq.z, a.sumWnz);
+                                a.sumWpp = __fmaf_rn(w, pp[j], a.sumWpp);
+                                a.sumWpn = __fmaf_rn(w, __fmaf_rn(nq.x, px[j], u), a.sumWpn);
+                                a.hits++;
+                            }
                         }
                     }
                 }
             }
+
+            store(buf ^ 1);
             __syncthreads();
+            buf ^= 1;
+            count = nextCount;
         }
 
         unsigned long long hits = 0;

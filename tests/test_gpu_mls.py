@@ -85,3 +85,46 @@ def test_field_matches_oracle_on_sphere_bin(orc, shape, limit):
     same_field(got, ref)
     assert np.isfinite(got).sum() > 1000
     assert work == (t, h) and launches == 1 and secs > 0
+
+
+def test_hit_threshold_boundary_cases(orc):
+    """Splats whose 0.99 cut-off falls within a few ulp of a corner's |p|^2, plus degenerate
+    radii (1/r^2 = 0, inf, NaN, denormal, huge): the kernel's threshold compare must take exactly
+    the decisions of `pp * invr2 < 0.99f` — same hit count, bit-identical field."""
+    import mlsgpu_b200 as m
+    from mlsgpu_b200.capi import DeviceBuffer, SPLAT_DTYPE
+    rng = np.random.default_rng(3)
+    n = 600
+    splats = np.zeros(n, SPLAT_DTYPE)
+    splats["position"] = rng.uniform(0.0, 16.0, (n, 3)).astype(np.float32)
+    nrm = rng.normal(size=(n, 3))
+    splats["normal"] = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
+    splats["quality"] = rng.uniform(0.5, 2.0, n).astype(np.float32)
+    inv = np.zeros(n, np.float32)
+    for i in range(n):
+        c = rng.integers(0, 16, 3).astype(np.float32)           # a corner of the region
+        p = splats["position"][i] - c
+        pp = np.float32(np.float32(p[0] * p[0]) + np.float32(p[1] * p[1]) + np.float32(p[2] * p[2]))
+        w = np.float32(0.99) / max(pp, np.float32(1e-3))
+        inv[i] = np.nextafter(w, np.float32(np.inf if rng.integers(2) else 0), dtype=np.float32) if rng.integers(3) else w
+        for _ in range(int(rng.integers(0, 3))):
+            inv[i] = np.nextafter(inv[i], np.float32(np.inf if rng.integers(2) else 0), dtype=np.float32)
+    inv[:8] = np.array([0.0, np.inf, np.nan, 1e-45, 1e-38, 3e38, 1e30, 1e-30], np.float32)
+    splats["radius"] = inv     # the kernel expects 1/r^2 here
+    commands = np.array([n + 1] + list(range(n)) + [-1], np.int32)
+    start = np.zeros(8, np.int32)
+    size, sub = (16, 16, 16), 3
+    img = np.zeros((16 * 16, 16), np.float32)
+    ref = img.copy()
+    t, h = orc.mls_process_corners(ref, splats, commands, start, 3 * sub, (0, 0, 0), 16, 16, 16, 0, 0, 15,
+                                   orc.boundary_factor(1.0), 0)
+    with m.Worker(max_splats=64, max_cells=31) as w:
+        w.set_work_counting(True)
+        bufs = [DeviceBuffer.from_array(a) for a in (splats, commands, start, img)]
+        w.mls_set_buffers((0, 0, 0), bufs[0], bufs[1], bufs[2], sub)
+        w.mls_corners(bufs[3], 16, 16, 16, 16, 0, 0, 15)
+        w.synchronize()
+        got = bufs[3].to_array(np.float32, img.shape)
+        assert w.mls_work() == (t, h)
+    same_field(got, ref)
+    assert h > 1000

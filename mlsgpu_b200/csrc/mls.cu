@@ -23,8 +23,10 @@ namespace mlsb
 namespace
 {
 
-constexpr int kThreads = 128;
-constexpr int kChunk = 128;          // splats staged per batch
+constexpr int kSlots = 2;                      // corners per thread (sharing y and z)
+constexpr int kThreads = 512 / kSlots;         // one CTA per 8x8x8 block of corners
+constexpr int kBrickX = 2 * kSlots;            // a warp covers a kBrickX x 4 x 4 brick
+constexpr int kBatch = 32;           // splats fetched per warp per batch
 constexpr float kRadiusCutoff = 0.99f;   // kernels/mls.cl:36
 constexpr int kHitsCutoff = 4;           // kernels/mls.cl:37
 
@@ -150,37 +152,40 @@ __device__ __forceinline__ float hitThreshold(float w)
 template <int SHAPE, bool COUNT>
 __global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
 {
-    __shared__ float4 sPosT[2][kChunk];    // x, y, z, hit threshold on |p|^2
-    __shared__ float4 sNormQ[2][kChunk];   // normal, quality
-    __shared__ float sInvR[2][kChunk];     // 1/r^2
-    __shared__ uint8_t sList[kThreads / 32][kChunk];
+    // per-warp staging buffers for the splats that survive the cull
+    __shared__ float4 sPosT[kThreads / 32][kBatch];    // x, y, z, hit threshold on |p|^2
+    __shared__ float4 sNormQ[kThreads / 32][kBatch];   // normal, quality
+    __shared__ float sInvR[kThreads / 32][kBatch];     // 1/r^2
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31, quad = tid >> 5;
-    // corner layout inside the block: x = xi + 2j (j = slot 0..3), y, z fixed per thread
-    const int xi = lane & 1;
-    const int ly = (int) ((lane >> 1) & 3) + 4 * (int) (quad & 1);
-    const int lz = (int) ((lane >> 3) & 3) + 4 * (int) (quad >> 1);
+    // corner layout inside the block: the warp owns a kBrickX x 4 x 4 brick; a thread owns the
+    // corners x = lx + 2j (j = slot), with y and z fixed
+    constexpr int kBricksX = 8 / kBrickX;
+    const int qx = kBrickX * (int) (quad % kBricksX), qy = 4 * (int) ((quad / kBricksX) & 1), qz = 4 * (int) (quad / (2 * kBricksX));
+    const int lx = qx + (int) (lane & 1);
+    const int ly = qy + (int) ((lane >> 1) & 3);
+    const int lz = qz + (int) ((lane >> 3) & 3);
     const int wx = blockIdx.x * kMlsWgs, wy = blockIdx.y * kMlsWgs, wz = blockIdx.z * kMlsWgs + (int) P.zFirst;
 
     const uint32_t code = (spread3(wx) | (spread3(wy) << 1) | (spread3(wz) << 2)) >> P.startShift;
     int32_t pos = P.start[code];
 
-    float out[4];
+    float out[kSlots];
 #pragma unroll
-    for (int j = 0; j < 4; j++) out[j] = __uint_as_float(0x7FC00000u);
+    for (int j = 0; j < kSlots; j++) out[j] = __uint_as_float(0x7FC00000u);
 
     if (pos >= 0)
     {
         const float cy = (float) (wy + ly + P.offset.y);
         const float cz = (float) (wz + lz + P.offset.z);
-        float cx[4];
+        float cx[kSlots];
 #pragma unroll
-        for (int j = 0; j < 4; j++) cx[j] = (float) (wx + xi + 2 * j + P.offset.x);
+        for (int j = 0; j < kSlots; j++) cx[j] = (float) (wx + lx + 2 * j + P.offset.x);
 
-        Accum acc[4];
+        Accum acc[kSlots];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < kSlots; j++)
         {
             acc[j].sumW = acc[j].sumWpx = acc[j].sumWpy = acc[j].sumWpz = 0.0f;
             acc[j].sumWnx = acc[j].sumWny = acc[j].sumWnz = acc[j].sumWpp = acc[j].sumWpn = 0.0f;
@@ -188,14 +193,18 @@ __global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
         }
         unsigned long long tests = 0;
 
-        // bounding box of this warp's 8x4x4 brick of corners (exact small integers)
-        const float bx0 = (float) (wx + P.offset.x), bx1 = (float) (wx + 7 + P.offset.x);
-        const float by0 = (float) (wy + 4 * (int) (quad & 1) + P.offset.y), by1 = by0 + 3.0f;
-        const float bz0 = (float) (wz + 4 * (int) (quad >> 1) + P.offset.z), bz1 = bz0 + 3.0f;
-        uint8_t *const list = sList[quad];
+        // bounding box of this warp's brick of corners (exact small integers)
+        const float bx0 = (float) (wx + qx + P.offset.x), bx1 = bx0 + (float) (kBrickX - 1);
+        const float by0 = (float) (wy + qy + P.offset.y), by1 = by0 + 3.0f;
+        const float bz0 = (float) (wz + qz + P.offset.z), bz1 = bz0 + 3.0f;
+        float4 *const wPosT = sPosT[quad];
+        float4 *const wNormQ = sNormQ[quad];
+        float *const wInvR = sInvR[quad];
 
-        // ---- chain walker (uniform across the CTA).  Unlike the reference (:336-358) a chunk may
-        // span several ranges; the per-corner visit order is still the chain order. ----
+        // ---- every warp walks the chain on its own (no block barriers): 32 splats at a time are
+        // fetched into registers, culled against the warp's brick, and the survivors are packed
+        // into the warp's shared-memory buffer in chain order.  Unlike the reference (:336-358) a
+        // batch may span several ranges; the per-corner visit order is still the chain order. ----
         int32_t end = P.commands[pos++];
         float4 rPos = make_float4(0.f, 0.f, 0.f, 0.f), rNq = rPos;
         bool rHave = false;
@@ -203,10 +212,10 @@ __global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
         auto fetch = [&]() {
             int filled = 0;
             int32_t id = -1;
-            while (filled < kChunk && pos >= 0)
+            while (filled < kBatch && pos >= 0)
             {
-                const int take = min(end - pos, kChunk - filled);
-                const int s = (int) tid - filled;
+                const int take = min(end - pos, kBatch - filled);
+                const int s = (int) lane - filled;
                 if (s >= 0 && s < take) id = P.commands[pos + s];
                 filled += take;
                 pos += take;
@@ -225,78 +234,60 @@ __global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
                 rNq = __ldg(sp + 1);
             }
         };
-        auto store = [&](int b) {
-            if (rHave)
-            {
-                sPosT[b][tid] = make_float4(rPos.x, rPos.y, rPos.z, hitThreshold(rPos.w));
-                sNormQ[b][tid] = rNq;
-                sInvR[b][tid] = rPos.w;
-            }
-        };
 
         fetch();
-        store(0);
-        int count = nextCount, buf = 0;
-        __syncthreads();
-        while (count > 0)
+        while (nextCount > 0)
         {
-            fetch();   // next chunk: global loads stay in flight while this one is processed
-            if (COUNT) tests += 4ull * count;
-
-            // ---- per-warp cull: keep the splats whose ball can reach this warp's brick ----
-            int n = 0;
-            for (int k = 0; k < count; k += 32)
+            if (COUNT) tests += (unsigned long long) kSlots * nextCount;
+            // ---- cull: can the splat's ball reach this warp's brick at all? ----
+            bool keep = false;
+            if (rHave)
             {
-                const int i = k + (int) lane;
-                bool keep = false;
-                if (i < count)
-                {
-                    const float4 s = sPosT[buf][i];
-                    const float dx = fmaxf(fmaxf(bx0 - s.x, s.x - bx1), 0.0f);
-                    const float dy = fmaxf(fmaxf(by0 - s.y, s.y - by1), 0.0f);
-                    const float dz = fmaxf(fmaxf(bz0 - s.z, s.z - bz1), 0.0f);
-                    // |p|^2 >= dist^2 to the box for every corner of the brick; 1e-5 of slack
-                    // covers the few-ulp rounding of both sides
-                    keep = (dx * dx + dy * dy + dz * dz) * 0.99999f < s.w;
-                }
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-                if (keep) list[n + __popc(m & ((1u << lane) - 1))] = (uint8_t) i;
-                n += __popc(m);
+                const float dx = fmaxf(fmaxf(bx0 - rPos.x, rPos.x - bx1), 0.0f);
+                const float dy = fmaxf(fmaxf(by0 - rPos.y, rPos.y - by1), 0.0f);
+                const float dz = fmaxf(fmaxf(bz0 - rPos.z, rPos.z - bz1), 0.0f);
+                // a hit needs RN(|p|^2 * invr2) < 0.99 and |p|^2 >= dist^2 to the box for every corner
+                // of the brick; the 1e-4 of slack dwarfs the few ulp of rounding on either side
+                keep = (dx * dx + dy * dy + dz * dz) * rPos.w < 0.9901f;
             }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+            const int n = __popc(m);
+            if (keep)
+            {
+                const int p = __popc(m & ((1u << lane) - 1));
+                wPosT[p] = make_float4(rPos.x, rPos.y, rPos.z, hitThreshold(rPos.w));
+                wNormQ[p] = rNq;
+                wInvR[p] = rPos.w;
+            }
+            fetch();   // next batch: its global loads stay in flight while this one is processed
             __syncwarp();
 
-            // ---- pair tests over the kept splats, in list (= chain) order ----
-            int iNext = n > 0 ? list[0] : 0;
-            float4 sNext = sPosT[buf][iNext];
-            for (int idx = 0; idx < n; idx++)
+            // ---- pair tests over the kept splats, in chain order ----
+            float4 sNext = wPosT[0];
+            for (int i = 0; i < n; i++)
             {
-                const int i = iNext;
                 const float4 s = sNext;
-                if (idx + 1 < n)
-                {
-                    iNext = list[idx + 1];
-                    sNext = sPosT[buf][iNext];
-                }
+                if (i + 1 < n) sNext = wPosT[i + 1];
                 const float pz = __fsub_rn(s.z, cz);
                 const float py = __fsub_rn(s.y, cy);
                 const float t = __fmaf_rn(py, py, __fmul_rn(pz, pz));
-                float px[4], pp[4];
-                bool hit[4], any = false;
+                float px[kSlots], pp[kSlots];
+                bool hit[kSlots];
 #pragma unroll
-                for (int j = 0; j < 4; j++)
+                for (int j = 0; j < kSlots; j++)
                 {
                     px[j] = __fsub_rn(s.x, cx[j]);
                     pp[j] = __fmaf_rn(px[j], px[j], t);
                     hit[j] = pp[j] < s.w;   // <=> pp * invr2 < 0.99f, see hitThreshold()
-                    any |= hit[j];
                 }
-                if (__any_sync(0xFFFFFFFFu, any))
+                // after the cull nearly every kept splat hits somewhere in the brick, so there is
+                // no brick-level vote: only one per slot (a 2x4x4 sub-brick)
                 {
-                    const float4 nq = sNormQ[buf][i];
-                    const float invr2 = sInvR[buf][i];
+                    const float4 nq = wNormQ[i];
+                    const float invr2 = wInvR[i];
                     const float u = __fmaf_rn(nq.y, py, __fmul_rn(nq.z, pz));   // shared part of dot3(n, p)
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
+                    for (int j = 0; j < kSlots; j++)
                     {
                         if (__any_sync(0xFFFFFFFFu, hit[j]))
                         {
@@ -323,16 +314,12 @@ __global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
                     }
                 }
             }
-
-            store(buf ^ 1);
-            __syncthreads();
-            buf ^= 1;
-            count = nextCount;
+            __syncwarp();   // the buffer is overwritten by the next batch
         }
 
         unsigned long long hits = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < kSlots; j++)
         {
             out[j] = finish<SHAPE>(acc[j], P.boundaryFactor);
             if (COUNT) hits += acc[j].hits;
@@ -354,9 +341,9 @@ __global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
 
     // write_imagef(corners, (x, y + z*zStride + zBias)), kernels/mls.cl:429-432
     const long row = (long) (wy + ly) + (long) (wz + lz) * P.zStride + P.zBias;
-    float *dst = P.field + row * P.pitch + wx + xi;
+    float *dst = P.field + row * P.pitch + wx + lx;
 #pragma unroll
-    for (int j = 0; j < 4; j++) dst[2 * j] = out[j];
+    for (int j = 0; j < kSlots; j++) dst[2 * j] = out[j];
 }
 
 // Dependent-free FFMA stream: 8 independent accumulators per thread, every issue slot an FFMA.

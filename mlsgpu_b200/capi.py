@@ -87,7 +87,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(_HERE, "libmlsb200.so")
+    # MLSB200_LIB selects another build of the same library (A/B runs of kernel variants)
+    return os.environ.get("MLSB200_LIB") or os.path.join(_HERE, "libmlsb200.so")
 
 
 def lib():

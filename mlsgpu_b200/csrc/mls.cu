@@ -23,7 +23,13 @@ namespace mlsb
 namespace
 {
 
-constexpr int kSlots = 2;                      // corners per thread (sharing y and z)
+#ifndef MLSB_MLS_SLOTS
+#define MLSB_MLS_SLOTS 2
+#endif
+#ifndef MLSB_MLS_MINBLOCKS
+#define MLSB_MLS_MINBLOCKS 1
+#endif
+constexpr int kSlots = MLSB_MLS_SLOTS;                      // corners per thread (sharing y and z)
 constexpr int kThreads = 512 / kSlots;         // one CTA per 8x8x8 block of corners
 constexpr int kBrickX = 2 * kSlots;            // a warp covers a kBrickX x 4 x 4 brick
 constexpr int kBatch = 32;           // splats fetched per warp per batch
@@ -150,7 +156,7 @@ __device__ __forceinline__ float hitThreshold(float w)
 }
 
 template <int SHAPE, bool COUNT>
-__global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
+__global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKernel(MlsParams P)
 {
     // per-warp staging buffers for the splats that survive the cull
     __shared__ float4 sPosT[kThreads / 32][kBatch];    // x, y, z, hit threshold on |p|^2
@@ -209,7 +215,11 @@ __global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
         float4 rPos = make_float4(0.f, 0.f, 0.f, 0.f), rNq = rPos;
         bool rHave = false;
         int nextCount = 0;
-        auto fetch = [&]() {
+        // two-deep software pipeline: the ids of batch k+2 and the splats of batch k+1 are in flight
+        // while batch k is processed
+        int32_t idAhead = -1;
+        int countAhead = 0;
+        auto walk = [&]() {
             int filled = 0;
             int32_t id = -1;
             while (filled < kBatch && pos >= 0)
@@ -225,16 +235,22 @@ __global__ void __launch_bounds__(kThreads) processCornersKernel(MlsParams P)
                     end = pos >= 0 ? P.commands[pos++] : INT_MIN;
                 }
             }
-            nextCount = filled;
-            rHave = id >= 0;
+            idAhead = id;
+            countAhead = filled;
+        };
+        auto fetch = [&]() {
+            nextCount = countAhead;
+            rHave = idAhead >= 0;
             if (rHave)
             {
-                const float4 *sp = reinterpret_cast<const float4 *>(P.splats + id);
+                const float4 *sp = reinterpret_cast<const float4 *>(P.splats + idAhead);
                 rPos = __ldg(sp);
                 rNq = __ldg(sp + 1);
             }
+            walk();
         };
 
+        walk();
         fetch();
         while (nextCount > 0)
         {

@@ -35,7 +35,8 @@ MLS_STAT = "kernel.mls.processCorners.time"
 OCTREE_STATS = ["kernel.octree.writeEntries.time", "kernel.octree.sort.time", "kernel.octree.fill.time",
                 "kernel.octree.countCommands.time", "kernel.octree.scan.time", "kernel.octree.writeSplatIds.time",
                 "kernel.octree.writeStart.time"]
-MARCHING_STATS = ["kernel.marching.zero.time", "kernel.marching.generateElements.time",
+MARCHING_STATS = ["kernel.marching.zero.time", "kernel.marching.genOccupied.time", "kernel.marching.scanElements.time",
+                  "kernel.marching.generateElements.time",
                   "kernel.marching.sortVertices.time", "kernel.marching.compactVertices.time",
                   "kernel.marching.reindex.time", "kernel.marching.readback.time"]
 

@@ -125,7 +125,9 @@ struct mlsb_worker
     float *welded = nullptr;          // packed float3
     uint64_t *weldedKeys = nullptr;
     uint32_t *marchCounters = nullptr;   // device: see marching.cu
-    uint32_t *sliceHist = nullptr;       // per-slice (vertices, indices) histogram
+    uint64_t *tileTotals = nullptr;      // per marching tile: totals, then exclusive bases
+    uint32_t *tileList = nullptr;        // non-empty marching tiles
+    uint32_t maxTiles = 0;
     float scale = 1.0f;
     float bias[3] = {0.0f, 0.0f, 0.0f};
     void *hostBlob = nullptr;     // pinned readback buffer

@@ -40,6 +40,7 @@ enum
     CTR_WELDED = 3,
     CTR_FIRST_EXTERNAL = 4,
     CTR_CELLS = 5,
+    CTR_TILES = 6,      // non-empty tiles
     CTR_GEN_TICKET = 8,
     CTR_WELD_TICKET = 9,
     CTR_COUNT = 16
@@ -170,186 +171,278 @@ struct GenParams
     float4 *unwelded;
     uint32_t *keys, *vidx, *indices;
     uint32_t *counters;
-    volatile uint64_t *status;
+    uint64_t *tileTotals;          // per tile: classify writes (v | i << 21 | cells << 42), scanTiles turns it
+                                   // into the tile's exclusive base (v | i << 31)
+    uint32_t *tileList;            // non-empty tiles in order; count in counters[CTR_TILES]
     const Tables *tables;
 };
 
 __device__ __forceinline__ bool finiteF(float x) { return (__float_as_uint(x) & 0x7F800000u) != 0x7F800000u; }
 
-// Tile = kGenRows rows of cells of one z slab (x-fastest linear order is preserved because tiles
-// are numbered z-major, then by row group).  The 2 x (rows+1) corner rows the tile needs are
-// staged in shared memory with coalesced float4 loads, so every field value is read from HBM
-// about 2.25 times per bin instead of 8, and a tile takes ONE ticket / look-back for up to
-// 8 x 511 cells.  Occupied cells (a few percent) are then emitted warp-cooperatively: one lane
-// per vertex / index, so the stores of a cell are contiguous.
+// Tile = kGenRows rows of cells of one z slab; tiles are numbered z-major, then by row group, so
+// the x-fastest linear cell order of the output is preserved.
+//
+// Classification is bit-parallel: for every corner row a warp turns 32 loaded field values into
+// two ballot masks (sign >= 0, finite); the occupancy of 32 cells is then a handful of logic
+// operations on the 16 masks of the cells' 8 corners, i.e. about one instruction per cell, and
+// the field is read straight from global memory, coalesced, exactly once per (tile, row) plus the
+// shared rows between tiles.  Only lanes that own an occupied cell (a few percent) assemble the
+// 8-bit cube code and look up its counts.
 constexpr int kGenRows = 8;
-constexpr int kGenMaxVRows = 16;   // rows x ceil(cellsX / 256) virtual rows per tile
+constexpr int kGenWarps = kGenThreads / 32;
 
-__device__ __forceinline__ uint32_t cellCode(const float *s0, const float *s1, uint32_t ps, uint32_t x, bool *valid)
+struct RowMasks
 {
-    // s0 / s1: corner row y of slices z / z+1 in shared memory; ps = row pitch
-    const float iso[8] = {s0[x], s0[x + 1], s0[ps + x], s0[ps + x + 1], s1[x], s1[x + 1], s1[ps + x], s1[ps + x + 1]};
-    uint32_t code = 0;
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-    {
-        code |= (iso[i] >= 0.0f ? 1u : 0u) << i;
-        ok = ok && finiteF(iso[i]);
-    }
-    *valid = ok;
-    return code;
+    uint32_t s0, s1;   // sign bits (iso >= 0) at corner x / x+1
+    uint32_t f0, f1;   // finite bits at corner x / x+1
+};
+
+// Masks of one corner row of one slice for the 32 cells starting at cell x0 (needs 33 corners).
+__device__ __forceinline__ RowMasks loadRowMasks(const float *__restrict__ row, uint32_t x0, uint32_t lane, uint32_t numCorners)
+{
+    const uint32_t x = x0 + lane;
+    const float v = x < numCorners ? __ldg(row + x) : __uint_as_float(0x7FC00000u);
+    float e = __uint_as_float(0x7FC00000u);
+    if (lane == 0 && x0 + 32 < numCorners) e = __ldg(row + x0 + 32);
+    const uint32_t s = __ballot_sync(0xFFFFFFFFu, v >= 0.0f);
+    const uint32_t f = __ballot_sync(0xFFFFFFFFu, finiteF(v));
+    const uint32_t eb = __shfl_sync(0xFFFFFFFFu, (uint32_t) (e >= 0.0f) | ((uint32_t) finiteF(e) << 1), 0);
+    RowMasks m;
+    m.s0 = s;
+    m.f0 = f;
+    m.s1 = (s >> 1) | ((eb & 1u) << 31);
+    m.f1 = (f >> 1) | ((eb >> 1) << 31);
+    return m;
 }
 
-__global__ void __launch_bounds__(kGenThreads) generateCellsKernel(GenParams P)
+// EMIT = false: classify the tile's cells and write its (vertices, indices, cells) totals.
+// EMIT = true:  re-classify a NON-EMPTY tile (blockIdx.x indexes tileList), list its occupied cells
+//               in shared memory and emit one vertex / one index per thread at the base that
+//               scanTilesKernel computed, so that all stores are contiguous.
+// Splitting the pass keeps every CTA free of inter-CTA waits; only the few percent of tiles that
+// hold surface are classified twice.  CHUNKS = ceil(cellsX / 256).
+template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) generateCellsKernel(GenParams P)
 {
-    extern __shared__ float sField[];   // [2 slices][kGenRows + 1 rows][ps]
-    __shared__ uint64_t sWarpTot[kGenMaxVRows * (kGenThreads / 32)];
+    constexpr int kVRows = kGenRows * CHUNKS;
+    extern __shared__ uint32_t sList[];   // EMIT: [3][kVRows * 256]: cell, vertex base, index base
+    __shared__ uint64_t sWarpTot[kVRows * kGenWarps];
     __shared__ uint64_t sScan[33];
-    __shared__ uint32_t sTile;
-    __shared__ uint64_t sPrefix;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sTile = atomicAdd(&P.counters[CTR_GEN_TICKET], 1u);
-    __syncthreads();
-    const uint32_t tile = sTile;
+    if (EMIT && blockIdx.x >= P.counters[CTR_TILES]) return;
+    const uint32_t tile = EMIT ? P.tileList[blockIdx.x] : blockIdx.x;
     const uint32_t rowGroups = (P.cellsY + kGenRows - 1) / kGenRows;
     const uint32_t z = P.zFirst + tile / rowGroups;
     const uint32_t y0 = (tile % rowGroups) * kGenRows;
     const uint32_t nRows = min((uint32_t) kGenRows, P.cellsY - y0);
-    const uint32_t ps = (P.cellsX + 1 + 3) & ~3u;          // staged row pitch (floats), <= P.pitch
-    const uint32_t chunks = (P.cellsX + kGenThreads - 1) / kGenThreads;
-    const uint32_t vRows = nRows * chunks;
-
-    // ---- stage the corner rows (float4, coalesced) ----
-    {
-        const uint32_t ps4 = ps / 4, rowsPerSlice = nRows + 1;
-        const uint32_t total4 = 2 * rowsPerSlice * ps4;
-        for (uint32_t i = tid; i < total4; i += kGenThreads)
-        {
-            uint32_t col4 = i % ps4, r = i / ps4;
-            uint32_t slice = r / rowsPerSlice, row = r % rowsPerSlice;
-            const float4 *src = reinterpret_cast<const float4 *>(P.field + ((size_t) (z + slice) * P.zStride + y0 + row) * P.pitch) + col4;
-            reinterpret_cast<float4 *>(sField + (slice * (kGenRows + 1) + row) * ps)[col4] = __ldg(src);
-        }
-    }
-    __syncthreads();
-    const float *sl0 = sField, *sl1 = sField + (kGenRows + 1) * ps;
-
-    // ---- genOccupied + tile-local scan (fields: vertices | indices << 21 | cells << 42) ----
-    // inside a warp the three counts fit 10 + 12 + 6 bits of one 32-bit word
-    uint32_t excl[kGenMaxVRows];
-#pragma unroll
-    for (int v = 0; v < kGenMaxVRows; v++)
-    {
-        excl[v] = 0;
-        if ((uint32_t) v < vRows)
-        {
-            const uint32_t r = v / chunks, x = (v % chunks) * kGenThreads + tid;
-            uint32_t packed = 0;
-            if (x < P.cellsX)
-            {
-                bool valid;
-                uint32_t code = cellCode(sl0 + r * ps, sl1 + r * ps, ps, x, &valid);
-                if (valid && code != 0 && code != 255)
-                    packed = (uint32_t) P.tables->count[code][0] | ((uint32_t) P.tables->count[code][1] << 10) | (1u << 22);
-            }
-            uint32_t inc = warpInclusiveScan(packed);
-            excl[v] = inc - packed;
-            if (lane == 31)
-                sWarpTot[v * (kGenThreads / 32) + warp] =
-                    (uint64_t) (inc & 0x3FF) | ((uint64_t) ((inc >> 10) & 0xFFF) << 21) | ((uint64_t) (inc >> 22) << 42);
-        }
-    }
-    __syncthreads();
-    {
-        uint64_t t = tid < vRows * (kGenThreads / 32) ? sWarpTot[tid] : 0ull;
-        uint64_t total;
-        uint64_t e = blockExclusiveScan(t, sScan, &total);
-        if (tid < vRows * (kGenThreads / 32)) sWarpTot[tid] = e;
-        if (tid < 32)
-        {
-            const uint64_t agg = (total & 0x1FFFFF) | (((total >> 21) & 0x1FFFFF) << 31);
-            uint64_t p = lookbackExclusive(P.status, tile, agg);
-            if (tid == 0)
-            {
-                sPrefix = p;
-                if (tile == gridDim.x - 1)
-                {
-                    P.counters[CTR_VERTS] = (uint32_t) ((p + agg) & 0x7FFFFFFFu);
-                    P.counters[CTR_INDICES] = (uint32_t) ((p + agg) >> 31);
-                }
-                if (total >> 42) atomicAdd(&P.counters[CTR_CELLS], (uint32_t) (total >> 42));
-            }
-        }
-    }
-    __syncthreads();
-    const uint32_t vBase = (uint32_t) (sPrefix & 0x7FFFFFFFu), iBase = (uint32_t) (sPrefix >> 31);
-
-    // ---- generateElements for the occupied cells, one warp per cell ----
+    const uint32_t numCorners = P.cellsX + 1;
     const Tables &T = *P.tables;
-#pragma unroll
-    for (int v = 0; v < kGenMaxVRows; v++)
+    const float *slice0 = P.field + ((size_t) z * P.zStride + y0) * P.pitch;
+    const float *slice1 = slice0 + (size_t) P.zStride * P.pitch;
+    if (EMIT)
     {
-        if ((uint32_t) v >= vRows) break;
-        const uint32_t r = v / chunks, x = (v % chunks) * kGenThreads + tid;
-        const float *s0 = sl0 + r * ps, *s1 = sl1 + r * ps;
-        uint32_t code = 0;
-        bool occupied = false;
-        if (x < P.cellsX)
+        // (row, warp) totals are only written where a warp finds an occupied cell
+        for (uint32_t i = tid; i < kVRows * kGenWarps; i += kGenThreads) sWarpTot[i] = 0;
+        __syncthreads();
+    }
+
+    // ---- genOccupied (kernels/marching.cl:84-120), 32 cells per warp and row at a time ----
+    // per virtual row v = r * CHUNKS + c: this lane's packed count (vertices | indices << 10 |
+    // cell << 22, exclusive over the warp) and cube code (0 = not occupied)
+    uint32_t excl[kVRows], codes[kVRows];
+    uint64_t mine = 0;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; c++)
+    {
+        const uint32_t x0 = c * kGenThreads + warp * 32;
+        const bool active = x0 < P.cellsX;     // warp-uniform
+        RowMasks p0 = {0, 0, 0, 0}, p1 = {0, 0, 0, 0};
+        if (active)
         {
-            bool valid;
-            code = cellCode(s0, s1, ps, x, &valid);
-            occupied = valid && code != 0 && code != 255;
+            p0 = loadRowMasks(slice0, x0, lane, numCorners);
+            p1 = loadRowMasks(slice1, x0, lane, numCorners);
         }
-        unsigned mask = __ballot_sync(0xFFFFFFFFu, occupied);
-        if (mask == 0) continue;
-        const uint64_t wbase = sWarpTot[v * (kGenThreads / 32) + warp];
-        const uint32_t myV = vBase + (uint32_t) (wbase & 0x1FFFFF) + (excl[v] & 0x3FF);
-        const uint32_t myI = iBase + (uint32_t) ((wbase >> 21) & 0x1FFFFF) + ((excl[v] >> 10) & 0xFFF);
-        while (mask)
+        const uint32_t inRange = P.cellsX - x0 >= 32 ? 0xFFFFFFFFu : (active ? (1u << (P.cellsX - x0)) - 1 : 0u);
+#pragma unroll
+        for (int r = 0; r < kGenRows; r++)
         {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const uint32_t cx = __shfl_sync(0xFFFFFFFFu, x, src);
-            const uint32_t cc = __shfl_sync(0xFFFFFFFFu, code, src);
-            const uint32_t vNext = __shfl_sync(0xFFFFFFFFu, myV, src);
-            const uint32_t iNext = __shfl_sync(0xFFFFFFFFu, myI, src);
-            const uint32_t nv = T.count[cc][0], ni = T.count[cc][1];
-            if (vNext + nv > P.vertexSpace || iNext + ni > P.indexSpace)
+            const int v = r * CHUNKS + c;
+            uint32_t packed = 0, code = 0;
+            if (active && (uint32_t) r < nRows)
             {
-                if (lane == 0) P.counters[CTR_OVERFLOW] = 1;
-                continue;
+                const RowMasks c0 = loadRowMasks(slice0 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners);
+                const RowMasks c1 = loadRowMasks(slice1 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners);
+                const uint32_t valid = p0.f0 & p0.f1 & c0.f0 & c0.f1 & p1.f0 & p1.f1 & c1.f0 & c1.f1;
+                const uint32_t all = p0.s0 & p0.s1 & c0.s0 & c0.s1 & p1.s0 & p1.s1 & c1.s0 & c1.s1;
+                const uint32_t any = p0.s0 | p0.s1 | c0.s0 | c0.s1 | p1.s0 | p1.s1 | c1.s0 | c1.s1;
+                const uint32_t occ = valid & any & ~all & inRange;
+                if (occ)
+                {
+                    if ((occ >> lane) & 1)
+                    {
+                        // corner k sits at offset (k&1, (k>>1)&1, k>>2): kernels/marching.cl:98-106
+                        code = ((p0.s0 >> lane) & 1) | (((p0.s1 >> lane) & 1) << 1) | (((c0.s0 >> lane) & 1) << 2)
+                               | (((c0.s1 >> lane) & 1) << 3) | (((p1.s0 >> lane) & 1) << 4) | (((p1.s1 >> lane) & 1) << 5)
+                               | (((c1.s0 >> lane) & 1) << 6) | (((c1.s1 >> lane) & 1) << 7);
+                        packed = (uint32_t) T.count[code][0] | ((uint32_t) T.count[code][1] << 10) | (1u << 22);
+                    }
+                    if (EMIT)
+                    {
+                        const uint32_t inc = warpInclusiveScan(packed);
+                        excl[v] = inc - packed;
+                        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                        if (lane == 0)
+                            sWarpTot[v * kGenWarps + warp] =
+                                (uint64_t) (tot & 0x3FF) | ((uint64_t) ((tot >> 10) & 0xFFF) << 21) | ((uint64_t) (tot >> 22) << 42);
+                    }
+                    else
+                        mine += (uint64_t) (packed & 0x3FF) | ((uint64_t) ((packed >> 10) & 0xFFF) << 21) | ((uint64_t) (packed >> 22) << 42);
+                }
+                p0 = c0;
+                p1 = c1;
             }
-            const uint32_t sx = T.start[cc][0], sy = T.start[cc][1];
-            const uint32_t y = y0 + r;
-            if (lane < nv)
+            if (EMIT)
             {
-                const uint32_t e = T.data[sx + lane];
-                const uint32_t a = T.edge[e][0], b = T.edge[e][1];
-                const uint32_t oax = a & 1, oay = (a >> 1) & 1, oaz = a >> 2;
-                const uint32_t obx = b & 1, oby = (b >> 1) & 1, obz = b >> 2;
-                const uint32_t dx = obx - oax, dy = oby - oay, dz = obz - oaz;
-                const float isoA = (oaz ? s1 : s0)[oay * ps + cx + oax];
-                const float isoB = (obz ? s1 : s0)[oby * ps + cx + obx];
-                // interp(), kernels/marching.cl:130-138: no contraction, explicit fma
-                const float inv = __fdiv_rn(1.0f, __fsub_rn(isoA, isoB));
-                const float t = __fmul_rn(isoA, inv);
-                float4 pos;
-                pos.x = __fmaf_rn(t, (float) dx, (float) (cx + P.gridOffset.x + oax));
-                pos.y = __fmaf_rn(t, (float) dy, (float) (y + P.gridOffset.y + oay));
-                pos.z = __fmaf_rn(t, (float) dz, (float) (z + P.gridOffset.z + oaz));
-                pos.w = 0.0f;
-                // computeKey(), :148-154, on the compact layout (flag | z | y | x)
-                const uint32_t kx = 2 * cx + 2 * oax + dx, ky = 2 * y + 2 * oay + dy, kz = 2 * z + 2 * oaz + dz;
-                uint32_t key = (kz << (2 * P.keyBits)) | (ky << P.keyBits) | kx;
-                if (kx == 0 || ky == 0 || kx == P.top.x || ky == P.top.y || kz == P.top.z) key |= 1u << (3 * P.keyBits);
-                P.unwelded[vNext + lane] = pos;
-                P.keys[vNext + lane] = key;
-                P.vidx[vNext + lane] = vNext + lane;
+                codes[v] = code;
+                if (code == 0) excl[v] = 0;
             }
-            for (uint32_t i = lane; i < ni; i += 32) P.indices[iNext + i] = vNext + T.data[sy + i];
         }
+    }
+
+    if (!EMIT)
+    {
+        mine = warpSum(mine);
+        if (lane == 0) sWarpTot[warp] = mine;
+        __syncthreads();
+        if (tid == 0)
+        {
+            uint64_t total = 0;
+            for (int i = 0; i < kGenWarps; i++) total += sWarpTot[i];
+            P.tileTotals[tile] = total;
+        }
+        return;
+    }
+
+    // ---- scanElements inside the tile: exclusive bases of every (virtual row, warp) ----
+    __syncthreads();
+    uint64_t total;
+    {
+        uint64_t t = tid < kVRows * kGenWarps ? sWarpTot[tid] : 0ull;
+        uint64_t e = blockExclusiveScan(t, sScan, &total);
+        if (tid < kVRows * kGenWarps) sWarpTot[tid] = e;
+    }
+    __syncthreads();
+    const uint32_t numCells = (uint32_t) (total >> 42);
+    const uint32_t numVerts = (uint32_t) (total & 0x1FFFFF), numIdx = (uint32_t) ((total >> 21) & 0x1FFFFF);
+    uint32_t *const sCell = sList, *const sVloc = sList + kVRows * kGenThreads, *const sIloc = sList + 2 * kVRows * kGenThreads;
+#pragma unroll
+    for (int v = 0; v < kVRows; v++)
+    {
+        if (codes[v])
+        {
+            const uint64_t b = sWarpTot[v * kGenWarps + warp];
+            const uint32_t idx = (uint32_t) (b >> 42) + (excl[v] >> 22);
+            const uint32_t x = (v % CHUNKS) * kGenThreads + tid, r = v / CHUNKS;
+            sCell[idx] = x | (r << 16) | (codes[v] << 24);
+            sVloc[idx] = (uint32_t) (b & 0x1FFFFF) + (excl[v] & 0x3FF);
+            sIloc[idx] = (uint32_t) ((b >> 21) & 0x1FFFFF) + ((excl[v] >> 10) & 0xFFF);
+        }
+    }
+    __syncthreads();
+
+    const uint64_t tileBase = P.tileTotals[tile];
+    const uint32_t vBase = (uint32_t) (tileBase & 0x7FFFFFFFu), iBase = (uint32_t) (tileBase >> 31);
+    if (vBase + numVerts > P.vertexSpace || iBase + numIdx > P.indexSpace)
+    {
+        if (tid == 0) P.counters[CTR_OVERFLOW] = 1;
+        return;
+    }
+
+    // ---- generateElements (kernels/marching.cl:184-258): one thread per vertex ----
+    for (uint32_t j = tid; j < numVerts; j += kGenThreads)
+    {
+        // last cell whose first vertex is <= j
+        uint32_t lo = 0, hi = numCells;
+        while (hi - lo > 1)
+        {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sVloc[mid] <= j) lo = mid; else hi = mid;
+        }
+        const uint32_t cell = sCell[lo], k = j - sVloc[lo];
+        const uint32_t x = cell & 0xFFFF, r = (cell >> 16) & 0xFF, code = cell >> 24;
+        const uint32_t y = y0 + r;
+        const uint32_t e = T.data[T.start[code][0] + k];
+        const uint32_t a = T.edge[e][0], b = T.edge[e][1];
+        const uint32_t oax = a & 1, oay = (a >> 1) & 1, oaz = a >> 2;
+        const uint32_t obx = b & 1, oby = (b >> 1) & 1, obz = b >> 2;
+        const uint32_t dx = obx - oax, dy = oby - oay, dz = obz - oaz;
+        const float isoA = __ldg((oaz ? slice1 : slice0) + (size_t) (r + oay) * P.pitch + x + oax);
+        const float isoB = __ldg((obz ? slice1 : slice0) + (size_t) (r + oby) * P.pitch + x + obx);
+        // interp(), kernels/marching.cl:130-138: no contraction, explicit fma
+        const float inv = __fdiv_rn(1.0f, __fsub_rn(isoA, isoB));
+        const float t = __fmul_rn(isoA, inv);
+        float4 pos;
+        pos.x = __fmaf_rn(t, (float) dx, (float) (x + P.gridOffset.x + oax));
+        pos.y = __fmaf_rn(t, (float) dy, (float) (y + P.gridOffset.y + oay));
+        pos.z = __fmaf_rn(t, (float) dz, (float) (z + P.gridOffset.z + oaz));
+        pos.w = 0.0f;
+        // computeKey(), :148-154, on the compact layout (flag | z | y | x)
+        const uint32_t kx = 2 * x + 2 * oax + dx, ky = 2 * y + 2 * oay + dy, kz = 2 * z + 2 * oaz + dz;
+        uint32_t key = (kz << (2 * P.keyBits)) | (ky << P.keyBits) | kx;
+        if (kx == 0 || ky == 0 || kx == P.top.x || ky == P.top.y || kz == P.top.z) key |= 1u << (3 * P.keyBits);
+        P.unwelded[vBase + j] = pos;
+        P.keys[vBase + j] = key;
+        P.vidx[vBase + j] = vBase + j;
+    }
+    // ---- ... and one thread per index ----
+    for (uint32_t j = tid; j < numIdx; j += kGenThreads)
+    {
+        uint32_t lo = 0, hi = numCells;
+        while (hi - lo > 1)
+        {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sIloc[mid] <= j) lo = mid; else hi = mid;
+        }
+        const uint32_t code = sCell[lo] >> 24, k = j - sIloc[lo];
+        P.indices[iBase + j] = vBase + sVloc[lo] + T.data[T.start[code][1] + k];
+    }
+}
+
+// Exclusive scan of the tile totals (one CTA: at most ~33 k tiles), list of non-empty tiles,
+// grand totals -> counters.  The role of clogs::Scan(uint2) at src/marching.cpp:721.
+__global__ void __launch_bounds__(1024) scanTilesKernel(uint64_t *tileTotals, uint32_t *tileList, uint32_t numTiles,
+                                                        uint32_t *counters)
+{
+    __shared__ uint64_t sScan[33];
+    __shared__ uint32_t sScan32[33];
+    const uint32_t per = (numTiles + 1023) / 1024;
+    const uint32_t first = threadIdx.x * per, last = min(first + per, numTiles);
+    uint64_t sum = 0, cells = 0;
+    uint32_t nonEmpty = 0;
+    for (uint32_t t = first; t < last; t++)
+    {
+        const uint64_t v = tileTotals[t];
+        sum += (v & 0x1FFFFF) | (((v >> 21) & 0x1FFFFF) << 31);
+        cells += v >> 42;
+        nonEmpty += v != 0;
+    }
+    uint64_t total;
+    uint32_t totalNonEmpty;
+    uint64_t base = blockExclusiveScan(sum, sScan, &total);
+    uint32_t listPos = blockExclusiveScan(nonEmpty, sScan32, &totalNonEmpty);
+    for (uint32_t t = first; t < last; t++)
+    {
+        const uint64_t v = tileTotals[t];
+        tileTotals[t] = base;
+        base += (v & 0x1FFFFF) | (((v >> 21) & 0x1FFFFF) << 31);
+        if (v != 0) tileList[listPos++] = t;
+    }
+    if (cells) atomicAdd(&counters[CTR_CELLS], (uint32_t) cells);
+    if (threadIdx.x == 0)
+    {
+        counters[CTR_VERTS] = (uint32_t) (total & 0x7FFFFFFFu);
+        counters[CTR_INDICES] = (uint32_t) (total >> 31);
+        counters[CTR_TILES] = totalNonEmpty;
     }
 }
 
@@ -486,12 +579,17 @@ int marchingAlloc(mlsb_worker *w)
     MLSB_CUDA(cudaMalloc(&w->welded, (w->vertexSpace + 1) * 3 * sizeof(float)));
     MLSB_CUDA(cudaMalloc(&w->weldedKeys, (w->vertexSpace + 1) * sizeof(uint64_t)));
     MLSB_CUDA(cudaMalloc(&w->marchCounters, CTR_COUNT * sizeof(uint32_t)));
+    w->maxTiles = c.maxCells * divUp(c.maxCells, (uint32_t) kGenRows);
+    MLSB_CUDA(cudaMalloc(&w->tileTotals, (size_t) w->maxTiles * sizeof(uint64_t)));
+    MLSB_CUDA(cudaMalloc(&w->tileList, (size_t) w->maxTiles * sizeof(uint32_t)));
     MLSB_CUDA(cudaMalloc(&w->tables, sizeof(Tables)));
     MLSB_CUDA(cudaMemcpy(w->tables, &gTables.t, sizeof(Tables), cudaMemcpyHostToDevice));
     mlsb_mesh_sizes worst{w->vertexSpace, w->indexSpace / 3, 0};
     w->hostBlobBytes = mlsb_mesh_host_bytes(&worst) + 64;
     MLSB_CUDA(cudaMallocHost(&w->hostBlob, w->hostBlobBytes));
     MLSB_CUDA(cudaMallocHost(&w->hostCounters, CTR_COUNT * sizeof(uint32_t)));
+    MLSB_CUDA(cudaFuncSetAttribute(generateCellsKernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   3 * kGenRows * 2 * kGenThreads * (int) sizeof(uint32_t)));
     return MLSB_OK;
 }
 
@@ -509,6 +607,8 @@ void marchingFree(mlsb_worker *w)
     cudaFree(w->welded);
     cudaFree(w->weldedKeys);
     cudaFree(w->marchCounters);
+    cudaFree(w->tileTotals);
+    cudaFree(w->tileList);
     cudaFree(w->tables);
     cudaFreeHost(w->hostBlob);
     cudaFreeHost(w->hostCounters);
@@ -538,11 +638,11 @@ int shipBlock(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t s
     MLSB_REQUIRE(numCells64 < (1ull << 32) - kGenThreads, MLSB_ERR_LENGTH, "too many cells");
     const uint32_t numCells = (uint32_t) numCells64;
     const uint32_t tiles = (zLast - zFirst) * divUp(cellsY, (uint32_t) kGenRows);
-    const uint32_t stagedPitch = (cellsX + 1 + 3) & ~3u;
-    const size_t genSmem = 2 * (kGenRows + 1) * (size_t) stagedPitch * sizeof(float);
-    MLSB_REQUIRE(divUp(cellsX, (uint32_t) kGenThreads) * kGenRows <= (uint32_t) kGenMaxVRows, MLSB_ERR_LENGTH, "bin too wide");
+    const uint32_t chunks = divUp(cellsX, (uint32_t) kGenThreads);
+    MLSB_REQUIRE(chunks <= 2, MLSB_ERR_LENGTH, "bin too wide");
+    const size_t genSmem = 3 * (size_t) kGenRows * chunks * kGenThreads * sizeof(uint32_t);
     const uint32_t weldTilesMax = (uint32_t) divUp(w->vertexSpace, (uint64_t) (kWeldThreads * kWeldItems)) + 1;
-    MLSB_REQUIRE(std::max(tiles, weldTilesMax) <= w->scanStatusWords, MLSB_ERR_LENGTH, "scan status too small");
+    MLSB_REQUIRE(weldTilesMax <= w->scanStatusWords && tiles <= w->maxTiles, MLSB_ERR_LENGTH, "scan scratch too small");
 
     GenParams G;
     G.field = w->field;
@@ -563,19 +663,29 @@ int shipBlock(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t s
     G.vidx = w->vertIdx[0];
     G.indices = w->indices;
     G.counters = w->marchCounters;
-    G.status = w->scanStatus;
+    G.tileTotals = w->tileTotals;
+    G.tileList = w->tileList;
     G.tables = reinterpret_cast<const Tables *>(w->tables);
     MLSB_REQUIRE(3 * G.keyBits + 1 <= 32, MLSB_ERR_LENGTH, "bin too large for the compact vertex key");
 
     {
         ScopedStat st(w, "kernel.marching.zero.time", 0);
         MLSB_CUDA(cudaMemsetAsync(w->marchCounters, 0, CTR_COUNT * sizeof(uint32_t), s));
-        MLSB_CUDA(cudaMemsetAsync(w->scanStatus, 0, (size_t) tiles * sizeof(uint64_t), s));
+    }
+    {
+        ScopedStat st(w, "kernel.marching.genOccupied.time");
+        if (chunks == 1) generateCellsKernel<false, 1><<<tiles, kGenThreads, 0, s>>>(G);
+        else generateCellsKernel<false, 2><<<tiles, kGenThreads, 0, s>>>(G);
+    }
+    {
+        ScopedStat st(w, "kernel.marching.scanElements.time");
+        scanTilesKernel<<<1, 1024, 0, s>>>(w->tileTotals, w->tileList, tiles, w->marchCounters);
     }
     {
         ScopedStat st(w, "kernel.marching.generateElements.time");
-        generateCellsKernel<<<tiles, kGenThreads, genSmem, s>>>(G);
-        w->launches++;
+        if (chunks == 1) generateCellsKernel<true, 1><<<tiles, kGenThreads, genSmem, s>>>(G);
+        else generateCellsKernel<true, 2><<<tiles, kGenThreads, genSmem, s>>>(G);
+        w->launches += 3;
     }
     MLSB_CUDA(cudaGetLastError());
 

@@ -176,3 +176,19 @@ def prepare(splats, fit_grid, smooth=4.0, max_cells=255, max_splats=1 << 21, buc
     g = world_to_grid(s, fit_grid, lo)
     bins = make_bins(g, hi - lo, max_cells, max_splats)
     return g, bins, lo, np.float32(fit_grid)
+
+
+def partition_bins(bins, world):
+    """Static partition of bins over `world` GPUs (one worker group per GPU, no collective on the
+    data path): longest-processing-time greedy on the splat count, deterministic.  The
+    reference hands bins to the device with the most free staging capacity
+    (src/workers.cpp:329-343); a static split makes scaling runs reproducible.
+    Returns a list of `world` lists of bin indices."""
+    order = sorted(range(len(bins)), key=lambda i: (-len(bins[i]["ids"]), i))
+    loads = [0] * world
+    parts = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (loads[k], k))
+        parts[r].append(i)
+        loads[r] += len(bins[i]["ids"])
+    return [sorted(p) for p in parts]

@@ -21,10 +21,11 @@ def same_field(a, b):
     np.testing.assert_array_equal(a[~na].view(np.uint32), b[~nb].view(np.uint32))
 
 
-def test_process_corners_reference_fixture(orc):
+@pytest.mark.parametrize("radius", [65.0, 35.0])
+def test_process_corners_reference_fixture(orc, radius):
     import mlsgpu_b200 as m
     from mlsgpu_b200.capi import DeviceBuffer
-    c = process_corners_case(orc)
+    c = process_corners_case(orc, radius)
     ref = c["image"].copy()
     orc.mls_process_corners(ref, c["splats"], c["commands"], c["start"], 3 * c["sub"], c["offset"], c["size"][0],
                             c["size"][1], c["z_stride"], c["z_bias"], c["z_first"], c["z_last"],

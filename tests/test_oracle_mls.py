@@ -85,11 +85,14 @@ def test_fit_sphere(orc):
             assert doubles_equal(float(s["normal"][i]), float(g[i]), eps)
 
 
-def process_corners_case(orc):
-    """TestMls::testProcessCorners inputs, test/test_mls.cpp:416-480."""
+def process_corners_case(orc, radius=65.0):
+    """TestMls::testProcessCorners inputs, test/test_mls.cpp:416-480.
+
+    With the upstream radius (65) every corner of the region lies more than sqrt(3) inside the
+    sphere, so the upstream assertions only ever see NaN; radius=35 puts the surface through the
+    region and makes the same assertions compare real distances."""
     N = 50
     center = (10.0, 20.0, 35.0)
-    radius = 65.0
     size = (19, 24, 28)
     offset = (20, 15, 33)
     wgs = 8
@@ -135,15 +138,20 @@ def check_process_corners(c, image):
                 nan_count += int(np.isnan(actual))
                 assert doubles_equal(float(expected), float(actual), 1e-5), (x, y, z, expected, actual)
     assert 0 < nan_count
+    return nan_count
 
 
-def test_process_corners(orc):
-    c = process_corners_case(orc)
+@pytest.mark.parametrize("radius", [65.0, 35.0])
+def test_process_corners(orc, radius):
+    c = process_corners_case(orc, radius)
     t, h = orc.mls_process_corners(c["image"], c["splats"], c["commands"], c["start"], 3 * c["sub"],
                                    c["offset"], c["size"][0], c["size"][1], c["z_stride"], c["z_bias"],
                                    c["z_first"], c["z_last"], orc.boundary_factor(1.0), shape=0)
     assert t > 0 and 0 < h <= t
-    check_process_corners(c, c["image"])
+    nan_count = check_process_corners(c, c["image"])
+    total = c["size"][0] * c["size"][1] * (c["z_last"] - c["z_first"] + 1)
+    if radius == 35.0:
+        assert total - nan_count > 300     # real distances were compared
 
 
 def test_fused_matches_as_written():

@@ -141,12 +141,11 @@ class Runner:
                 self.mesh_bytes += 12 * int(s.numVertices) + 12 * int(s.numTriangles) + 8 * int(s.numVertices - s.numInternalVertices)
         self.sink = MESH_SINK(sink)
 
-    def _work(self, wi, from_host):
-        import ctypes as C
+    def _work(self, wi, from_host, single=False):
         from mlsgpu_b200.capi import lib, _check
         w = self.workers[wi]
         L = lib()
-        for b in self.bins[wi::len(self.workers)]:
+        for b in (self.bins if single else self.bins[wi::len(self.workers)]):
             if from_host:
                 src = self.pinned.ptr.value + 32 * b["first"]
             else:
@@ -154,9 +153,11 @@ class Runner:
             _check(L.mlsb_splats_upload_async(w.h, src, 0, b["n"]))
             _check(L.mlsb_worker_process_bin(w.h, 0, b["n"], b["size"].ctypes.data, b["offset"].ctypes.data, self.sink, None))
 
-    def step(self, from_host):
-        if len(self.workers) == 1:
-            self._work(0, from_host)
+    def step(self, from_host, single=False):
+        """One pass over all bins.  single=True: worker 0 alone (kernels do not overlap, which is
+        what a per-kernel roofline measurement needs)."""
+        if single or len(self.workers) == 1:
+            self._work(0, from_host, single=True)
             return
         ts = [threading.Thread(target=self._work, args=(i, from_host)) for i in range(len(self.workers))]
         for t in ts:
@@ -259,7 +260,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--splats", type=int, default=10_000_000)
-    ap.add_argument("--threads", type=int, default=2, help="workers per GPU (--device-threads)")
+    ap.add_argument("--threads", type=int, default=3, help="workers per GPU (--device-threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -292,7 +293,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(from_host, steps, profile):
+    def timed(from_host, steps, profile, single=False):
         for w in runner.workers:
             w.set_profiling(1 if profile else 0)
             w.reset_statistics()
@@ -303,7 +304,7 @@ def main():
         e0.record()
         t0 = time.perf_counter()
         for _ in range(steps):
-            runner.step(from_host)
+            runner.step(from_host, single)
         runner.sync()
         e1.record()
         torch.cuda.synchronize()
@@ -334,11 +335,15 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ms_dev, wall_dev, launches = timed(False, args.steps, profile=True)
-    mls_s, mls_n = runner.stat_sum([MLS_STAT])
-    clocks = sampler.stop()
+    mls_conc_s, _ = runner.stat_sum([MLS_STAT])
     runner.step(True)   # warm the host path
     ms_e2e, wall_e2e, _ = timed(True, args.steps, profile=False)
     d2h = runner.mesh_bytes // args.steps
+    # roofline pass: the same steps on ONE worker, so that processCorners never shares the GPU with
+    # another worker's kernels while its CUDA events are taken
+    ms_single, _, _ = timed(False, args.steps, profile=True, single=True)
+    mls_s, mls_n = runner.stat_sum([MLS_STAT])
+    clocks = sampler.stop()
 
     # ---- per-stage breakdown (untimed pass with every kernel timed) ----
     for w in runner.workers:
@@ -378,6 +383,10 @@ def main():
                      "model": "7*T + 16*H FP32 pipe instructions per step (SURVEY 8d), 2 flop each",
                      "pair_tests": int(T), "hits": int(H), "kernel_ms_per_step": 1e3 * mls_per_step,
                      "launches_per_step": mls_n // args.steps,
+                     "measured_in": "timed single-worker pass (%d steps, %.1f ms/step); with %d workers sharing the GPU "
+                                    "the same kernels take %.1f ms/step (frac %.3f)"
+                                    % (args.steps, ms_single / args.steps, args.threads, 1e3 * mls_conc_s / args.steps,
+                                       2.0 * inst / (mls_conc_s / args.steps) / 1e12 / peak if mls_conc_s else 0.0),
                      "peak_source": "measured here: dependent-free FFMA stream, %.2f T lane-inst/s "
                                     "(MEASURED_PEAKS.json has no FP32 figure)" % (peak_inst / 1e12)},
         "stages_ms_per_step": {"octree": 1e3 * oct_s, "mls": 1e3 * mls2_s, "marching": 1e3 * mar_s,

@@ -37,9 +37,9 @@ def test_mirror_demo_matches_python_binding(tmp_path):
     splats = np.ascontiguousarray(g[b["ids"]])
     path = tmp_path / "splats.bin"
     splats.tofile(path)
-    args = [demo, str(path)] + [str(int(v)) for v in b["size"]] + [str(int(v)) for v in b["offset"]] + ["63"]
+    args = [demo, str(path)] + [str(int(v)) for v in b["size"]] + [str(int(v)) for v in b["offset"]] + ["127"]
     out = subprocess.run(args, check=True, capture_output=True, text=True).stdout.split()
-    with m.Worker(max_splats=len(splats), max_cells=63) as w:
+    with m.Worker(max_splats=len(splats), max_cells=127) as w:
         w.upload_splats(splats)
         blocks = w.process_bin(0, len(splats), b["size"], b["offset"])
     blk = blocks[0]

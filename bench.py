@@ -277,8 +277,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: mlsgpu_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    # more spinning worker threads than cores would fight each other: block on events instead
+    if world * args.threads > (os.cpu_count() or 1) * 3 // 4:
+        os.environ.setdefault("MLSB_SYNC", "block")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("MLSB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import mlsgpu_b200 as m

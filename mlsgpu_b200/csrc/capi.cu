@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -73,6 +74,18 @@ void collectStats(mlsb_worker *w)
         w->eventPool.push_back(sp.end);
     }
     w->pendingSpans.clear();
+}
+
+int waitStream(mlsb_worker *w)
+{
+    if (w->blockingSync)
+    {
+        MLSB_CUDA(cudaEventRecord(w->syncEvent, w->stream));
+        MLSB_CUDA(cudaEventSynchronize(w->syncEvent));
+    }
+    else
+        MLSB_CUDA(cudaStreamSynchronize(w->stream));
+    return MLSB_OK;
 }
 
 // src/mls.cpp:137-144
@@ -158,6 +171,15 @@ int mlsb_worker_create(const mlsb_worker_config *config, mlsb_worker **out)
         setError("stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(MLSB_ERR_CUDA);
     }
+    {
+        const char *mode = getenv("MLSB_SYNC");
+        w->blockingSync = mode != nullptr && strcmp(mode, "block") == 0;
+        if (cudaEventCreateWithFlags(&w->syncEvent, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
+        {
+            setError("event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(MLSB_ERR_CUDA);
+        }
+    }
     if (cudaMalloc(&w->splats, (size_t) config->maxSplats * sizeof(mlsb_splat)) != cudaSuccess)
     {
         setError("cudaMalloc(splats) failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -199,6 +221,7 @@ void mlsb_worker_destroy(mlsb_worker *w)
     cudaFree(w->scanStatus);
     cudaFree(w->scanTicket);
     if (w->copyEvent) cudaEventDestroy(w->copyEvent);
+    if (w->syncEvent) cudaEventDestroy(w->syncEvent);
     if (w->stream) cudaStreamDestroy(w->stream);
     if (w->copyStream) cudaStreamDestroy(w->copyStream);
     delete w;

@@ -144,6 +144,9 @@ struct mlsb_worker
     std::vector<mlsb::TimedSpan> pendingSpans;
     std::vector<cudaEvent_t> eventPool;
     uint64_t launches = 0;
+    // host waits: spin (lowest latency) or block on an event (frees the core; MLSB_SYNC=block)
+    bool blockingSync = false;
+    cudaEvent_t syncEvent = nullptr;
 };
 
 namespace mlsb
@@ -164,6 +167,7 @@ private:
 };
 
 int statId(mlsb_worker *w, const char *name);
+int waitStream(mlsb_worker *w);   // host wait for the worker's compute stream
 void collectStats(mlsb_worker *w);   // requires the stream to be idle
 
 // sort.cu
@@ -174,8 +178,10 @@ void sortScratchFree(SortScratch &s);
 int radixSortPairs(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n, uint32_t bits,
                    int *result, const char *statName);
 // Same, with the element count min(*nDev, n) read on the device (grids are sized for n).
+// identityValues: values[0] is not read; the input value of element i is i.
 int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n,
-                              const uint32_t *nDev, uint32_t bits, int *result, const char *statName);
+                              const uint32_t *nDev, uint32_t bits, int *result, const char *statName,
+                              bool identityValues);
 
 // octree.cu
 int octreeAlloc(mlsb_worker *w);

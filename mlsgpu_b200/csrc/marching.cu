@@ -392,7 +392,6 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
         if (kx == 0 || ky == 0 || kx == P.top.x || ky == P.top.y || kz == P.top.z) key |= 1u << (3 * P.keyBits);
         P.unwelded[vBase + j] = pos;
         P.keys[vBase + j] = key;
-        P.vidx[vBase + j] = vBase + j;
     }
     // ---- ... and one thread per index ----
     for (uint32_t j = tid; j < numIdx; j += kGenThreads)
@@ -693,7 +692,7 @@ int shipBlock(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t s
     int cur = 0;
     MLSB_TRY(radixSortPairsDeviceCount(w, w->vertKeys, w->vertIdx, (uint32_t) w->vertexSpace,
                                        w->marchCounters + CTR_VERTS, 3 * G.keyBits + 1, &cur,
-                                       "kernel.marching.sortVertices.time"));
+                                       "kernel.marching.sortVertices.time", true));
 
     WeldParams W;
     W.keys = w->vertKeys[cur];
@@ -730,7 +729,7 @@ int shipBlock(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t s
         ScopedStat st(w, "kernel.marching.readback.time", 0);
         MLSB_CUDA(cudaMemcpyAsync(w->hostCounters, w->marchCounters, CTR_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     }
-    MLSB_CUDA(cudaStreamSynchronize(s));
+    MLSB_TRY(waitStream(w));
     const uint32_t *hc = w->hostCounters;
     if (hc[CTR_OVERFLOW] || hc[CTR_VERTS] > w->vertexSpace || hc[CTR_INDICES] > w->indexSpace) return MLSB_ERR_OVERFLOW;
     if (hc[CTR_VERTS] == 0) return MLSB_OK;
@@ -748,7 +747,7 @@ int shipBlock(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t s
         MLSB_CUDA(cudaMemcpyAsync(hKeys, w->weldedKeys + sizes.numInternalVertices, numExternal * sizeof(uint64_t),
                                   cudaMemcpyDeviceToHost, s));
     MLSB_CUDA(cudaMemcpyAsync(hVerts, w->welded, sizes.numVertices * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    MLSB_CUDA(cudaStreamSynchronize(s));
+    MLSB_TRY(waitStream(w));
     if (sink) sink(&sizes, blob, user);
     return MLSB_OK;
 }
@@ -798,7 +797,7 @@ int marchingGenerate(mlsb_worker *w, bool useMls, const float *hostField, const 
     }
     if (size[0] < 2 || size[1] < 2 || size[2] < 2)
     {
-        MLSB_CUDA(cudaStreamSynchronize(w->stream));
+        MLSB_TRY(waitStream(w));
         return MLSB_OK;
     }
     return shipRange(w, pitch, zStride, size, 0, size[2] - 1, keyOffset, sink, user);

@@ -124,14 +124,23 @@ sortOnesweepKernel(const uint32_t *__restrict__ keysIn, const uint32_t *__restri
     else
     {
         *st = kStFlagAggregate | tileCount;
+        // walk back over the predecessors, four status words in flight at a time
         int t = (int) tile - 1;
-        while (true)
+        bool done = false;
+        while (!done)
         {
-            uint32_t v;
-            do { v = status[(size_t) t * kRadix + d]; } while ((v & kStFlagMask) == 0);
-            exclusive += v & ~kStFlagMask;
-            if ((v & kStFlagMask) == kStFlagPrefix) break;
-            t--;
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = t - k >= 0 ? status[(size_t) (t - k) * kRadix + d] : (2u << 30) /* empty prefix */;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                if (done) break;
+                while ((v[k] & kStFlagMask) == 0) v[k] = status[(size_t) (t - k) * kRadix + d];
+                exclusive += v[k] & ~kStFlagMask;
+                done = (v[k] & kStFlagMask) == kStFlagPrefix;
+            }
+            t -= 4;
         }
         *st = kStFlagPrefix | (exclusive + tileCount);
     }
@@ -152,7 +161,7 @@ sortOnesweepKernel(const uint32_t *__restrict__ keysIn, const uint32_t *__restri
             uint32_t dd = (key[k] >> shift) & mask;
             uint32_t pos = sDigitStart[dd] + sWarpCnt[warp][dd] + rank[k];
             sKeys[pos] = key[k];
-            sVals[pos] = valsIn[idx];
+            sVals[pos] = valsIn ? valsIn[idx] : idx;
         }
     }
     __syncthreads();
@@ -174,28 +183,29 @@ int sortScratchAlloc(SortScratch &s, size_t maxItems, uint32_t maxPasses)
     s.maxPasses = maxPasses;
     size_t tiles = divUp(maxItems, (size_t) kSortTile) + 1;
     s.statusWordsPerPass = tiles * kRadix;
-    MLSB_CUDA(cudaMalloc(&s.hist, (size_t) maxPasses * kRadix * sizeof(uint32_t)));
-    MLSB_CUDA(cudaMalloc(&s.status, (size_t) maxPasses * s.statusWordsPerPass * sizeof(uint32_t)));
-    MLSB_CUDA(cudaMalloc(&s.tickets, maxPasses * sizeof(uint32_t)));
+    // one allocation [hist | tickets | status] so that a sort needs a single memset
+    const size_t words = (size_t) maxPasses * kRadix + 64 + (size_t) maxPasses * s.statusWordsPerPass;
+    MLSB_CUDA(cudaMalloc(&s.hist, words * sizeof(uint32_t)));
+    s.tickets = s.hist + (size_t) maxPasses * kRadix;
+    s.status = s.tickets + 64;
     return MLSB_OK;
 }
 
 void sortScratchFree(SortScratch &s)
 {
     cudaFree(s.hist);
-    cudaFree(s.status);
-    cudaFree(s.tickets);
     s = SortScratch();
 }
 
 int radixSortPairs(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n, uint32_t bits,
                    int *result, const char *statName)
 {
-    return radixSortPairsDeviceCount(w, keys, values, n, nullptr, bits, result, statName);
+    return radixSortPairsDeviceCount(w, keys, values, n, nullptr, bits, result, statName, false);
 }
 
 int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n,
-                              const uint32_t *nDev, uint32_t bits, int *result, const char *statName)
+                              const uint32_t *nDev, uint32_t bits, int *result, const char *statName,
+                              bool identityValues)
 {
     *result = 0;
     if (n == 0 || bits == 0) return MLSB_OK;
@@ -204,10 +214,9 @@ int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *value
     MLSB_REQUIRE(n <= s.maxItems && passes <= s.maxPasses && passes <= 4, MLSB_ERR_LENGTH, "sort scratch too small");
     ScopedStat stat(w, statName, 1 + passes);
     uint32_t tiles = divUp(n, (uint32_t) kSortTile);
-    MLSB_CUDA(cudaMemsetAsync(s.hist, 0, (size_t) passes * kRadix * sizeof(uint32_t), w->stream));
-    MLSB_CUDA(cudaMemsetAsync(s.tickets, 0, passes * sizeof(uint32_t), w->stream));
-    for (uint32_t p = 0; p < passes; p++)
-        MLSB_CUDA(cudaMemsetAsync(s.status + p * s.statusWordsPerPass, 0, (size_t) tiles * kRadix * sizeof(uint32_t), w->stream));
+    // status of pass p lives at s.status + p * tiles * 256: compact, so one memset covers everything
+    const size_t statusStride = (size_t) tiles * kRadix;
+    MLSB_CUDA(cudaMemsetAsync(s.hist, 0, ((size_t) s.maxPasses * kRadix + 64 + passes * statusStride) * sizeof(uint32_t), w->stream));
     uint32_t histBlocks = min(divUp(n, 256u * 8u), 148u * 8u);
     sortHistogramKernel<<<histBlocks, 256, 0, w->stream>>>(keys[0], n, nDev, s.hist, passes, bits);
     int cur = 0;
@@ -215,8 +224,8 @@ int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *value
     {
         uint32_t wbits = bits - 8 * p < 8 ? bits - 8 * p : 8;
         sortOnesweepKernel<<<tiles, kSortThreads, 0, w->stream>>>(
-            keys[cur], values[cur], keys[cur ^ 1], values[cur ^ 1], n, nDev, 8 * p, (1u << wbits) - 1,
-            s.hist + p * kRadix, s.status + p * s.statusWordsPerPass, s.tickets + p);
+            keys[cur], (p == 0 && identityValues) ? nullptr : values[cur], keys[cur ^ 1], values[cur ^ 1], n, nDev, 8 * p, (1u << wbits) - 1,
+            s.hist + p * kRadix, s.status + p * statusStride, s.tickets + p);
         cur ^= 1;
     }
     w->launches += 1 + passes;

@@ -116,6 +116,7 @@ struct mlsb_worker
     // ---- marching (Marching members, src/marching.cpp:380-405) ----
     uint32_t fieldDim = 0;        // corners per axis the field was allocated for, rounded to 8
     float *field = nullptr;       // [z][y][x], pitch fieldDim
+    uint8_t *blockActive = nullptr;   // [bz][by][bx] per 8x8x8 block of the field: written by the MLS kernel
     uint64_t vertexSpace = 0, indexSpace = 0;
     float4 *unwelded = nullptr;
     uint32_t *vertKeys[2] = {nullptr, nullptr};
@@ -193,7 +194,7 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
 int measureFp32Peak(double *laneInstPerSecond, double *seconds);
 int mlsAlloc(mlsb_worker *w);
 void mlsFree(mlsb_worker *w);
-int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &sw);
+int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &sw, bool recordActive = false);
 
 // marching.cu
 int marchingAlloc(mlsb_worker *w);

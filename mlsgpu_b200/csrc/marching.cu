@@ -174,6 +174,8 @@ struct GenParams
     uint64_t *tileTotals;          // per tile: classify writes (v | i << 21 | cells << 42), scanTiles turns it
                                    // into the tile's exclusive base (v | i << 31)
     uint32_t *tileList;            // non-empty tiles in order; count in counters[CTR_TILES]
+    const uint8_t *blockActive;    // optional [bz][by][bx] hint: 0 = every corner of that 8x8x8 block is NaN
+    uint32_t activeDim;
     const Tables *tables;
 };
 
@@ -255,7 +257,11 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
     for (int c = 0; c < CHUNKS; c++)
     {
         const uint32_t x0 = c * kGenThreads + warp * 32;
-        const bool active = x0 < P.cellsX;     // warp-uniform
+        bool active = x0 < P.cellsX;     // warp-uniform
+        // a cell whose lowest corner lies in a block without splats is invalid: if none of the four
+        // blocks this warp spans has any, skip its rows altogether (tiles are aligned to block rows)
+        if (active && P.blockActive != nullptr)
+            active = *reinterpret_cast<const uint32_t *>(P.blockActive + ((size_t) (z >> 3) * P.activeDim + (y0 >> 3)) * P.activeDim + (x0 >> 3)) != 0;
         RowMasks p0 = {0, 0, 0, 0}, p1 = {0, 0, 0, 0};
         if (active)
         {
@@ -567,6 +573,11 @@ int marchingAlloc(mlsb_worker *w)
     w->indexSpace = meshCells * kMaxCellIndices;
     MLSB_REQUIRE(w->vertexSpace < (1ull << 31) && w->indexSpace < (1ull << 31), MLSB_ERR_LENGTH, "meshBytes too large");
     MLSB_CUDA(cudaMalloc(&w->field, (size_t) w->fieldDim * w->fieldDim * w->fieldDim * sizeof(float)));
+    {
+        const size_t nb = roundUp(w->fieldDim / kMlsWgs, 4u);
+        MLSB_CUDA(cudaMalloc(&w->blockActive, nb * nb * nb + 16));
+        MLSB_CUDA(cudaMemset(w->blockActive, 0, nb * nb * nb + 16));
+    }
     MLSB_CUDA(cudaMalloc(&w->unwelded, (w->vertexSpace + 1) * sizeof(float4)));
     for (int i = 0; i < 2; i++)
     {
@@ -595,6 +606,7 @@ int marchingAlloc(mlsb_worker *w)
 void marchingFree(mlsb_worker *w)
 {
     cudaFree(w->field);
+    cudaFree(w->blockActive);
     cudaFree(w->unwelded);
     for (int i = 0; i < 2; i++)
     {
@@ -627,8 +639,8 @@ uint32_t bitLength(uint32_t v)
 // shipOut with zTop = zFirst, zMax = zLast).  Returns MLSB_ERR_OVERFLOW if the block does not
 // fit in the worker's mesh memory (the caller then splits the z range, as
 // src/marching.cpp:651-704 does with its per-slice histogram).
-int shipBlock(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t size[3], uint32_t zFirst, uint32_t zLast,
-              const uint32_t keyOffset[3], mlsb_mesh_sink sink, void *user)
+int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, const uint32_t size[3], uint32_t zFirst,
+              uint32_t zLast, const uint32_t keyOffset[3], mlsb_mesh_sink sink, void *user)
 {
     cudaStream_t s = w->stream;
     const uint32_t cellsX = size[0] - 1, cellsY = size[1] - 1;
@@ -663,6 +675,8 @@ int shipBlock(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t s
     G.indices = w->indices;
     G.counters = w->marchCounters;
     G.tileTotals = w->tileTotals;
+    G.blockActive = useActive ? w->blockActive : nullptr;
+    G.activeDim = roundUp(w->fieldDim / kMlsWgs, 4u);
     G.tileList = w->tileList;
     G.tables = reinterpret_cast<const Tables *>(w->tables);
     MLSB_REQUIRE(3 * G.keyBits + 1 <= 32, MLSB_ERR_LENGTH, "bin too large for the compact vertex key");
@@ -752,10 +766,10 @@ int shipBlock(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t s
     return MLSB_OK;
 }
 
-int shipRange(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t size[3], uint32_t zFirst, uint32_t zLast,
-              const uint32_t keyOffset[3], mlsb_mesh_sink sink, void *user)
+int shipRange(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, const uint32_t size[3], uint32_t zFirst,
+              uint32_t zLast, const uint32_t keyOffset[3], mlsb_mesh_sink sink, void *user)
 {
-    int st = shipBlock(w, pitch, zStride, size, zFirst, zLast, keyOffset, sink, user);
+    int st = shipBlock(w, useActive, pitch, zStride, size, zFirst, zLast, keyOffset, sink, user);
     if (st != MLSB_ERR_OVERFLOW) return st;
     if (zLast - zFirst <= 1)
     {
@@ -765,8 +779,8 @@ int shipRange(mlsb_worker *w, uint32_t pitch, uint32_t zStride, const uint32_t s
     // Too big for the mesh memory: split the slice range and ship the halves separately; the
     // seam is welded by the consumer through the external vertex keys.
     uint32_t mid = zFirst + (zLast - zFirst) / 2;
-    MLSB_TRY(shipRange(w, pitch, zStride, size, zFirst, mid, keyOffset, sink, user));
-    return shipRange(w, pitch, zStride, size, mid, zLast, keyOffset, sink, user);
+    MLSB_TRY(shipRange(w, useActive, pitch, zStride, size, zFirst, mid, keyOffset, sink, user));
+    return shipRange(w, useActive, pitch, zStride, size, mid, zLast, keyOffset, sink, user);
 }
 
 }  // namespace
@@ -785,7 +799,7 @@ int marchingGenerate(mlsb_worker *w, bool useMls, const float *hostField, const 
     if (useMls)
     {
         mlsb_swathe sw{size[0], size[1], zStride, 0, 0, size[2] - 1};
-        MLSB_TRY(mlsCorners(w, w->field, pitch, sw));
+        MLSB_TRY(mlsCorners(w, w->field, pitch, sw, true));
     }
     else
     {
@@ -800,7 +814,7 @@ int marchingGenerate(mlsb_worker *w, bool useMls, const float *hostField, const 
         MLSB_TRY(waitStream(w));
         return MLSB_OK;
     }
-    return shipRange(w, pitch, zStride, size, 0, size[2] - 1, keyOffset, sink, user);
+    return shipRange(w, useMls, pitch, zStride, size, 0, size[2] - 1, keyOffset, sink, user);
 }
 
 }  // namespace mlsb

@@ -26,6 +26,9 @@ namespace
 #ifndef MLSB_MLS_SLOTS
 #define MLSB_MLS_SLOTS 2
 #endif
+#ifndef MLSB_MLS_VARIANT
+#define MLSB_MLS_VARIANT 3
+#endif
 #ifndef MLSB_MLS_MINBLOCKS
 #define MLSB_MLS_MINBLOCKS 3
 #endif
@@ -50,6 +53,8 @@ struct MlsParams
     uint32_t zFirst;
     float boundaryFactor;
     unsigned long long *work;   // [0] pair tests, [1] hits (COUNT builds only)
+    uint8_t *blockActive;       // optional [bz][by][bx]: 1 where the block has splats (hint for marching)
+    uint32_t activeDimX, activeDimY;
 };
 
 __device__ __forceinline__ uint32_t spread3(uint32_t v)
@@ -176,6 +181,8 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
 
     const uint32_t code = (spread3(wx) | (spread3(wy) << 1) | (spread3(wz) << 2)) >> P.startShift;
     int32_t pos = P.start[code];
+    if (P.blockActive != nullptr && tid == 0)
+        P.blockActive[((size_t) (wz >> 3) * P.activeDimY + blockIdx.y) * P.activeDimX + blockIdx.x] = pos >= 0;
 
     float out[kSlots];
 #pragma unroll
@@ -272,11 +279,17 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
             __syncwarp();
 
             // ---- pair tests over the kept splats, in chain order ----
+#if MLSB_MLS_VARIANT & 1
+            for (int i = 0; i < n; i++)
+            {
+                const float4 s = wPosT[i];
+#else
             float4 sNext = wPosT[0];
             for (int i = 0; i < n; i++)
             {
                 const float4 s = sNext;
                 if (i + 1 < n) sNext = wPosT[i + 1];
+#endif
                 const float pz = __fsub_rn(s.z, cz);
                 const float py = __fsub_rn(s.y, cy);
                 const float t = __fmaf_rn(py, py, __fmul_rn(pz, pz));
@@ -289,6 +302,42 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
                     pp[j] = __fmaf_rn(px[j], px[j], t);
                     hit[j] = pp[j] < s.w;   // <=> pp * invr2 < 0.99f, see hitThreshold()
                 }
+#if MLSB_MLS_VARIANT & 2
+                // One uniform branch per splat; inside it the accumulation runs for every lane with
+                // the weight (and pp, which alone could be non-finite) forced to zero where there is
+                // no hit: adding w = 0 terms is exact, so no divergent region is needed.
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < kSlots; j++) any |= hit[j];
+                if (__any_sync(0xFFFFFFFFu, any))
+                {
+                    const float4 nq = wNormQ[i];
+                    const float invr2 = wInvR[i];
+                    const float u = __fmaf_rn(nq.y, py, __fmul_rn(nq.z, pz));   // shared part of dot3(n, p)
+#pragma unroll
+                    for (int j = 0; j < kSlots; j++)
+                    {
+                        const float d = __fmul_rn(pp[j], invr2);
+                        float w = __fsub_rn(1.0f, d);
+                        w = __fmul_rn(w, w);
+                        w = __fmul_rn(w, w);
+                        w = __fmul_rn(w, nq.w);
+                        w = hit[j] ? w : 0.0f;
+                        const float ppj = hit[j] ? pp[j] : 0.0f;
+                        Accum &a = acc[j];
+                        a.sumW = __fadd_rn(a.sumW, w);
+                        a.sumWpx = __fmaf_rn(w, px[j], a.sumWpx);
+                        a.sumWpy = __fmaf_rn(w, py, a.sumWpy);
+                        a.sumWpz = __fmaf_rn(w, pz, a.sumWpz);
+                        a.sumWnx = __fmaf_rn(w, nq.x, a.sumWnx);
+                        a.sumWny = __fmaf_rn(w, nq.y, a.sumWny);
+                        a.sumWnz = __fmaf_rn(w, nq.z, a.sumWnz);
+                        a.sumWpp = __fmaf_rn(w, ppj, a.sumWpp);
+                        a.sumWpn = __fmaf_rn(w, __fmaf_rn(nq.x, px[j], u), a.sumWpn);
+                        a.hits += hit[j];
+                    }
+                }
+#else
                 // after the cull nearly every kept splat hits somewhere in the brick, so there is
                 // no brick-level vote: only one per slot (a 2x4x4 sub-brick)
                 {
@@ -322,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
                         }
                     }
                 }
+#endif
             }
             __syncwarp();   // the buffer is overwritten by the next batch
         }
@@ -421,7 +471,7 @@ int mlsAlloc(mlsb_worker *w)
 
 void mlsFree(mlsb_worker *w) { cudaFree(w->mlsWork); }
 
-int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &sw)
+int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &sw, bool recordActive)
 {
     MLSB_REQUIRE(w->mlsBound, MLSB_ERR_STATE, "mlsb_mls_set has not been called");
     // src/mls.cpp:108-117
@@ -446,6 +496,8 @@ int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &
     P.zFirst = sw.zFirst;
     P.boundaryFactor = w->boundaryFactor;
     P.work = w->mlsWork;
+    P.blockActive = recordActive ? w->blockActive : nullptr;
+    P.activeDimX = P.activeDimY = roundUp(w->fieldDim / kMlsWgs, 4u);   // rows are read as 32-bit words
     dim3 grid(width / kMlsWgs, height / kMlsWgs, divUp(sw.zLast - sw.zFirst + 1, (uint32_t) kMlsWgs));
     ScopedStat st(w, "kernel.mls.processCorners.time", 1, 1);
     const bool count = w->countWork;

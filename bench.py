@@ -260,7 +260,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--splats", type=int, default=10_000_000)
-    ap.add_argument("--threads", type=int, default=3, help="workers per GPU (--device-threads)")
+    ap.add_argument("--threads", type=int, default=4, help="workers per GPU (--device-threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -373,6 +373,13 @@ def main():
     achieved = 2.0 * inst / mls_per_step / 1e12      # TFLOP/s at 2 flop per lane-instruction
     peak = 2.0 * peak_inst / 1e12
     inst_bytes = len(wl["splats"])
+    # DRAM bytes per processCorners launch from the committed ncu --set full capture (profiles/)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1b_processCorners_ncu.json")) as f:
+            traffic = json.load(f)["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     line = {
         "metric": "Msplats/s", "value": value, "unit": "Msplats/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -383,7 +390,9 @@ def main():
         "clocks": clocks,
         "mls_corners_per_s": corners * args.steps / mls_s if mls_s > 0 else None,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "processCornersKernel",
+                     "traffic": traffic, "traffic_note": "DRAM bytes per launch on a large bin, ncu --set full "
+                     "(profiles/r1b_processCorners_ncu.json); the kernel is FP32-issue-bound, not HBM-bound",
+                     "kernel": "processCornersKernel",
                      "model": "7*T + 16*H FP32 pipe instructions per step (SURVEY 8d), 2 flop each",
                      "pair_tests": int(T), "hits": int(H), "kernel_ms_per_step": 1e3 * mls_per_step,
                      "launches_per_step": mls_n // args.steps,

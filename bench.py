@@ -120,10 +120,15 @@ class Runner:
         self.bins = wl["bins"]
         total = len(wl["splats"])
         self.max_bin = max(b["n"] for b in self.bins)
-        self.workers = [m.Worker(device=device, max_splats=self.max_bin, max_cells=255, mesh_bytes=256 << 20)
-                        for _ in range(threads)]
+        # the native worker group (CopyGroup + DeviceWorkerGroup): `threads` worker threads, bins are
+        # copied straight from the pointer given to submit (pinned host memory or HBM)
+        self.group = m.WorkerGroup(num_workers=threads, stage=False, sink=None, device=device,
+                                   max_splats=self.max_bin, max_cells=255, mesh_bytes=256 << 20)
+        self.workers = self.group.workers
+        # a lone worker for the per-kernel roofline pass (no other kernels on the GPU)
+        self.single = m.Worker(device=device, max_splats=self.max_bin, max_cells=255, mesh_bytes=256 << 20)
         bias = wl["lo"].astype(np.float32) * wl["spacing"]
-        for w in self.workers:
+        for w in self.workers + [self.single]:
             w.set_scale_bias(float(wl["spacing"]), bias)
         self.pinned = PinnedBuffer(m.SPLAT_DTYPE, total)
         self.pinned.array[:] = wl["splats"]
@@ -141,37 +146,35 @@ class Runner:
                 self.mesh_bytes += 12 * int(s.numVertices) + 12 * int(s.numTriangles) + 8 * int(s.numVertices - s.numInternalVertices)
         self.sink = MESH_SINK(sink)
 
-    def _work(self, wi, from_host, single=False):
-        from mlsgpu_b200.capi import lib, _check
-        w = self.workers[wi]
-        L = lib()
-        for b in (self.bins if single else self.bins[wi::len(self.workers)]):
-            if from_host:
-                src = self.pinned.ptr.value + 32 * b["first"]
-            else:
-                src = self.resident.ptr.value + 32 * b["first"]
-            _check(L.mlsb_splats_upload_async(w.h, src, 0, b["n"]))
-            _check(L.mlsb_worker_process_bin(w.h, 0, b["n"], b["size"].ctypes.data, b["offset"].ctypes.data, self.sink, None))
-
     def step(self, from_host, single=False):
-        """One pass over all bins.  single=True: worker 0 alone (kernels do not overlap, which is
-        what a per-kernel roofline measurement needs)."""
-        if single or len(self.workers) == 1:
-            self._work(0, from_host, single=True)
+        """One pass over all bins.  single=True: the lone worker (kernels do not overlap, which is
+        what a per-kernel roofline measurement needs); otherwise the worker group."""
+        from mlsgpu_b200.capi import lib, _check
+        base = self.pinned.ptr.value if from_host else self.resident.ptr.value
+        if single:
+            L, w = lib(), self.single
+            for b in self.bins:
+                _check(L.mlsb_splats_upload_async(w.h, base + 32 * b["first"], 0, b["n"]))
+                _check(L.mlsb_worker_process_bin(w.h, 0, b["n"], b["size"].ctypes.data, b["offset"].ctypes.data,
+                                                 self.sink, None))
             return
-        ts = [threading.Thread(target=self._work, args=(i, from_host)) for i in range(len(self.workers))]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
+        before = self.group.counters()[2]
+        for i, b in enumerate(self.bins):
+            self.group.submit((base + 32 * b["first"], b["n"]), b["size"], b["offset"], tag=i)
+        self.group.wait()
+        self.mesh_bytes += self.group.counters()[2] - before
 
     def sync(self):
-        for w in self.workers:
+        self.group.wait()
+        for w in self.workers + [self.single]:
             w.synchronize()
+
+    def all_workers(self):
+        return self.workers + [self.single]
 
     def stat_sum(self, names):
         tot, cnt = 0.0, 0
-        for w in self.workers:
+        for w in self.all_workers():
             for n in names:
                 s, c = w.statistic(n)
                 tot += s
@@ -179,8 +182,8 @@ class Runner:
         return tot, cnt
 
     def close(self):
-        for w in self.workers:
-            w.close()
+        self.group.close()
+        self.single.close()
         self.resident.free()
         self.pinned.free()
 
@@ -298,13 +301,13 @@ def main():
         torch.cuda.synchronize()
 
     def timed(from_host, steps, profile, single=False):
-        for w in runner.workers:
+        for w in runner.all_workers():
             w.set_profiling(1 if profile else 0)
             w.reset_statistics()
         runner.mesh_bytes = 0
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = sum(w.launch_count for w in runner.workers)
+        l0 = sum(w.launch_count for w in runner.all_workers())
         e0.record()
         t0 = time.perf_counter()
         for _ in range(steps):
@@ -314,7 +317,7 @@ def main():
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
-        launches = sum(w.launch_count for w in runner.workers) - l0
+        launches = sum(w.launch_count for w in runner.all_workers()) - l0
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -322,14 +325,14 @@ def main():
         return ms, wall * 1e3, launches
 
     # ---- work model (untimed): T pair tests and H hits of one step ----
-    for w in runner.workers:
+    for w in runner.all_workers():
         w.set_work_counting(True)
         w.reset_statistics()
     runner.step(False)
     runner.sync()
-    T = sum(w.mls_work()[0] for w in runner.workers)
-    H = sum(w.mls_work()[1] for w in runner.workers)
-    for w in runner.workers:
+    T = sum(w.mls_work()[0] for w in runner.all_workers())
+    H = sum(w.mls_work()[1] for w in runner.all_workers())
+    for w in runner.all_workers():
         w.set_work_counting(False)
     corners = sum(int(np.prod([-(-int(v) // 8) * 8 for v in b["size"]])) for b in wl["bins"])
 
@@ -350,7 +353,7 @@ def main():
     clocks = sampler.stop()
 
     # ---- per-stage breakdown (untimed pass with every kernel timed) ----
-    for w in runner.workers:
+    for w in runner.all_workers():
         w.set_profiling(2)
         w.reset_statistics()
     runner.step(False)
@@ -362,7 +365,7 @@ def main():
         for name in OCTREE_STATS + [MLS_STAT] + MARCHING_STATS:
             s_, c_ = runner.stat_sum([name])
             log("  %-44s %9.3f ms/step  %5d launches" % (name, 1e3 * s_, c_))
-    for w in runner.workers:
+    for w in runner.all_workers():
         w.set_profiling(0)
 
     total_splats = args.splats * world

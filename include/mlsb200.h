@@ -178,6 +178,36 @@ MLSB_API int mlsb_worker_process_bin(mlsb_worker *w, uint32_t firstSplat, uint32
                                      const uint32_t size[3], const int32_t offset[3],
                                      mlsb_mesh_sink sink, void *user);
 
+/* ---- worker group: CopyGroup + DeviceWorkerGroup (src/workers.h:136-438) ------------------ */
+
+typedef struct mlsb_group mlsb_group;
+
+/* Like mlsb_mesh_sink, plus the tag given at submission (the ChunkId / bin identity that
+ * OutputGeneratorBuilder carries, src/workers.h:488-509).  Calls are serialised across workers
+ * but come from the group's worker threads. */
+typedef void (*mlsb_group_sink)(uint64_t tag, const mlsb_mesh_sizes *sizes, const void *hostBlob, void *user);
+
+/* numWorkers worker threads on config->device, each with its own mlsb_worker (the reference's
+ * --device-threads), fed by a bounded queue of queueDepth bins (0 = 2 x numWorkers).
+ * stageSplats != 0: every worker copies the bin's splats into its own pinned staging buffer before
+ * the asynchronous H2D, so the caller's memory (pageable or pinned) is free again when
+ * mlsb_group_wait returns or the queue slot is consumed — CopyGroupBase::Worker::operator(),
+ * src/workers.cpp:377-418.  stageSplats == 0: the pointer given to submit is copied directly
+ * (pinned host or device memory) and must stay valid until the bin has been processed. */
+MLSB_API int mlsb_group_create(const mlsb_worker_config *config, uint32_t numWorkers, uint32_t queueDepth,
+                               int stageSplats, mlsb_group_sink sink, void *user, mlsb_group **out);
+MLSB_API void mlsb_group_destroy(mlsb_group *g);
+/* Queues one bin (WorkerGroup::get + push, src/worker_group.h:137-199); blocks while the queue is
+ * full.  size = corners per axis, offset = low extent of the bin in the full grid. */
+MLSB_API int mlsb_group_submit(mlsb_group *g, const mlsb_splat *splats, uint32_t numSplats,
+                               const uint32_t size[3], const int32_t offset[3], uint64_t tag);
+/* Blocks until every queued bin has been processed; returns the first error any worker hit. */
+MLSB_API int mlsb_group_wait(mlsb_group *g);
+/* Worker i of the group (to set scale/bias, boundary limit, profiling; not while bins are queued). */
+MLSB_API int mlsb_group_worker(mlsb_group *g, uint32_t index, mlsb_worker **worker);
+/* Totals since creation: bins and splats processed, bytes of mesh handed to the sink. */
+MLSB_API int mlsb_group_counters(mlsb_group *g, uint64_t *bins, uint64_t *splats, uint64_t *meshBytes);
+
 /* ---- statistics (--statistics-cl, src/statistics_cl.cpp) -------------------------------- */
 
 /* CUDA-event timing under the reference's statistic names (kernel.octree.*.time,

@@ -7,8 +7,8 @@ The product is ``libmlsb200.so`` (hand-written CUDA for sm_100a behind the C ABI
 There is no CPU fallback: importing works anywhere, but every compute call needs the built
 library and a CUDA device and raises :class:`MlsbError` otherwise.
 """
-from .capi import (MlsbError, SPLAT_DTYPE, Worker, WorkerConfig, device_count, lib, library_path,
+from .capi import (MlsbError, SPLAT_DTYPE, Worker, WorkerConfig, WorkerGroup, device_count, lib, library_path,
                    marching_tables, measure_fp32_peak, version)
 
-__all__ = ["MlsbError", "SPLAT_DTYPE", "Worker", "WorkerConfig", "device_count", "lib", "library_path",
+__all__ = ["MlsbError", "SPLAT_DTYPE", "Worker", "WorkerConfig", "WorkerGroup", "device_count", "lib", "library_path",
            "marching_tables", "measure_fp32_peak", "version"]

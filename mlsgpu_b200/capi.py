@@ -40,6 +40,7 @@ class MeshSizes(C.Structure):
 
 
 MESH_SINK = C.CFUNCTYPE(None, C.POINTER(MeshSizes), C.c_void_p, C.c_void_p)
+GROUP_SINK = C.CFUNCTYPE(None, C.c_uint64, C.POINTER(MeshSizes), C.c_void_p, C.c_void_p)
 
 # every symbol include/mlsb200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -69,6 +70,12 @@ API = {
     "mlsb_mesh_host_bytes": (C.c_uint64, [C.POINTER(MeshSizes)]),
     "mlsb_marching_tables": (C.c_int, [_P, _P, _P, _P]),
     "mlsb_worker_process_bin": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, MESH_SINK, _P]),
+    "mlsb_group_create": (C.c_int, [C.POINTER(WorkerConfig), C.c_uint32, C.c_uint32, C.c_int, GROUP_SINK, _P, C.POINTER(_P)]),
+    "mlsb_group_destroy": (None, [_P]),
+    "mlsb_group_submit": (C.c_int, [_P, _P, C.c_uint32, _P, _P, C.c_uint64]),
+    "mlsb_group_wait": (C.c_int, [_P]),
+    "mlsb_group_worker": (C.c_int, [_P, C.c_uint32, C.POINTER(_P)]),
+    "mlsb_group_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "mlsb_worker_set_profiling": (C.c_int, [_P, C.c_int]),
     "mlsb_worker_get_statistic": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "mlsb_worker_reset_statistics": (C.c_int, [_P]),
@@ -203,6 +210,16 @@ class PinnedBuffer:
 class Worker:
     """One worker = one GPU = one host thread (DeviceWorkerGroupBase::Worker)."""
 
+    @classmethod
+    def borrowed(cls, handle, cfg):
+        """A view of a worker owned by a WorkerGroup (never destroyed from here)."""
+        self = cls.__new__(cls)
+        self.cfg = cfg
+        self.h = _P(handle)
+        self._keep = []
+        self._borrowed = True
+        return self
+
     def __init__(self, device=0, max_levels=6, subsampling=3, max_splats=1 << 20, max_cells=255,
                  mesh_bytes=None, shape=0, boundary_limit=1.0):
         if mesh_bytes is None:
@@ -215,9 +232,9 @@ class Worker:
 
     # ---- lifetime --------------------------------------------------------------------------
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "_borrowed", False):
             lib().mlsb_worker_destroy(self.h)
-            self.h = _P()
+        self.h = _P()
 
     def __enter__(self):
         return self
@@ -378,3 +395,75 @@ class Worker:
     @property
     def launch_count(self):
         return int(lib().mlsb_worker_launch_count(self.h))
+
+
+class WorkerGroup:
+    """CopyGroup + DeviceWorkerGroup: `num_workers` native worker threads on one GPU fed by a bounded
+    queue of bins (mlsb_group_*).  `sink(tag, block)` is called, serialised, with each mesh block
+    (same dict layout as Worker.marching_generate); sink=None only counts bytes."""
+
+    def __init__(self, num_workers=4, queue_depth=0, stage=True, sink=None, device=0, max_levels=6, subsampling=3,
+                 max_splats=1 << 20, max_cells=255, mesh_bytes=None, shape=0, boundary_limit=1.0):
+        if mesh_bytes is None:
+            mesh_bytes = max(64 << 20, max_cells * max_cells * 872)
+        self.cfg = WorkerConfig(device, max_levels, subsampling, max_splats, max_cells, mesh_bytes, shape, boundary_limit)
+        self.num_workers = num_workers
+        self._keep = []
+        if sink is not None:
+            def cb(tag, sizes_p, blob, _user):
+                blocks = []
+                Worker._collector(blocks)(sizes_p, blob, None)
+                sink(int(tag), blocks[0])
+            self._cb = GROUP_SINK(cb)
+        else:
+            self._cb = GROUP_SINK()
+        self.h = _P()
+        _check(lib().mlsb_group_create(C.byref(self.cfg), num_workers, queue_depth, int(stage), self._cb, None,
+                                       C.byref(self.h)))
+
+    def worker(self, i):
+        h = _P()
+        _check(lib().mlsb_group_worker(self.h, i, C.byref(h)))
+        return Worker.borrowed(h.value, self.cfg)
+
+    @property
+    def workers(self):
+        return [self.worker(i) for i in range(self.num_workers)]
+
+    def submit(self, splats, size, offset, tag=0):
+        """splats: numpy array (host) — kept alive until wait() — or (device_ptr, count)."""
+        size = _arr3(size, np.uint32)
+        offset = _arr3(offset, np.int32)
+        if isinstance(splats, tuple):
+            ptr, n = splats
+        else:
+            assert splats.dtype == SPLAT_DTYPE and splats.flags.c_contiguous
+            self._keep.append(splats)
+            ptr, n = splats.ctypes.data, len(splats)
+        _check(lib().mlsb_group_submit(self.h, ptr, n, size.ctypes.data, offset.ctypes.data, tag))
+
+    def wait(self):
+        _check(lib().mlsb_group_wait(self.h))
+        self._keep.clear()
+
+    def counters(self):
+        b, s, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib().mlsb_group_counters(self.h, C.byref(b), C.byref(s), C.byref(m)))
+        return b.value, s.value, m.value
+
+    def close(self):
+        if self.h:
+            lib().mlsb_group_destroy(self.h)
+            self.h = _P()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -193,6 +193,7 @@ int mlsb_worker_create(const mlsb_worker_config *config, mlsb_worker **out)
     if ((st = sortScratchAlloc(w->sort, maxSort, 4)) != MLSB_OK) return fail(st);
     uint64_t cells = (uint64_t) config->maxCells * config->maxCells * config->maxCells;
     uint64_t words = std::max<uint64_t>({divUp<uint64_t>(cells, 256) + 2, divUp<uint64_t>(w->numStartMax, 2048) + 2,
+                                         divUp<uint64_t>(config->maxSplats, 256) + 2,
                                          divUp<uint64_t>(w->vertexSpace, 1024) + 2});
     w->scanStatusWords = (uint32_t) words;
     if (cudaMalloc(&w->scanStatus, words * sizeof(uint64_t)) != cudaSuccess

@@ -54,13 +54,25 @@ __device__ __forceinline__ float pointBoxDist2(float px, float py, float pz, flo
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// The reference writes exactly 8 (key, id) slots per splat, UINT_MAX in the rejected ones, and sorts
+// all 8N.  Here only the accepted entries are written, packed in (splat, slot) order through a
+// decoupled look-back over the per-CTA counts, and their number goes to *numValid: the sort, the
+// run detection and the command emission then touch 2-4x fewer elements, with identical results
+// (rejected slots sort to the end and are skipped by writeSplatIds, kernels/octree.cl:266).
 __global__ void __launch_bounds__(256) writeEntriesKernel(uint32_t *__restrict__ keys, uint32_t *__restrict__ values,
                                                           mlsb_splat *__restrict__ splats, int3 bias, LevelInfo lv,
-                                                          uint32_t firstSplat, uint32_t numSplats)
+                                                          uint32_t firstSplat, uint32_t numSplats,
+                                                          volatile uint64_t *status, uint32_t *ticket, uint32_t *numValid)
 {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= numSplats) return;
-    uint32_t gid = g + firstSplat;
+    __shared__ uint32_t sScan[33];
+    __shared__ uint32_t sTile;
+    __shared__ uint64_t sPrefix;
+    if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sTile;
+    const uint32_t g = tile * blockDim.x + threadIdx.x;
+    const bool inRange = g < numSplats;
+    const uint32_t gid = (inRange ? g : 0) + firstSplat;
     float4 pr = *reinterpret_cast<const float4 *>(&splats[gid]);
 
     // prepare(), kernels/octree.cl:79-89
@@ -74,7 +86,7 @@ __global__ void __launch_bounds__(256) writeEntriesKernel(uint32_t *__restrict__
     int ilx = max(lox - bias.x, 0) >> shift, ily = max(loy - bias.y, 0) >> shift, ilz = max(loz - bias.z, 0) >> shift;
 
     float radius2 = __fmul_rn(pr.w, pr.w);
-    splats[gid].radius = __fdiv_rn(1.0f, radius2);
+    if (inRange) splats[gid].radius = __fdiv_rn(1.0f, radius2);
     radius2 = __fmul_rn(radius2, 1.00001f);
     uint32_t levelOffset = lv.offsets[shift];
     int bound = 1 << (lv.maxShift - shift);
@@ -90,20 +102,39 @@ __global__ void __launch_bounds__(256) writeEntriesKernel(uint32_t *__restrict__
         float blz = (float) ((int) ((uint32_t) az << shift) + bias.z), bhz = (float) ((int) ((uint32_t) (az + 1) << shift) + bias.z);
         bool isect = pointBoxDist2(pr.x, pr.y, pr.z, blx, bly, blz, bhx, bhy, bhz) < radius2;
         isect = isect && ax < bound && ay < bound && az < bound;
-        k[o] = isect ? makeCode(ax, ay, az) + levelOffset : 0xFFFFFFFFu;
+        k[o] = (isect && inRange) ? makeCode(ax, ay, az) + levelOffset : 0xFFFFFFFFu;
     }
-    uint4 *kout = reinterpret_cast<uint4 *>(keys + 8 * (size_t) g);
-    uint4 *vout = reinterpret_cast<uint4 *>(values + 8 * (size_t) g);
-    kout[0] = make_uint4(k[0], k[1], k[2], k[3]);
-    kout[1] = make_uint4(k[4], k[5], k[6], k[7]);
-    vout[0] = make_uint4(gid, gid, gid, gid);
-    vout[1] = make_uint4(gid, gid, gid, gid);
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int o = 0; o < 8; o++) cnt += k[o] != 0xFFFFFFFFu;
+    uint32_t total;
+    const uint32_t excl = blockExclusiveScan(cnt, sScan, &total);
+    if (threadIdx.x < 32)
+    {
+        const uint64_t p = lookbackExclusive(status, tile, total);
+        if (threadIdx.x == 0)
+        {
+            sPrefix = p;
+            if (tile == gridDim.x - 1) *numValid = (uint32_t) (p + total);
+        }
+    }
+    __syncthreads();
+    uint32_t dst = (uint32_t) sPrefix + excl;
+#pragma unroll
+    for (int o = 0; o < 8; o++)
+        if (k[o] != 0xFFFFFFFFu)
+        {
+            keys[dst] = k[o];
+            values[dst] = gid;
+            dst++;
+        }
 }
 
 // First and last sorted position of each key (boundaries of equal-key runs).
-__global__ void __launch_bounds__(256) findRunsKernel(const uint32_t *__restrict__ keys, uint32_t numEntries,
+__global__ void __launch_bounds__(256) findRunsKernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ numValid,
                                                       int32_t *__restrict__ runFirst, int32_t *__restrict__ runLast)
 {
+    const uint32_t numEntries = *numValid;
     uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= numEntries) return;
     uint32_t cur = keys[pos];
@@ -173,8 +204,10 @@ scanRunsKernel(const int32_t *__restrict__ runFirst, const int32_t *__restrict__
 // writeSplatIds, kernels/octree.cl:256-279, with commandMap computed in place.
 __global__ void __launch_bounds__(256) emitCommandsKernel(int32_t *__restrict__ commands, const uint32_t *__restrict__ keys,
                                                           const uint32_t *__restrict__ ids,
-                                                          const uint32_t *__restrict__ runIndex, uint32_t numEntries)
+                                                          const uint32_t *__restrict__ runIndex,
+                                                          const uint32_t *__restrict__ numValid)
 {
+    const uint32_t numEntries = *numValid;
     uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= numEntries) return;
     uint32_t key = keys[pos];
@@ -286,14 +319,20 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
     {
         {
             ScopedStat st(w, "kernel.octree.writeEntries.time");
-            writeEntriesKernel<<<divUp(numSplats, 256u), 256, 0, s>>>(
+            const uint32_t tiles = divUp(numSplats, 256u);
+            MLSB_REQUIRE(tiles <= w->scanStatusWords, MLSB_ERR_LENGTH, "scan status too small");
+            MLSB_CUDA(cudaMemsetAsync(w->scanStatus, 0, (size_t) tiles * sizeof(uint64_t), s));
+            MLSB_CUDA(cudaMemsetAsync(w->scanTicket, 0, 4 * sizeof(uint32_t), s));
+            writeEntriesKernel<<<tiles, 256, 0, s>>>(
                 w->entryKeys[0], w->entryValues[0], w->splats, make_int3(offset[0], offset[1], offset[2]), lv,
-                firstSplat, numSplats);
+                firstSplat, numSplats, w->scanStatus, w->scanTicket + 1, w->scanTicket + 2);
         }
     }
     int cur = 0;
-    MLSB_TRY(radixSortPairs(w, w->entryKeys, w->entryValues, numEntries, 3 * (maxShift - minShift) + 1, &cur,
-                            "kernel.octree.sort.time"));
+    if (numSplats == 0) MLSB_CUDA(cudaMemsetAsync(w->scanTicket, 0, 4 * sizeof(uint32_t), s));
+    const uint32_t *numValid = w->scanTicket + 2;   // device-side count of accepted entries
+    MLSB_TRY(radixSortPairsDeviceCount(w, w->entryKeys, w->entryValues, numEntries, numValid,
+                                       3 * (maxShift - minShift) + 1, &cur, "kernel.octree.sort.time", false));
     {
         ScopedStat st(w, "kernel.octree.fill.time", 0);
         MLSB_CUDA(cudaMemsetAsync(w->runFirst, 0xFF, (size_t) numStart * sizeof(int32_t), s));
@@ -301,14 +340,14 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
     if (numEntries > 0)
     {
         ScopedStat st(w, "kernel.octree.countCommands.time");
-        findRunsKernel<<<divUp(numEntries, 256u), 256, 0, s>>>(w->entryKeys[cur], numEntries, w->runFirst, w->runLast);
+        findRunsKernel<<<divUp(numEntries, 256u), 256, 0, s>>>(w->entryKeys[cur], numValid, w->runFirst, w->runLast);
     }
     {
         ScopedStat st(w, "kernel.octree.scan.time");
         uint32_t tiles = divUp(numStart, (uint32_t) (kScanThreads * kScanItems));
         MLSB_REQUIRE(tiles <= w->scanStatusWords, MLSB_ERR_LENGTH, "scan status too small");
         MLSB_CUDA(cudaMemsetAsync(w->scanStatus, 0, (size_t) tiles * sizeof(uint64_t), s));
-        MLSB_CUDA(cudaMemsetAsync(w->scanTicket, 0, sizeof(uint32_t), s));
+        MLSB_CUDA(cudaMemsetAsync(w->scanTicket, 0, sizeof(uint32_t), s));   // ticket 0 only: [2] holds numValid
         scanRunsKernel<<<tiles, kScanThreads, 0, s>>>(w->runFirst, w->runLast, numStart, w->runIndex, w->runStart,
                                                       w->jumpPos, w->scanStatus, w->scanTicket);
     }
@@ -316,7 +355,7 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
     {
         ScopedStat st(w, "kernel.octree.writeSplatIds.time");
         emitCommandsKernel<<<divUp(numEntries, 256u), 256, 0, s>>>(w->commands, w->entryKeys[cur], w->entryValues[cur],
-                                                                   w->runIndex, numEntries);
+                                                                   w->runIndex, numValid);
     }
     {
         ScopedStat st(w, "kernel.octree.writeStart.time");

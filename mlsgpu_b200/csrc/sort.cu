@@ -13,9 +13,9 @@ namespace mlsb
 namespace
 {
 
-constexpr int kSortThreads = 256;
+constexpr int kSortThreadsSmall = 256, kSortThreadsLarge = 1024;
+constexpr uint32_t kSortLargeThreshold = 3u << 20;   // elements (host-side bound) from which large tiles are used
 constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortThreads * kSortItems;   // 4096
 constexpr int kRadix = 256;
 constexpr uint32_t kStFlagAggregate = 1u << 30;
 constexpr uint32_t kStFlagPrefix = 2u << 30;
@@ -46,17 +46,23 @@ __global__ void __launch_bounds__(256) sortHistogramKernel(const uint32_t *__res
         if (sHist[i]) atomicAdd(&hist[i], sHist[i]);
 }
 
-__global__ void __launch_bounds__(kSortThreads)
+// THREADS = 256 (4096-key tiles: plenty of CTAs for the ~1 M-element sorts of a typical bin) or
+// 1024 (16384-key tiles, one CTA per SM: with hundreds of small tiles in flight the look-back chain
+// — one status word per tile and digit — becomes the bottleneck of multi-million-element sorts).
+template <int THREADS> __global__ void __launch_bounds__(THREADS)
 sortOnesweepKernel(const uint32_t *__restrict__ keysIn, const uint32_t *__restrict__ valsIn,
                    uint32_t *__restrict__ keysOut, uint32_t *__restrict__ valsOut, uint32_t nHost,
                    const uint32_t *__restrict__ nDev, uint32_t shift, uint32_t mask, const uint32_t *__restrict__ hist,
                    volatile uint32_t *status, uint32_t *ticket)
 {
-    __shared__ uint32_t sWarpCnt[kSortThreads / 32][kRadix];
-    __shared__ uint32_t sKeys[kSortTile];
-    __shared__ uint32_t sVals[kSortTile];
-    __shared__ uint32_t sDigitStart[kRadix];
-    __shared__ uint32_t sGlobalBase[kRadix];
+    constexpr int kSortThreads = THREADS;
+    constexpr int kSortTile = THREADS * kSortItems;
+    extern __shared__ uint32_t sortSmem[];
+    uint32_t(*sWarpCnt)[kRadix] = reinterpret_cast<uint32_t(*)[kRadix]>(sortSmem);
+    uint32_t *sKeys = sortSmem + (THREADS / 32) * kRadix;
+    uint32_t *sVals = sKeys + kSortTile;
+    uint32_t *sDigitStart = sVals + kSortTile;
+    uint32_t *sGlobalBase = sDigitStart + kRadix;
     __shared__ uint32_t sScan[33];
     __shared__ uint32_t sTile;
 
@@ -105,21 +111,27 @@ sortOnesweepKernel(const uint32_t *__restrict__ keysIn, const uint32_t *__restri
     }
     __syncthreads();
 
-    // ---- per-digit totals of the tile (thread d owns digit d) ----
-    const uint32_t d = tid;
+    // ---- per-digit totals of the tile (thread d < 256 owns digit d) ----
+    const uint32_t d = tid & (kRadix - 1);
+    const bool owner = tid < kRadix;
     uint32_t tileCount = 0;
-#pragma unroll
-    for (int w = 0; w < kSortThreads / 32; w++)
+    if (owner)
     {
-        uint32_t t = sWarpCnt[w][d];
-        sWarpCnt[w][d] = tileCount;
-        tileCount += t;
+#pragma unroll 8
+        for (int w = 0; w < kSortThreads / 32; w++)
+        {
+            uint32_t t = sWarpCnt[w][d];
+            sWarpCnt[w][d] = tileCount;
+            tileCount += t;
+        }
     }
 
     // ---- decoupled look-back on this digit's chain ----
     uint32_t exclusive = 0;
     volatile uint32_t *st = status + (size_t) tile * kRadix + d;
-    if (tile == 0)
+    if (!owner)
+        ;
+    else if (tile == 0)
         *st = kStFlagPrefix | tileCount;
     else
     {
@@ -146,9 +158,12 @@ sortOnesweepKernel(const uint32_t *__restrict__ keysIn, const uint32_t *__restri
     }
 
     uint32_t digitStart = blockExclusiveScan(tileCount, sScan, (uint32_t *) nullptr);
-    uint32_t histPrefix = blockExclusiveScan(hist[d], sScan, (uint32_t *) nullptr);
-    sDigitStart[d] = digitStart;
-    sGlobalBase[d] = histPrefix + exclusive - digitStart;
+    uint32_t histPrefix = blockExclusiveScan(owner ? hist[d] : 0u, sScan, (uint32_t *) nullptr);
+    if (owner)
+    {
+        sDigitStart[d] = digitStart;
+        sGlobalBase[d] = histPrefix + exclusive - digitStart;
+    }
     __syncthreads();
 
     // ---- scatter into shared memory in sorted order, then stream out coalesced runs ----
@@ -181,8 +196,10 @@ int sortScratchAlloc(SortScratch &s, size_t maxItems, uint32_t maxPasses)
 {
     s.maxItems = maxItems;
     s.maxPasses = maxPasses;
-    size_t tiles = divUp(maxItems, (size_t) kSortTile) + 1;
+    size_t tiles = divUp(maxItems, (size_t) (kSortThreadsSmall * kSortItems)) + 1;
     s.statusWordsPerPass = tiles * kRadix;
+    MLSB_CUDA(cudaFuncSetAttribute(sortOnesweepKernel<kSortThreadsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int) (((kSortThreadsLarge / 32) * kRadix + 2 * kSortThreadsLarge * kSortItems + 2 * kRadix) * sizeof(uint32_t))));
     // one allocation [hist | tickets | status] so that a sort needs a single memset
     const size_t words = (size_t) maxPasses * kRadix + 64 + (size_t) maxPasses * s.statusWordsPerPass;
     MLSB_CUDA(cudaMalloc(&s.hist, words * sizeof(uint32_t)));
@@ -213,7 +230,10 @@ int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *value
     uint32_t passes = divUp(bits, 8u);
     MLSB_REQUIRE(n <= s.maxItems && passes <= s.maxPasses && passes <= 4, MLSB_ERR_LENGTH, "sort scratch too small");
     ScopedStat stat(w, statName, 1 + passes);
-    uint32_t tiles = divUp(n, (uint32_t) kSortTile);
+    const bool large = n >= kSortLargeThreshold;
+    const int threads = large ? kSortThreadsLarge : kSortThreadsSmall;
+    uint32_t tiles = divUp(n, (uint32_t) (threads * kSortItems));
+    const size_t smem = ((size_t) (threads / 32) * kRadix + 2 * (size_t) threads * kSortItems + 2 * kRadix) * sizeof(uint32_t);
     // status of pass p lives at s.status + p * tiles * 256: compact, so one memset covers everything
     const size_t statusStride = (size_t) tiles * kRadix;
     MLSB_CUDA(cudaMemsetAsync(s.hist, 0, ((size_t) s.maxPasses * kRadix + 64 + passes * statusStride) * sizeof(uint32_t), w->stream));
@@ -223,9 +243,15 @@ int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *value
     for (uint32_t p = 0; p < passes; p++)
     {
         uint32_t wbits = bits - 8 * p < 8 ? bits - 8 * p : 8;
-        sortOnesweepKernel<<<tiles, kSortThreads, 0, w->stream>>>(
-            keys[cur], (p == 0 && identityValues) ? nullptr : values[cur], keys[cur ^ 1], values[cur ^ 1], n, nDev, 8 * p, (1u << wbits) - 1,
-            s.hist + p * kRadix, s.status + p * statusStride, s.tickets + p);
+        const uint32_t *vin = (p == 0 && identityValues) ? nullptr : values[cur];
+        if (large)
+            sortOnesweepKernel<kSortThreadsLarge><<<tiles, kSortThreadsLarge, smem, w->stream>>>(
+                keys[cur], vin, keys[cur ^ 1], values[cur ^ 1], n, nDev, 8 * p, (1u << wbits) - 1, s.hist + p * kRadix,
+                s.status + p * statusStride, s.tickets + p);
+        else
+            sortOnesweepKernel<kSortThreadsSmall><<<tiles, kSortThreadsSmall, smem, w->stream>>>(
+                keys[cur], vin, keys[cur ^ 1], values[cur ^ 1], n, nDev, 8 * p, (1u << wbits) - 1, s.hist + p * kRadix,
+                s.status + p * statusStride, s.tickets + p);
         cur ^= 1;
     }
     w->launches += 1 + passes;

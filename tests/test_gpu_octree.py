@@ -84,3 +84,14 @@ def test_mixed_radii_levels(orc):
     rows[:, 3] = np.exp(rng.uniform(np.log(0.3), np.log(60.0), n))
     splats = make_splats([tuple(r) for r in rows])
     compare(orc, splats, 0, n, (5, 0, 9), 3, 6)
+
+
+def test_large_bin_uses_large_sort_tiles(orc):
+    """>= 3 M entry slots switch the radix sort to 16384-key tiles; results stay bit-identical."""
+    from mlsgpu_b200 import host
+    s = host.sphere_splats(500000, seed=8, radius=0.004)
+    g, bins, lo, spacing = host.prepare(s, 0.01)
+    assert len(bins) == 1
+    b = bins[0]
+    splats = np.ascontiguousarray(g[b["ids"]])
+    compare(orc, splats, 0, len(splats), b["offset"], 3, 6)

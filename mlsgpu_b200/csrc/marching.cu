@@ -416,7 +416,7 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
 // Exclusive scan of the tile totals (one CTA: at most ~33 k tiles), list of non-empty tiles,
 // grand totals -> counters.  The role of clogs::Scan(uint2) at src/marching.cpp:721.
 __global__ void __launch_bounds__(1024) scanTilesKernel(uint64_t *tileTotals, uint32_t *tileList, uint32_t numTiles,
-                                                        uint32_t *counters)
+                                                        uint32_t *counters, uint32_t vertexSpace, uint32_t indexSpace)
 {
     __shared__ uint64_t sScan[33];
     __shared__ uint32_t sScan32[33];
@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(1024) scanTilesKernel(uint64_t *tileTotals, ui
         counters[CTR_VERTS] = (uint32_t) (total & 0x7FFFFFFFu);
         counters[CTR_INDICES] = (uint32_t) (total >> 31);
         counters[CTR_TILES] = totalNonEmpty;
+        if ((total & 0x7FFFFFFFu) > vertexSpace || (total >> 31) > indexSpace) counters[CTR_OVERFLOW] = 1;
     }
 }
 
@@ -471,6 +472,7 @@ __global__ void __launch_bounds__(kWeldThreads) weldVerticesKernel(WeldParams P)
     __shared__ uint64_t sScan[33];
     __shared__ uint32_t sTile;
     __shared__ uint64_t sPrefix;
+    if (P.counters[CTR_OVERFLOW]) return;   // the block did not fit: the host splits it and starts over
     const uint32_t n = P.counters[CTR_VERTS];
     if (threadIdx.x == 0) sTile = atomicAdd(&P.counters[CTR_WELD_TICKET], 1u);
     __syncthreads();
@@ -540,6 +542,7 @@ __global__ void __launch_bounds__(kWeldThreads) weldVerticesKernel(WeldParams P)
 __global__ void __launch_bounds__(256) reindexKernel(uint32_t *__restrict__ indices, const uint32_t *__restrict__ indexRemap,
                                                      const uint32_t *__restrict__ counters)
 {
+    if (counters[CTR_OVERFLOW]) return;
     const uint32_t n = counters[CTR_INDICES];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         indices[i] = indexRemap[indices[i]];
@@ -692,7 +695,8 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     }
     {
         ScopedStat st(w, "kernel.marching.scanElements.time");
-        scanTilesKernel<<<1, 1024, 0, s>>>(w->tileTotals, w->tileList, tiles, w->marchCounters);
+        scanTilesKernel<<<1, 1024, 0, s>>>(w->tileTotals, w->tileList, tiles, w->marchCounters, (uint32_t) w->vertexSpace,
+                                           (uint32_t) w->indexSpace);
     }
     {
         ScopedStat st(w, "kernel.marching.generateElements.time");

@@ -54,80 +54,123 @@ __device__ __forceinline__ float pointBoxDist2(float px, float py, float pz, flo
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// prepare() + the 2x2x2 candidate loop of writeEntries, kernels/octree.cl:79-110,184-212.
+// The candidates are ilo + {0,1}^3, so the per-axis box distances (and Morton bit spreads) are
+// computed once for the two options of each axis and combined per candidate; the squared
+// distance is still summed as (dx*dx + dy*dy) + dz*dz, one rounding per operation, exactly like
+// pointBoxDist2() above.  CODES = false only counts the accepted candidates.
+template <bool CODES>
+__device__ __forceinline__ uint32_t splatEntries(const float4 pr, const int3 bias, const LevelInfo &lv, uint32_t k[8])
+{
+    const float p[3] = {pr.x, pr.y, pr.z};
+    const int b[3] = {bias.x, bias.y, bias.z};
+    int lo[3], big = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+    {
+        lo[a] = __float2int_rd(__fsub_rn(p[a], pr.w));
+        big = max(big, __float2int_rd(__fadd_rn(p[a], pr.w)) - lo[a]);
+    }
+    int shift = big > 1 ? 32 - __clz(big - 1) : 0;   // levelShift(), :50-55
+    shift = min(max(shift, (int) lv.minShift), (int) lv.maxShift);
+    const float radius2 = __fmul_rn(__fmul_rn(pr.w, pr.w), 1.00001f);
+    const int bound = 1 << (lv.maxShift - shift);
+    float sq[3][2];
+    uint32_t bits[3][2];
+    bool inside[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+    {
+        const int il = max(lo[a] - b[a], 0) >> shift;
+#pragma unroll
+        for (int o = 0; o < 2; o++)
+        {
+            const int c = il + o;
+            // goodEntry(), :100-110: box [c << shift, (c+1) << shift] + bias along this axis
+            const float blo = (float) ((int) ((uint32_t) c << shift) + b[a]);
+            const float bhi = (float) ((int) ((uint32_t) (c + 1) << shift) + b[a]);
+            const float d = __fsub_rn(fmaxf(blo, fminf(bhi, p[a])), p[a]);
+            sq[a][o] = __fmul_rn(d, d);
+            inside[a][o] = c < bound;
+            if (CODES) bits[a][o] = spread3((uint32_t) c) << a;
+        }
+    }
+    const uint32_t levelOffset = CODES ? lv.offsets[shift] : 0u;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int o = 0; o < 8; o++)
+    {
+        const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
+        const float dist2 = __fadd_rn(__fadd_rn(sq[0][ox], sq[1][oy]), sq[2][oz]);
+        const bool isect = dist2 < radius2 && inside[0][ox] && inside[1][oy] && inside[2][oz];
+        if (CODES) k[o] = isect ? (bits[0][ox] | bits[1][oy] | bits[2][oz]) + levelOffset : 0xFFFFFFFFu;
+        cnt += isect;
+    }
+    return cnt;
+}
+
 // The reference writes exactly 8 (key, id) slots per splat, UINT_MAX in the rejected ones, and sorts
-// all 8N.  Here only the accepted entries are written, packed in (splat, slot) order through a
-// decoupled look-back over the per-CTA counts, and their number goes to *numValid: the sort, the
-// run detection and the command emission then touch 2-4x fewer elements, with identical results
-// (rejected slots sort to the end and are skipped by writeSplatIds, kernels/octree.cl:266).
+// all 8N.  Here only the accepted entries are written, packed in (splat, slot) order, and their
+// number goes to *numValid: the sort, the run detection and the command emission then touch 2-4x
+// fewer elements, with identical results (rejected slots sort to the end and are skipped by
+// writeSplatIds, kernels/octree.cl:266).  Three launches, none of which waits on another CTA:
+// EMIT = false counts per 256-splat tile, scanCountsKernel turns the counts into bases, EMIT = true
+// recomputes the (cheap) candidates and writes them.
+template <bool EMIT>
 __global__ void __launch_bounds__(256) writeEntriesKernel(uint32_t *__restrict__ keys, uint32_t *__restrict__ values,
                                                           mlsb_splat *__restrict__ splats, int3 bias, LevelInfo lv,
                                                           uint32_t firstSplat, uint32_t numSplats,
-                                                          volatile uint64_t *status, uint32_t *ticket, uint32_t *numValid)
+                                                          uint32_t *__restrict__ tileCounts)
 {
     __shared__ uint32_t sScan[33];
-    __shared__ uint32_t sTile;
-    __shared__ uint64_t sPrefix;
-    if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = sTile;
-    const uint32_t g = tile * blockDim.x + threadIdx.x;
-    const bool inRange = g < numSplats;
-    const uint32_t gid = (inRange ? g : 0) + firstSplat;
-    float4 pr = *reinterpret_cast<const float4 *>(&splats[gid]);
-
-    // prepare(), kernels/octree.cl:79-89
-    int lox = __float2int_rd(__fsub_rn(pr.x, pr.w)), loy = __float2int_rd(__fsub_rn(pr.y, pr.w)),
-        loz = __float2int_rd(__fsub_rn(pr.z, pr.w));
-    int hix = __float2int_rd(__fadd_rn(pr.x, pr.w)), hiy = __float2int_rd(__fadd_rn(pr.y, pr.w)),
-        hiz = __float2int_rd(__fadd_rn(pr.z, pr.w));
-    int big = max(max(hix - lox, hiy - loy), hiz - loz);
-    int shift = big > 1 ? 32 - __clz(big - 1) : 0;   // levelShift(), :50-55
-    shift = min(max(shift, (int) lv.minShift), (int) lv.maxShift);
-    int ilx = max(lox - bias.x, 0) >> shift, ily = max(loy - bias.y, 0) >> shift, ilz = max(loz - bias.z, 0) >> shift;
-
-    float radius2 = __fmul_rn(pr.w, pr.w);
-    if (inRange) splats[gid].radius = __fdiv_rn(1.0f, radius2);
-    radius2 = __fmul_rn(radius2, 1.00001f);
-    uint32_t levelOffset = lv.offsets[shift];
-    int bound = 1 << (lv.maxShift - shift);
-
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t k[8];
-#pragma unroll
-    for (int o = 0; o < 8; o++)
-    {
-        int ax = ilx + (o & 1), ay = ily + ((o >> 1) & 1), az = ilz + (o >> 2);
-        // goodEntry(), :100-110
-        float blx = (float) ((int) ((uint32_t) ax << shift) + bias.x), bhx = (float) ((int) ((uint32_t) (ax + 1) << shift) + bias.x);
-        float bly = (float) ((int) ((uint32_t) ay << shift) + bias.y), bhy = (float) ((int) ((uint32_t) (ay + 1) << shift) + bias.y);
-        float blz = (float) ((int) ((uint32_t) az << shift) + bias.z), bhz = (float) ((int) ((uint32_t) (az + 1) << shift) + bias.z);
-        bool isect = pointBoxDist2(pr.x, pr.y, pr.z, blx, bly, blz, bhx, bhy, bhz) < radius2;
-        isect = isect && ax < bound && ay < bound && az < bound;
-        k[o] = (isect && inRange) ? makeCode(ax, ay, az) + levelOffset : 0xFFFFFFFFu;
-    }
     uint32_t cnt = 0;
-#pragma unroll
-    for (int o = 0; o < 8; o++) cnt += k[o] != 0xFFFFFFFFu;
+    const uint32_t gid = g + firstSplat;
+    if (g < numSplats)
+    {
+        const float4 pr = *reinterpret_cast<const float4 *>(&splats[gid]);
+        cnt = splatEntries<EMIT>(pr, bias, lv, k);
+        if (EMIT) splats[gid].radius = __fdiv_rn(1.0f, __fmul_rn(pr.w, pr.w));   // kernels/octree.cl:193
+    }
     uint32_t total;
     const uint32_t excl = blockExclusiveScan(cnt, sScan, &total);
-    if (threadIdx.x < 32)
+    if (!EMIT)
     {
-        const uint64_t p = lookbackExclusive(status, tile, total);
-        if (threadIdx.x == 0)
-        {
-            sPrefix = p;
-            if (tile == gridDim.x - 1) *numValid = (uint32_t) (p + total);
-        }
+        if (threadIdx.x == 0) tileCounts[blockIdx.x] = total;
+        return;
     }
-    __syncthreads();
-    uint32_t dst = (uint32_t) sPrefix + excl;
+    uint32_t dst = tileCounts[blockIdx.x] + excl;
+    if (cnt)
+    {
 #pragma unroll
-    for (int o = 0; o < 8; o++)
-        if (k[o] != 0xFFFFFFFFu)
-        {
-            keys[dst] = k[o];
-            values[dst] = gid;
-            dst++;
-        }
+        for (int o = 0; o < 8; o++)
+            if (k[o] != 0xFFFFFFFFu)
+            {
+                keys[dst] = k[o];
+                values[dst] = gid;
+                dst++;
+            }
+    }
+}
+
+// In-place exclusive scan of n per-tile counts by one CTA; the grand total goes to *total.
+__global__ void __launch_bounds__(1024) scanCountsKernel(uint32_t *counts, uint32_t n, uint32_t *total)
+{
+    __shared__ uint32_t sScan[33];
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t first = threadIdx.x * per, last = min(first + per, n);
+    uint32_t sum = 0;
+    for (uint32_t i = first; i < last; i++) sum += counts[i];
+    uint32_t all;
+    uint32_t base = blockExclusiveScan(sum, sScan, &all);
+    for (uint32_t i = first; i < last; i++)
+    {
+        const uint32_t c = counts[i];
+        counts[i] = base;
+        base += c;
+    }
+    if (threadIdx.x == 0) *total = all;
 }
 
 // First and last sorted position of each key (boundaries of equal-key runs).
@@ -135,14 +178,15 @@ __global__ void __launch_bounds__(256) findRunsKernel(const uint32_t *__restrict
                                                       int32_t *__restrict__ runFirst, int32_t *__restrict__ runLast)
 {
     const uint32_t numEntries = *numValid;
-    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= numEntries) return;
-    uint32_t cur = keys[pos];
-    if (cur == 0xFFFFFFFFu) return;
-    uint32_t prev = pos > 0 ? keys[pos - 1] : 0xFFFFFFFFu;
-    uint32_t next = pos + 1 < numEntries ? keys[pos + 1] : 0xFFFFFFFFu;
-    if (prev != cur) runFirst[cur] = (int32_t) pos;
-    if (cur != next) runLast[cur] = (int32_t) pos;
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < numEntries; pos += gridDim.x * blockDim.x)
+    {
+        uint32_t cur = keys[pos];
+        if (cur == 0xFFFFFFFFu) continue;
+        uint32_t prev = pos > 0 ? keys[pos - 1] : 0xFFFFFFFFu;
+        uint32_t next = pos + 1 < numEntries ? keys[pos + 1] : 0xFFFFFFFFu;
+        if (prev != cur) runFirst[cur] = (int32_t) pos;
+        if (cur != next) runLast[cur] = (int32_t) pos;
+    }
 }
 
 // Device-wide exclusive count of non-empty keys, then the command positions of each run:
@@ -208,11 +252,12 @@ __global__ void __launch_bounds__(256) emitCommandsKernel(int32_t *__restrict__ 
                                                           const uint32_t *__restrict__ numValid)
 {
     const uint32_t numEntries = *numValid;
-    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= numEntries) return;
-    uint32_t key = keys[pos];
-    if (key == 0xFFFFFFFFu) return;
-    commands[1 + pos + 2 * runIndex[key]] = (int32_t) ids[pos];
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < numEntries; pos += gridDim.x * blockDim.x)
+    {
+        uint32_t key = keys[pos];
+        if (key == 0xFFFFFFFFu) continue;
+        commands[1 + pos + 2 * runIndex[key]] = (int32_t) ids[pos];
+    }
 }
 
 // writeStart / writeStartTop for every level at once (kernels/octree.cl:292-341).
@@ -320,12 +365,13 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
         {
             ScopedStat st(w, "kernel.octree.writeEntries.time");
             const uint32_t tiles = divUp(numSplats, 256u);
-            MLSB_REQUIRE(tiles <= w->scanStatusWords, MLSB_ERR_LENGTH, "scan status too small");
-            MLSB_CUDA(cudaMemsetAsync(w->scanStatus, 0, (size_t) tiles * sizeof(uint64_t), s));
-            MLSB_CUDA(cudaMemsetAsync(w->scanTicket, 0, 4 * sizeof(uint32_t), s));
-            writeEntriesKernel<<<tiles, 256, 0, s>>>(
-                w->entryKeys[0], w->entryValues[0], w->splats, make_int3(offset[0], offset[1], offset[2]), lv,
-                firstSplat, numSplats, w->scanStatus, w->scanTicket + 1, w->scanTicket + 2);
+            MLSB_REQUIRE(tiles <= 2 * w->scanStatusWords, MLSB_ERR_LENGTH, "scan scratch too small");
+            uint32_t *tileCounts = reinterpret_cast<uint32_t *>(w->scanStatus);
+            const int3 bias = make_int3(offset[0], offset[1], offset[2]);
+            writeEntriesKernel<false><<<tiles, 256, 0, s>>>(nullptr, nullptr, w->splats, bias, lv, firstSplat, numSplats, tileCounts);
+            scanCountsKernel<<<1, 1024, 0, s>>>(tileCounts, tiles, w->scanTicket + 2);
+            writeEntriesKernel<true><<<tiles, 256, 0, s>>>(w->entryKeys[0], w->entryValues[0], w->splats, bias, lv, firstSplat,
+                                                          numSplats, tileCounts);
         }
     }
     int cur = 0;
@@ -340,7 +386,7 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
     if (numEntries > 0)
     {
         ScopedStat st(w, "kernel.octree.countCommands.time");
-        findRunsKernel<<<divUp(numEntries, 256u), 256, 0, s>>>(w->entryKeys[cur], numValid, w->runFirst, w->runLast);
+        findRunsKernel<<<min(divUp(numEntries, 256u), 148u * 16u), 256, 0, s>>>(w->entryKeys[cur], numValid, w->runFirst, w->runLast);
     }
     {
         ScopedStat st(w, "kernel.octree.scan.time");
@@ -354,14 +400,14 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
     if (numEntries > 0)
     {
         ScopedStat st(w, "kernel.octree.writeSplatIds.time");
-        emitCommandsKernel<<<divUp(numEntries, 256u), 256, 0, s>>>(w->commands, w->entryKeys[cur], w->entryValues[cur],
+        emitCommandsKernel<<<min(divUp(numEntries, 256u), 148u * 16u), 256, 0, s>>>(w->commands, w->entryKeys[cur], w->entryValues[cur],
                                                                    w->runIndex, numValid);
     }
     {
         ScopedStat st(w, "kernel.octree.writeStart.time");
         linkLevelsKernel<<<divUp(numStart, 256u), 256, 0, s>>>(w->start, w->commands, w->runStart, w->jumpPos, lv, numStart);
     }
-    w->launches += (numSplats > 0 ? 3 : 0) + 2;
+    w->launches += (numSplats > 0 ? 5 : 0) + 2;
     MLSB_CUDA(cudaGetLastError());
     return MLSB_OK;
 }

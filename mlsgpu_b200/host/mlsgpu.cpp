@@ -1,0 +1,293 @@
+// mlsgpu — command-line driver with the reference's option surface (src/mlsgpu_core.cpp:73-175,
+// mlsgpu.cpp:83-263) on top of libmlsb200:
+//
+//   PLY files -> conditioned splats -> bounding grid -> bins -> worker group (octree, MLS,
+//   marching on the GPU) -> host mesher (seam weld, prune) -> PLY
+//
+// Option names, defaults and validation follow the reference; options that configure parts of the
+// reference that do not exist here (out-of-core readers/writers, temporary files, checkpoints,
+// MPI) are accepted and ignored so that existing command lines keep working.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dirent.h>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <memory>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#include "bucket.hpp"
+#include "mesher.hpp"
+#include "mlsb200.hpp"
+#include "ply_io.hpp"
+
+namespace
+{
+
+struct Options
+{
+    // src/mlsgpu_core.cpp:100-139 (defaults), :73-98 (names)
+    double fitSmooth = 4.0;
+    double maxRadius = std::numeric_limits<float>::infinity();
+    double fitGrid = 0.01;
+    double fitPrune = 0.02;
+    double fitBoundaryLimit = 1.0;
+    std::string fitShape = "sphere";
+    int levels = 6;
+    int subsampling = 3;
+    int leafCells = 63;
+    int deviceThreads = 4;           // the reference defaults to 1 and recommends more (src/marching.h:573-576)
+    std::uint64_t memBucketSplats = 64ull << 20;   // bytes
+    std::uint64_t memMesh = 512ull << 20;
+    int device = 0;
+    bool quiet = false, statistics = false;
+    std::string output;
+    std::vector<std::string> inputs;
+};
+
+void usage()
+{
+    std::cout <<
+        "Usage: mlsgpu [options] -o output.ply input.ply [input.ply...]\n"
+        "  -h, --help                  show this help\n"
+        "  -q, --quiet                 do not show informational messages\n"
+        "  -o, --output-file FILE      output file (required)\n"
+        "  --fit-smooth X              smoothing factor (4)\n"
+        "  --max-radius X              limit influence radii\n"
+        "  --fit-grid X                spacing of grid cells (0.01)\n"
+        "  --fit-prune X               minimum fraction of vertices per component (0.02)\n"
+        "  --fit-boundary-limit X      tuning factor for boundary detection (1)\n"
+        "  --fit-shape sphere|plane    model shape (sphere)\n"
+        "  --levels N                  levels in octree (6)\n"
+        "  --subsampling N             subsampling of octree (3)\n"
+        "  --leaf-cells N              leaf size for initial histogram (63)\n"
+        "  --device-threads N          worker threads per device (4)\n"
+        "  --mem-bucket-splats SIZE    device memory for splats of one bin, K/M/G suffix (64M)\n"
+        "  --mem-mesh SIZE             device memory for raw mesh data (512M)\n"
+        "  --device N                  CUDA device ordinal (replaces --cl-device)\n"
+        "  --statistics                print statistics at the end\n";
+}
+
+// Capacity, src/options.cpp:38-69
+std::uint64_t parseCapacity(const std::string &s)
+{
+    char *end = nullptr;
+    double v = std::strtod(s.c_str(), &end);
+    std::uint64_t mul = 1;
+    if (*end == 'K' || *end == 'k') mul = 1ull << 10;
+    else if (*end == 'M' || *end == 'm') mul = 1ull << 20;
+    else if (*end == 'G' || *end == 'g') mul = 1ull << 30;
+    else if (*end != '\0' && *end != 'B') throw std::invalid_argument("bad capacity " + s);
+    return (std::uint64_t) (v * mul);
+}
+
+Options parse(int argc, char **argv)
+{
+    Options o;
+    // accepted for compatibility, value ignored
+    static const std::map<std::string, bool> ignored = {
+        {"--response-file", true}, {"--tmp-dir", true}, {"--statistics-file", true}, {"--statistics-cl", false},
+        {"--timeplot", true}, {"--max-split", true}, {"--reader", true}, {"--writer", true}, {"--omp-threads", true},
+        {"--decache", false}, {"--checkpoint", true}, {"--resume", true}, {"--mem-load-splats", true},
+        {"--mem-host-splats", true}, {"--mem-reorder", true}, {"--mem-gather", true}, {"--split", false},
+        {"--split-size", true}, {"--cl-device", true}, {"--cl-gpu", false}, {"--cl-cpu", false}, {"--debug", false}};
+    for (int i = 1; i < argc; i++)
+    {
+        std::string a = argv[i], v;
+        auto eq = a.find('=');
+        bool hasValue = false;
+        if (a.rfind("--", 0) == 0 && eq != std::string::npos)
+        {
+            v = a.substr(eq + 1);
+            a = a.substr(0, eq);
+            hasValue = true;
+        }
+        auto value = [&]() -> std::string {
+            if (hasValue) return v;
+            if (i + 1 >= argc) throw std::invalid_argument("option " + a + " needs a value");
+            return argv[++i];
+        };
+        if (a == "-h" || a == "--help") { usage(); std::exit(0); }
+        else if (a == "-q" || a == "--quiet") o.quiet = true;
+        else if (a == "-o" || a == "--output-file") o.output = value();
+        else if (a == "--fit-smooth") o.fitSmooth = std::stod(value());
+        else if (a == "--max-radius") o.maxRadius = std::stod(value());
+        else if (a == "--fit-grid") o.fitGrid = std::stod(value());
+        else if (a == "--fit-prune") o.fitPrune = std::stod(value());
+        else if (a == "--fit-boundary-limit") o.fitBoundaryLimit = std::stod(value());
+        else if (a == "--fit-shape") o.fitShape = value();
+        else if (a == "--levels") o.levels = std::stoi(value());
+        else if (a == "--subsampling") o.subsampling = std::stoi(value());
+        else if (a == "--leaf-cells") o.leafCells = std::stoi(value());
+        else if (a == "--device-threads") o.deviceThreads = std::stoi(value());
+        else if (a == "--mem-bucket-splats") o.memBucketSplats = parseCapacity(value());
+        else if (a == "--mem-mesh") o.memMesh = parseCapacity(value());
+        else if (a == "--device") o.device = std::stoi(value());
+        else if (a == "--statistics") o.statistics = true;
+        else if (ignored.count(a)) { if (ignored.at(a)) (void) value(); }
+        else if (a.rfind("-", 0) == 0) throw std::invalid_argument("unknown option " + a);
+        else o.inputs.push_back(a);
+    }
+    // validateOptions, src/mlsgpu_core.cpp:398-457
+    if (o.output.empty()) throw std::invalid_argument("the option '--output-file' is required but missing");
+    if (o.inputs.empty()) throw std::invalid_argument("At least one input file must be specified.");
+    if (o.levels < 1 || o.levels > 10) throw std::invalid_argument("Value of --levels must be in the range 1 to 10.");
+    if (o.subsampling < 3) throw std::invalid_argument("Value of --subsampling must be at least 3.");
+    if (o.levels + o.subsampling > 14) throw std::invalid_argument("Sum of --subsampling and --levels is too large.");
+    if (o.levels + o.subsampling - 1 > 9) throw std::invalid_argument("bins above 512 corners per side are not supported by this build.");
+    if (o.leafCells < 1) throw std::invalid_argument("Value of --leaf-cells must be positive.");
+    if (o.deviceThreads < 1) throw std::invalid_argument("Value of --device-threads must be at least 1.");
+    if (!(o.fitPrune >= 0.0 && o.fitPrune <= 1.0)) throw std::invalid_argument("Value of --fit-prune must be in [0, 1].");
+    if (o.fitShape != "sphere" && o.fitShape != "plane") throw std::invalid_argument("Value of --fit-shape must be sphere or plane.");
+    if (!(o.fitGrid > 0.0)) throw std::invalid_argument("Value of --fit-grid must be positive.");
+    if (o.memBucketSplats < sizeof(mlsb_splat)) throw std::invalid_argument("Value of --mem-bucket-splats is too small.");
+    return o;
+}
+
+void collectInputs(const std::vector<std::string> &args, std::vector<std::string> &files)
+{
+    for (const std::string &a : args)
+    {
+        struct stat st;
+        if (stat(a.c_str(), &st) == 0 && S_ISDIR(st.st_mode))
+        {
+            // directories are scanned for *.ply, src/mlsgpu_core.cpp:540-566
+            std::vector<std::string> found;
+            if (DIR *d = opendir(a.c_str()))
+            {
+                while (dirent *e = readdir(d))
+                {
+                    std::string n = e->d_name;
+                    if (n.size() > 4 && n.substr(n.size() - 4) == ".ply") found.push_back(a + "/" + n);
+                }
+                closedir(d);
+            }
+            std::sort(found.begin(), found.end());
+            files.insert(files.end(), found.begin(), found.end());
+        }
+        else
+            files.push_back(a);
+    }
+}
+
+struct SinkState
+{
+    mlsb::Mesher mesher;
+};
+
+void meshSink(std::uint64_t, const mlsb_mesh_sizes *sizes, const void *blob, void *user)
+{
+    static_cast<SinkState *>(user)->mesher.add(*sizes, blob);
+}
+
+double now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    try
+    {
+        const Options o = parse(argc, argv);
+        const double t0 = now();
+
+        // ---- read and condition (FastPly::Reader) ----
+        std::vector<std::string> files;
+        collectInputs(o.inputs, files);
+        std::vector<mlsb_splat> splats;
+        for (const std::string &f : files)
+        {
+            mlsb::PlyReader reader(f, (float) o.fitSmooth, (float) o.maxRadius);
+            splats.reserve(splats.size() + reader.size());
+            reader.read(0, reader.size(), splats);
+        }
+        const std::size_t numSplats = splats.size();
+        if (numSplats == 0) throw std::runtime_error("At least one input point is required.");
+        const double tRead = now();
+
+        // ---- grid, bins (doComputeBlobs / doBucket) ----
+        const std::int64_t maxCells = (std::int64_t(1) << (o.levels + o.subsampling - 1)) - 1;   // src/mlsgpu_core.cpp:722
+        const std::int64_t bucketSize = std::min<std::int64_t>(o.leafCells, maxCells);             // :600-603
+        const mlsb::Grid grid = mlsb::boundingGrid(splats, (float) o.fitGrid, bucketSize);
+        for (int a = 0; a < 3; a++)
+            if (grid.numCells(a) + 1 > (1 << 20) - 1)   // src/mlsgpu_core.cpp:623-629
+                throw std::runtime_error("The bounding box is too big. Perhaps you have used the wrong units for --fit-grid.");
+        mlsb::worldToGrid(splats, grid);
+        const std::size_t maxBucketSplats = (std::size_t) (o.memBucketSplats / sizeof(mlsb_splat));
+        std::vector<mlsb::Bin> bins = mlsb::makeBins(splats, grid, maxCells, maxBucketSplats);
+        std::size_t largest = 1;
+        for (const mlsb::Bin &b : bins) largest = std::max(largest, b.ids.size());
+        const double tBucket = now();
+
+        // ---- device pipeline ----
+        mlsb_worker_config cfg;
+        cfg.device = o.device;
+        cfg.maxLevels = (std::uint32_t) o.levels;
+        cfg.subsampling = (std::uint32_t) o.subsampling;
+        cfg.maxSplats = (std::uint32_t) largest;
+        cfg.maxCells = (std::uint32_t) maxCells;
+        cfg.meshBytes = std::max<std::uint64_t>(o.memMesh / (o.deviceThreads + 1), (std::uint64_t) maxCells * maxCells * 872);
+        cfg.shape = o.fitShape == "plane" ? MLSB_SHAPE_PLANE : MLSB_SHAPE_SPHERE;
+        cfg.boundaryLimit = (float) o.fitBoundaryLimit;
+        SinkState state;
+        mlsb_group *group = nullptr;
+        mlsb::check(mlsb_group_create(&cfg, (std::uint32_t) o.deviceThreads, 0, 1, meshSink, &state, &group));
+        struct GroupGuard { mlsb_group *g; ~GroupGuard() { mlsb_group_destroy(g); } } guard{group};
+        float origin[3];
+        grid.getVertex0(origin);
+        for (int i = 0; i < o.deviceThreads; i++)
+        {
+            mlsb_worker *w = nullptr;
+            mlsb::check(mlsb_group_worker(group, (std::uint32_t) i, &w));
+            mlsb::check(mlsb_set_scale_bias(w, grid.spacing, origin));   // ScaleBiasFilter::setScaleBias(grid)
+        }
+        std::vector<std::vector<mlsb_splat>> staged(bins.size());
+        for (std::size_t b = 0; b < bins.size(); b++)
+        {
+            // BucketLoader::operator(): gather the bin's splats (src/bucket_loader.cpp:104-126)
+            staged[b].resize(bins[b].ids.size());
+            for (std::size_t i = 0; i < bins[b].ids.size(); i++) staged[b][i] = splats[bins[b].ids[i]];
+            mlsb::check(mlsb_group_submit(group, staged[b].data(), (std::uint32_t) staged[b].size(), bins[b].size, bins[b].offset, b));
+        }
+        mlsb::check(mlsb_group_wait(group));
+        const double tDevice = now();
+
+        // ---- mesher: prune, write (OOCMesher::write) ----
+        mlsb::Mesher::Result mesh = state.mesher.finish(o.fitPrune);
+        mlsb::PlyWriter writer;
+        {
+            // options are echoed as comments, src/mlsgpu_core.cpp:680-685
+            char buf[256];
+            std::snprintf(buf, sizeof(buf), "mlsgpu (mlsb200) fit-smooth=%g fit-grid=%g fit-prune=%g fit-boundary-limit=%g fit-shape=%s levels=%d subsampling=%d",
+                          o.fitSmooth, o.fitGrid, o.fitPrune, o.fitBoundaryLimit, o.fitShape.c_str(), o.levels, o.subsampling);
+            writer.addComment(buf);
+        }
+        writer.write(o.output, mesh.vertices, mesh.triangles);
+        const double tEnd = now();
+
+        if (!o.quiet || o.statistics)
+        {
+            std::cout << "files.splats: " << numSplats << "\n"
+                      << "bins: " << bins.size() << "\n"
+                      << "components.total: " << mesh.totalComponents << "\ncomponents.kept: " << mesh.keptComponents << "\n"
+                      << "output.vertices: " << mesh.vertices.size() << "\noutput.triangles: " << mesh.triangles.size() << "\n";
+            std::printf("read.time: %.3f\nbucket.time: %.3f\ndevice.time: %.3f\nmesher.time: %.3f\nrun.time: %.3f\n",
+                        tRead - t0, tBucket - tRead, tDevice - tBucket, tEnd - tDevice, tEnd - t0);
+            std::printf("splats/s end-to-end: %.3g\n", numSplats / (tEnd - t0));
+        }
+        return 0;
+    }
+    catch (const std::exception &e)
+    {
+        std::cerr << "mlsgpu: " << e.what() << "\n";
+        return 1;
+    }
+}

@@ -1,0 +1,222 @@
+// Binary PLY input (splats) and output (mesh), the formats of src/fast_ply.{h,cpp}.
+//
+// Reader: little-endian binary PLY whose vertex element has float32 x, y, z, nx, ny, nz, radius in
+// any order, possibly among other fixed-size properties (src/fast_ply.cpp:185-325).  decode()
+// applies the conditioning of FastPly::Reader::decode (:334-350).
+// Writer: float32 x, y, z vertices and "list uint8 uint32 vertex_indices" faces with the header
+// padded to a multiple of four bytes by a trailing comment (:443-481).
+#ifndef MLSB200_PLY_IO_HPP
+#define MLSB200_PLY_IO_HPP
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mlsb200.h"
+
+namespace mlsb
+{
+
+class PlyReader
+{
+public:
+    PlyReader(const std::string &path, float smooth, float maxRadius) : path(path), smooth(smooth), maxRadius(maxRadius)
+    {
+        file = std::fopen(path.c_str(), "rb");
+        if (!file) throw std::runtime_error("cannot open " + path);
+        try
+        {
+            readHeader();
+        }
+        catch (...)
+        {
+            std::fclose(file);
+            throw;
+        }
+    }
+    ~PlyReader() { if (file) std::fclose(file); }
+    PlyReader(const PlyReader &) = delete;
+    PlyReader &operator=(const PlyReader &) = delete;
+
+    std::size_t size() const { return numVertices; }
+
+    /// Reads vertices [first, last) and appends the finite ones as conditioned splats
+    /// (non-finite splats are dropped, src/splat_set.cpp:221-240).
+    void read(std::size_t first, std::size_t last, std::vector<mlsb_splat> &out)
+    {
+        std::vector<char> buffer(std::min<std::size_t>(last - first, 1u << 16) * vertexSize);
+        std::fseek(file, (long) (headerSize + first * vertexSize), SEEK_SET);
+        while (first < last)
+        {
+            const std::size_t n = std::min<std::size_t>(last - first, buffer.size() / vertexSize);
+            if (std::fread(buffer.data(), vertexSize, n, file) != n) throw std::runtime_error("short read in " + path);
+            for (std::size_t i = 0; i < n; i++)
+            {
+                mlsb_splat s = decode(buffer.data() + i * vertexSize);
+                bool finite = true;
+                const float *f = reinterpret_cast<const float *>(&s);
+                for (int k = 0; k < 8; k++) finite = finite && std::isfinite(f[k]);
+                if (finite) out.push_back(s);
+            }
+            first += n;
+        }
+    }
+
+private:
+    mlsb_splat decode(const char *p) const
+    {
+        mlsb_splat s;
+        std::memcpy(&s.position[0], p + offsets[0], 4);
+        std::memcpy(&s.position[1], p + offsets[1], 4);
+        std::memcpy(&s.position[2], p + offsets[2], 4);
+        std::memcpy(&s.normal[0], p + offsets[3], 4);
+        std::memcpy(&s.normal[1], p + offsets[4], 4);
+        std::memcpy(&s.normal[2], p + offsets[5], 4);
+        std::memcpy(&s.radius, p + offsets[6], 4);
+        s.radius = std::min(s.radius, maxRadius);
+        s.radius *= smooth;
+        s.quality = (float) (1.0 / (s.radius * s.radius));   // double division, as upstream
+        return s;
+    }
+
+    static std::size_t typeSize(const std::string &t)
+    {
+        static const std::map<std::string, std::size_t> sizes = {
+            {"char", 1}, {"int8", 1}, {"uchar", 1}, {"uint8", 1}, {"short", 2}, {"int16", 2}, {"ushort", 2}, {"uint16", 2},
+            {"int", 4}, {"int32", 4}, {"uint", 4}, {"uint32", 4}, {"float", 4}, {"float32", 4}, {"double", 8}, {"float64", 8}};
+        auto it = sizes.find(t);
+        if (it == sizes.end()) throw std::runtime_error("unknown PLY type " + t);
+        return it->second;
+    }
+
+    void readHeader()
+    {
+        static const char *names[7] = {"x", "y", "z", "nx", "ny", "nz", "radius"};
+        std::string line;
+        bool inVertex = false, sawVertex = false, little = false;
+        bool have[7] = {};
+        auto getline = [&]() {
+            line.clear();
+            int c;
+            while ((c = std::fgetc(file)) != EOF && c != '\n') line.push_back((char) c);
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            return c != EOF;
+        };
+        if (!getline() || line != "ply") throw std::runtime_error(path + ": PLY signature missing");
+        while (getline())
+        {
+            std::istringstream in(line);
+            std::string tok;
+            in >> tok;
+            if (tok == "end_header") break;
+            if (tok == "format")
+            {
+                std::string fmt;
+                in >> fmt;
+                if (fmt != "binary_little_endian") throw std::runtime_error(path + ": only binary_little_endian is supported");
+                little = true;
+            }
+            else if (tok == "element")
+            {
+                std::string name;
+                std::size_t count;
+                in >> name >> count;
+                if (inVertex) inVertex = false;
+                if (name == "vertex")
+                {
+                    if (sawVertex) throw std::runtime_error(path + ": two vertex elements");
+                    inVertex = sawVertex = true;
+                    numVertices = count;
+                }
+                else if (!sawVertex)
+                    throw std::runtime_error(path + ": the vertex element must come first");
+            }
+            else if (tok == "property" && inVertex)
+            {
+                std::string type, name;
+                in >> type;
+                if (type == "list") throw std::runtime_error(path + ": list property in vertex element");
+                in >> name;
+                for (int k = 0; k < 7; k++)
+                    if (name == names[k])
+                    {
+                        if (type != "float" && type != "float32") throw std::runtime_error(path + ": property " + name + " must be float32");
+                        offsets[k] = vertexSize;
+                        have[k] = true;
+                    }
+                vertexSize += typeSize(type);
+            }
+        }
+        if (!little) throw std::runtime_error(path + ": no format line");
+        for (int k = 0; k < 7; k++)
+            if (!have[k]) throw std::runtime_error(path + ": property " + names[k] + " is missing");
+        headerSize = (std::size_t) std::ftell(file);
+    }
+
+    std::string path;
+    std::FILE *file = nullptr;
+    float smooth, maxRadius;
+    std::size_t numVertices = 0, vertexSize = 0, headerSize = 0;
+    std::size_t offsets[7] = {};
+};
+
+/// FastPly::Writer, src/fast_ply.cpp:398-564.
+class PlyWriter
+{
+public:
+    void addComment(const std::string &c) { comments.push_back(c); }
+
+    void write(const std::string &path, const std::vector<std::array<float, 3>> &vertices,
+               const std::vector<std::array<std::uint32_t, 3>> &triangles) const
+    {
+        std::FILE *f = std::fopen(path.c_str(), "wb");
+        if (!f) throw std::runtime_error("cannot create " + path);
+        const std::string header = makeHeader(vertices.size(), triangles.size());
+        std::fwrite(header.data(), 1, header.size(), f);
+        if (!vertices.empty()) std::fwrite(vertices.data(), sizeof(vertices[0]), vertices.size(), f);
+        std::vector<unsigned char> faces(triangles.size() * 13);
+        for (std::size_t i = 0; i < triangles.size(); i++)
+        {
+            faces[13 * i] = 3;
+            std::memcpy(&faces[13 * i + 1], triangles[i].data(), 12);
+        }
+        if (!faces.empty()) std::fwrite(faces.data(), 1, faces.size(), f);
+        if (std::fclose(f) != 0) throw std::runtime_error("error writing " + path);
+    }
+
+    std::string makeHeader(std::size_t numVertices, std::size_t numTriangles) const
+    {
+        std::ostringstream out;
+        out << "ply\nformat binary_little_endian 1.0\n";
+        for (const std::string &c : comments) out << "comment " << c << '\n';
+        out << "element vertex " << numVertices << '\n'
+            << "property float32 x\nproperty float32 y\nproperty float32 z\n"
+            << "element face " << numTriangles << '\n'
+            << "property list uint8 uint32 vertex_indices\n"
+            << "comment padding:";
+        std::size_t size = (std::size_t) out.tellp() + 12;   // 12 for \nend_header\n
+        while (size % 4 != 0)
+        {
+            out << 'X';
+            size++;
+        }
+        out << "\nend_header\n";
+        return out.str();
+    }
+
+private:
+    std::vector<std::string> comments;
+};
+
+}  // namespace mlsb
+
+#endif

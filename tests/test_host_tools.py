@@ -1,0 +1,124 @@
+"""Host-side tools around the device path: PLY I/O, host mesher (seam weld + prune)
+and the mlsgpu command line with the reference's option names."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from fixtures import is_manifold
+from mlsgpu_b200 import host, plyfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "mlsgpu_b200", "host")
+
+
+def build(target):
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "mlsgpu_b200"), "host/" + target], check=True)
+    return os.path.join(HOST, target)
+
+
+def tetra(offset, keys=None):
+    """A tetrahedron surface: 4 vertices, 4 triangles; `keys` marks its last vertices external."""
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32) + np.float32(offset)
+    t = np.array([[0, 2, 1], [0, 1, 3], [0, 3, 2], [1, 2, 3]], np.uint32)
+    keys = np.array(keys or [], np.uint64)
+    return dict(vertices=v, triangles=t, keys=keys, num_internal=4 - len(keys))
+
+
+def write_blocks(path, blocks):
+    with open(path, "wb") as f:
+        f.write(np.uint64(len(blocks)).tobytes())
+        for b in blocks:
+            f.write(np.array([len(b["vertices"]), len(b["triangles"]), b["num_internal"]], np.uint64).tobytes())
+            f.write(b["keys"].tobytes() + b["vertices"].tobytes() + b["triangles"].tobytes())
+
+
+def test_mesher_welds_by_key_and_prunes(tmp_path):
+    exe = build("mesher_test")
+    # two big strips sharing two external vertices (keys 7 and 9) + one isolated small component
+    big1 = tetra((0, 0, 0), keys=[7, 9])
+    big2 = tetra((5, 5, 5), keys=[9, 7])      # same keys, other order
+    many = [tetra((10 + 3 * i, 0, 0), keys=[100 + i, 101 + i]) for i in range(30)]   # a chain welded through keys
+    small = tetra((-50, 0, 0))
+    blocks = [big1, big2] + many + [small]
+    write_blocks(tmp_path / "blocks.bin", blocks)
+    out = tmp_path / "out.ply"
+    res = subprocess.run([exe, str(tmp_path / "blocks.bin"), "0.1", str(out)], check=True, capture_output=True, text=True)
+    nv, nt, total, kept, threshold = (int(x) for x in res.stdout.split())
+    # welded vertices: big pair 4+4-2, chain 30*4 - 29 shared... (block i shares key 101+i with block i+1)
+    assert nv == 6 + (30 * 4 - 29) + 4 and nt == 4 * 33
+    assert total == 3 and threshold == int(nv * 0.1) and kept == 1      # only the chain is >= 10 % of the vertices
+    verts, tris, header = plyfile.read_mesh_ply(out)
+    assert len(verts) == 30 * 4 - 29 and len(tris) == 30 * 4
+    assert tris.max() < len(verts)
+    # header: padded to a multiple of 4 bytes with the reference's trailing comment (src/fast_ply.cpp:462-479)
+    assert len(header) % 4 == 0 and "comment padding:" in header and "property list uint8 uint32 vertex_indices" in header
+    # prune 0 keeps everything
+    res = subprocess.run([exe, str(tmp_path / "blocks.bin"), "0", str(out)], check=True, capture_output=True, text=True)
+    verts, tris, _ = plyfile.read_mesh_ply(out)
+    assert len(verts) == nv and len(tris) == nt
+
+
+def test_cli_option_validation():
+    exe = build("mlsgpu")
+    def run(*args):
+        return subprocess.run([exe] + list(args), capture_output=True, text=True)
+    assert run("--help").returncode == 0
+    for args, msg in [(["in.ply"], "--output-file"), (["-o", "o.ply"], "input file"),
+                      (["-o", "o.ply", "--levels", "11", "in.ply"], "--levels"),
+                      (["-o", "o.ply", "--subsampling", "2", "in.ply"], "--subsampling"),
+                      (["-o", "o.ply", "--fit-prune", "1.5", "in.ply"], "--fit-prune"),
+                      (["-o", "o.ply", "--fit-shape", "cube", "in.ply"], "--fit-shape"),
+                      (["-o", "o.ply", "--bogus", "in.ply"], "unknown option")]:
+        r = run(*args)
+        assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)
+    r = run("-o", "o.ply", "/nonexistent/in.ply", "--mem-bucket-splats=32M", "--tmp-dir", "/tmp", "--cl-gpu")
+    assert r.returncode == 1 and "cannot open" in r.stderr     # ignored options are accepted
+
+
+def test_cli_rejects_bad_ply(tmp_path):
+    exe = build("mlsgpu")
+    p = tmp_path / "bad.ply"
+    p.write_bytes(b"ply\nformat binary_little_endian 1.0\nelement vertex 1\nproperty float32 x\nend_header\n\0\0\0\0")
+    r = subprocess.run([exe, "-o", str(tmp_path / "o.ply"), str(p)], capture_output=True, text=True)
+    assert r.returncode == 1 and "is missing" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end_sphere(tmp_path):
+    """PLY in -> mlsgpu -> PLY out: closed manifold sphere, islands pruned, same vertex count as the
+    Python pipeline over the same bins."""
+    import mlsgpu_b200 as m
+    from test_oracle_marching import weld_by_key
+    exe = build("mlsgpu")
+    s = host.sphere_splats(60000, seed=4, radius=0.012 / 4, noise=0.002)
+    island = host.sphere_splats(300, seed=5, radius=0.012 / 4, noise=0.0, R=0.05)
+    island["position"] += np.float32([1.6, 0, 0])
+    both = np.concatenate([s, island])
+    inp = tmp_path / "in.ply"
+    plyfile.write_splat_ply(inp, both, extra_property=True)
+    out = tmp_path / "out.ply"
+    r = subprocess.run([exe, "-o", str(out), "--fit-grid", "0.025", "--levels", "3", "--fit-prune", "0.02",
+                        "--device-threads", "3", "--statistics", str(inp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    stats = dict(line.split(": ") for line in r.stdout.strip().splitlines() if ": " in line)
+    assert int(stats["files.splats"]) == len(both) and int(stats["bins"]) >= 8
+    assert int(stats["components.total"]) >= 2 and int(stats["components.kept"]) == 1
+    verts, tris, header = plyfile.read_mesh_ply(out)
+    assert is_manifold(len(verts), tris) == ""
+    assert np.abs(np.linalg.norm(verts, axis=1) - 1.0).max() < 0.03      # only the big sphere is left
+    # the same input through the Python binding, bin by bin, welded by key
+    g, bins, lo, spacing = host.prepare(both, 0.025, max_cells=31)
+    blocks = []
+    with m.Worker(max_splats=len(g), max_cells=31) as w:
+        w.set_scale_bias(float(spacing), lo.astype(np.float32) * spacing)
+        for b in bins:
+            w.upload_splats(np.ascontiguousarray(g[b["ids"]]))
+            for blk in w.process_bin(0, len(b["ids"]), b["size"], b["offset"]):
+                ni = blk["num_internal"]
+                blocks.append(dict(vertices=blk["vertices"], triangles=blk["triangles"], num_internal=ni,
+                                   keys=np.concatenate([np.zeros(ni, np.uint64), blk["external_keys"]])))
+    pv, pt = weld_by_key(blocks)
+    keep = np.linalg.norm(pv, axis=1) < 1.3                      # drop the island, as --fit-prune did
+    assert keep.sum() == len(verts) and keep[pt[:, 0]].sum() == len(tris)

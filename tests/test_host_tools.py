@@ -92,8 +92,8 @@ def test_cli_end_to_end_sphere(tmp_path):
     import mlsgpu_b200 as m
     from test_oracle_marching import weld_by_key
     exe = build("mlsgpu")
-    s = host.sphere_splats(60000, seed=4, radius=0.012 / 4, noise=0.002)
-    island = host.sphere_splats(300, seed=5, radius=0.012 / 4, noise=0.0, R=0.05)
+    s = host.sphere_splats(60000, seed=4, radius=0.012, noise=0.002)
+    island = host.sphere_splats(300, seed=5, radius=0.012, noise=0.0, R=0.05)
     island["position"] += np.float32([1.6, 0, 0])
     both = np.concatenate([s, island])
     inp = tmp_path / "in.ply"

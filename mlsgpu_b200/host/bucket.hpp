@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <omp.h>
 #include <stdexcept>
 #include <vector>
 
@@ -119,33 +120,50 @@ inline std::vector<Bin> makeBins(const std::vector<mlsb_splat> &splats, const Gr
         n[a] = std::max<std::int64_t>(g.numCells(a), 1);
         counts[a] = (n[a] + maxCells - 1) / maxCells;
     }
-    // candidate lists per block from each splat's bounding box in block units
-    std::vector<std::vector<std::uint32_t>> blocks((std::size_t) (counts[0] * counts[1] * counts[2]));
+    // candidate lists per block from each splat's bounding box in block units; every thread takes
+    // a contiguous range of splats, so concatenating the per-thread lists keeps ids ascending
+    const std::size_t numBlocks = (std::size_t) (counts[0] * counts[1] * counts[2]);
+    std::vector<std::vector<std::uint32_t>> blocks(numBlocks);
     auto edge = [&](int a, std::int64_t b) { return b * n[a] / counts[a]; };
-    for (std::uint32_t id = 0; id < splats.size(); id++)
+#pragma omp parallel
     {
-        const mlsb_splat &s = splats[id];
-        std::int64_t first[3], last[3];
-        for (int a = 0; a < 3; a++)
+        std::vector<std::vector<std::uint32_t>> mine(numBlocks);
+#pragma omp for schedule(static)
+        for (std::int64_t id = 0; id < (std::int64_t) splats.size(); id++)
         {
-            const double l = (double) s.position[a] - s.radius, h = (double) s.position[a] + s.radius;
-            std::int64_t f = (std::int64_t) std::floor(l * counts[a] / n[a]) - 1, t = (std::int64_t) std::floor(h * counts[a] / n[a]) + 1;
-            first[a] = std::min(std::max<std::int64_t>(f, 0), counts[a] - 1);
-            last[a] = std::min(std::max<std::int64_t>(t, 0), counts[a] - 1);
-        }
-        for (std::int64_t bz = first[2]; bz <= last[2]; bz++)
-            for (std::int64_t by = first[1]; by <= last[1]; by++)
-                for (std::int64_t bx = first[0]; bx <= last[0]; bx++)
-                    blocks[(std::size_t) ((bz * counts[1] + by) * counts[0] + bx)].push_back(id);
-    }
-    for (std::int64_t bz = 0; bz < counts[2]; bz++)
-        for (std::int64_t by = 0; by < counts[1]; by++)
-            for (std::int64_t bx = 0; bx < counts[0]; bx++)
+            const mlsb_splat &s = splats[(std::size_t) id];
+            std::int64_t first[3], last[3];
+            for (int a = 0; a < 3; a++)
             {
-                const std::int64_t lo[3] = {edge(0, bx), edge(1, by), edge(2, bz)};
-                const std::int64_t hi[3] = {edge(0, bx + 1), edge(1, by + 1), edge(2, bz + 1)};
-                detail::split(splats, lo, hi, blocks[(std::size_t) ((bz * counts[1] + by) * counts[0] + bx)], maxCells, maxSplats, bins);
+                const double l = (double) s.position[a] - s.radius, h = (double) s.position[a] + s.radius;
+                std::int64_t f = (std::int64_t) std::floor(l * counts[a] / n[a]) - 1, t = (std::int64_t) std::floor(h * counts[a] / n[a]) + 1;
+                first[a] = std::min(std::max<std::int64_t>(f, 0), counts[a] - 1);
+                last[a] = std::min(std::max<std::int64_t>(t, 0), counts[a] - 1);
             }
+            for (std::int64_t bz = first[2]; bz <= last[2]; bz++)
+                for (std::int64_t by = first[1]; by <= last[1]; by++)
+                    for (std::int64_t bx = first[0]; bx <= last[0]; bx++)
+                        mine[(std::size_t) ((bz * counts[1] + by) * counts[0] + bx)].push_back((std::uint32_t) id);
+        }
+#pragma omp for ordered schedule(static, 1)
+        for (int t = 0; t < omp_get_num_threads(); t++)
+        {
+#pragma omp ordered
+            for (std::size_t b = 0; b < numBlocks; b++) blocks[b].insert(blocks[b].end(), mine[b].begin(), mine[b].end());
+        }
+    }
+    // blocks are independent: split them in parallel, then flatten in z-major block order
+    std::vector<std::vector<Bin>> perBlock(numBlocks);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (std::int64_t bi = 0; bi < (std::int64_t) numBlocks; bi++)
+    {
+        const std::int64_t bx = bi % counts[0], by = (bi / counts[0]) % counts[1], bz = bi / (counts[0] * counts[1]);
+        const std::int64_t lo[3] = {edge(0, bx), edge(1, by), edge(2, bz)};
+        const std::int64_t hi[3] = {edge(0, bx + 1), edge(1, by + 1), edge(2, bz + 1)};
+        detail::split(splats, lo, hi, blocks[(std::size_t) bi], maxCells, maxSplats, perBlock[(std::size_t) bi]);
+    }
+    for (std::vector<Bin> &v : perBlock)
+        for (Bin &b : v) bins.push_back(std::move(b));
     return bins;
 }
 

@@ -175,19 +175,23 @@ void collectInputs(const std::vector<std::string> &args, std::vector<std::string
     }
 }
 
+double now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 struct SinkState
 {
     mlsb::Mesher mesher;
+    double seconds = 0.0;   // time spent welding blocks (serialised, on the worker threads)
 };
 
 void meshSink(std::uint64_t, const mlsb_mesh_sizes *sizes, const void *blob, void *user)
 {
-    static_cast<SinkState *>(user)->mesher.add(*sizes, blob);
-}
-
-double now()
-{
-    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    SinkState *st = static_cast<SinkState *>(user);
+    const double t = now();
+    st->mesher.add(*sizes, blob);
+    st->seconds += now() - t;
 }
 
 }  // namespace
@@ -238,6 +242,7 @@ int main(int argc, char **argv)
         cfg.shape = o.fitShape == "plane" ? MLSB_SHAPE_PLANE : MLSB_SHAPE_SPHERE;
         cfg.boundaryLimit = (float) o.fitBoundaryLimit;
         SinkState state;
+        const double tCreate0 = now();
         mlsb_group *group = nullptr;
         mlsb::check(mlsb_group_create(&cfg, (std::uint32_t) o.deviceThreads, 0, 1, meshSink, &state, &group));
         struct GroupGuard { mlsb_group *g; ~GroupGuard() { mlsb_group_destroy(g); } } guard{group};
@@ -249,12 +254,16 @@ int main(int argc, char **argv)
             mlsb::check(mlsb_group_worker(group, (std::uint32_t) i, &w));
             mlsb::check(mlsb_set_scale_bias(w, grid.spacing, origin));   // ScaleBiasFilter::setScaleBias(grid)
         }
+        const double tCreate = now() - tCreate0;
+        double tGather = 0.0;
         std::vector<std::vector<mlsb_splat>> staged(bins.size());
         for (std::size_t b = 0; b < bins.size(); b++)
         {
             // BucketLoader::operator(): gather the bin's splats (src/bucket_loader.cpp:104-126)
+            const double tg = now();
             staged[b].resize(bins[b].ids.size());
             for (std::size_t i = 0; i < bins[b].ids.size(); i++) staged[b][i] = splats[bins[b].ids[i]];
+            tGather += now() - tg;
             mlsb::check(mlsb_group_submit(group, staged[b].data(), (std::uint32_t) staged[b].size(), bins[b].size, bins[b].offset, b));
         }
         mlsb::check(mlsb_group_wait(group));
@@ -281,6 +290,7 @@ int main(int argc, char **argv)
                       << "output.vertices: " << mesh.vertices.size() << "\noutput.triangles: " << mesh.triangles.size() << "\n";
             std::printf("read.time: %.3f\nbucket.time: %.3f\ndevice.time: %.3f\nmesher.time: %.3f\nrun.time: %.3f\n",
                         tRead - t0, tBucket - tRead, tDevice - tBucket, tEnd - tDevice, tEnd - t0);
+            std::printf("device.create.time: %.3f\ndevice.gather.time: %.3f\ndevice.weld.time: %.3f\n", tCreate, tGather, state.seconds);
             std::printf("splats/s end-to-end: %.3g\n", numSplats / (tEnd - t0));
         }
         return 0;

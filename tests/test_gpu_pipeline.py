@@ -113,3 +113,42 @@ def test_worker_group_matches_single_worker(orc):
                                 keys=np.concatenate([np.zeros(ni, np.uint64), a["external_keys"]])))
     verts, tris = weld_by_key(out)
     assert is_manifold(len(verts), tris) == ""
+
+
+def test_c1_full_size_properties():
+    """BASELINE.json configs[0] at full size (1 M-splat noisy sphere, fit-grid 0.01, single bin),
+    checked through size-independent properties: one shipped block, closed oriented manifold,
+    vertices on the sphere, keys absent (no external vertices), Euler characteristic 2, and the
+    run is reproducible bit for bit (also through the worker group)."""
+    import mlsgpu_b200 as m
+    from mlsgpu_b200 import host
+    s = host.sphere_splats(1_000_000, seed=1, radius=0.005, noise=0.002)
+    g, bins, lo, spacing = host.prepare(s, 0.01)
+    assert len(bins) == 1
+    b = bins[0]
+    assert b["size"].max() <= 256 and len(b["ids"]) == 1_000_000
+    splats = np.ascontiguousarray(g[b["ids"]])
+    bias = lo.astype(np.float32) * spacing
+    runs = []
+    with m.Worker(max_splats=len(splats), max_cells=255, mesh_bytes=256 << 20) as w:
+        w.set_scale_bias(float(spacing), bias)
+        for _ in range(2):
+            w.upload_splats(splats)
+            runs.append(w.process_bin(0, len(splats), b["size"], b["offset"]))
+    got = []
+    with m.WorkerGroup(num_workers=2, sink=lambda tag, blk: got.append(blk), max_splats=len(splats), max_cells=255,
+                       mesh_bytes=256 << 20) as grp:
+        for w in grp.workers:
+            w.set_scale_bias(float(spacing), bias)
+        grp.submit(splats, b["size"], b["offset"])
+        grp.wait()
+    assert len(runs[0]) == 1 and len(got) == 1
+    blk = runs[0][0]
+    for other in (runs[1][0], got[0]):
+        np.testing.assert_array_equal(blk["vertices"].view(np.uint32), other["vertices"].view(np.uint32))
+        np.testing.assert_array_equal(blk["triangles"], other["triangles"])
+    v, t = blk["vertices"], blk["triangles"]
+    assert blk["num_internal"] == len(v) and len(blk["external_keys"]) == 0
+    assert np.abs(np.linalg.norm(v.astype(np.float64), axis=1) - 1.0).max() < 0.01
+    assert len(v) > 100_000 and len(v) - 3 * len(t) // 2 + len(t) == 2      # V - E + F = 2 for a closed genus-0 surface
+    assert is_manifold(len(v), t) == ""

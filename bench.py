@@ -280,6 +280,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: mlsgpu_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_node = None
+    if world > 1 and os.environ.get("MLSB_NUMA_BIND", "1") != "0":
+        from mlsgpu_b200 import host as _host
+        numa_node = _host.bind_to_gpu_numa_node(local)   # before any pinned allocation / worker thread
+        log("rank %d: GPU %d on NUMA node %s, %d CPUs" % (rank, local, numa_node, len(os.sched_getaffinity(0))))
     # more spinning worker threads than cores would fight each other: block on events instead
     if world * args.threads > (os.cpu_count() or 1) * 3 // 4:
         os.environ.setdefault("MLSB_SYNC", "block")

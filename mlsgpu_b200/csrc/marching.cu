@@ -269,6 +269,9 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
             p1 = loadRowMasks(slice1, x0, lane, numCorners);
         }
         const uint32_t inRange = P.cellsX - x0 >= 32 ? 0xFFFFFFFFu : (active ? (1u << (P.cellsX - x0)) - 1 : 0u);
+        // per corner row, combined over its four corners per cell column (x, x+1 of both slices):
+        // all finite / all outside / any outside.  A cell row then needs five more operations.
+        uint32_t pv = p0.f0 & p0.f1 & p1.f0 & p1.f1, pa = p0.s0 & p0.s1 & p1.s0 & p1.s1, po = p0.s0 | p0.s1 | p1.s0 | p1.s1;
 #pragma unroll
         for (int r = 0; r < kGenRows; r++)
         {
@@ -278,10 +281,8 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
             {
                 const RowMasks c0 = loadRowMasks(slice0 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners);
                 const RowMasks c1 = loadRowMasks(slice1 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners);
-                const uint32_t valid = p0.f0 & p0.f1 & c0.f0 & c0.f1 & p1.f0 & p1.f1 & c1.f0 & c1.f1;
-                const uint32_t all = p0.s0 & p0.s1 & c0.s0 & c0.s1 & p1.s0 & p1.s1 & c1.s0 & c1.s1;
-                const uint32_t any = p0.s0 | p0.s1 | c0.s0 | c0.s1 | p1.s0 | p1.s1 | c1.s0 | c1.s1;
-                const uint32_t occ = valid & any & ~all & inRange;
+                const uint32_t cv = c0.f0 & c0.f1 & c1.f0 & c1.f1, ca = c0.s0 & c0.s1 & c1.s0 & c1.s1, co = c0.s0 | c0.s1 | c1.s0 | c1.s1;
+                const uint32_t occ = (pv & cv) & (po | co) & ~(pa & ca) & inRange;
                 if (occ)
                 {
                     if ((occ >> lane) & 1)
@@ -306,6 +307,9 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
                 }
                 p0 = c0;
                 p1 = c1;
+                pv = cv;
+                pa = ca;
+                po = co;
             }
             if (EMIT)
             {

@@ -192,3 +192,35 @@ def partition_bins(bins, world):
         parts[r].append(i)
         loads[r] += len(bins[i]["ids"])
     return [sorted(p) for p in parts]
+
+
+def bind_to_gpu_numa_node(device):
+    """Pins the calling process to the CPUs of the NUMA node the GPU hangs off, so that worker
+    threads and the pinned staging / mesh buffers they first touch are local to the GPU's PCIe root.
+    With one process per GPU on a multi-socket box this keeps the mesh read-back (about twice the
+    input in bytes) off the inter-socket link.  Returns the node, or None if it cannot be found."""
+    import os
+    import subprocess
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(device), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        if len(bus.split(":")[0]) == 8:       # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, subprocess.SubprocessError):
+        return None

@@ -122,3 +122,50 @@ def test_cli_end_to_end_sphere(tmp_path):
     pv, pt = weld_by_key(blocks)
     keep = np.linalg.norm(pv, axis=1) < 1.3                      # drop the island, as --fit-prune did
     assert keep.sum() == len(verts) and keep[pt[:, 0]].sum() == len(tris)
+
+
+@pytest.mark.gpu
+def test_cli_plane_fit_boundary_and_prune(tmp_path):
+    """A C5-style input at reduced size: near-planar terrain with a rectangular hole and isolated
+    islands, plane fit, tightened boundary limit, pruning.  The result must be an oriented manifold
+    WITH boundary (outer edge + hole), lie on the terrain, and contain none of the islands."""
+    exe = build("mlsgpu")
+    rng = np.random.default_rng(11)
+    n = 80000
+    xy = rng.uniform(0.0, 2.0, (n, 2))
+    hole = (np.abs(xy[:, 0] - 1.0) < 0.25) & (np.abs(xy[:, 1] - 1.2) < 0.2)
+    xy = xy[~hole]
+    z = 0.02 * np.sin(3 * xy[:, 0]) * np.cos(2 * xy[:, 1])
+    s = np.zeros(len(xy), host.SPLAT_DTYPE)
+    s["position"] = np.stack([xy[:, 0], xy[:, 1], z], axis=1).astype(np.float32)
+    gx = 0.06 * np.cos(3 * xy[:, 0]) * np.cos(2 * xy[:, 1])
+    gy = -0.04 * np.sin(3 * xy[:, 0]) * np.sin(2 * xy[:, 1])
+    nrm = np.stack([-gx, -gy, np.ones(len(xy))], axis=1)
+    s["normal"] = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
+    s["radius"] = 0.012
+    islands = []
+    for k in range(5):
+        isl = np.zeros(60, host.SPLAT_DTYPE)
+        c = np.array([2.6 + 0.3 * k, 0.5, 0.0])
+        isl["position"] = (c + np.c_[rng.uniform(-0.03, 0.03, (60, 2)), np.zeros(60)]).astype(np.float32)
+        isl["normal"] = (0, 0, 1)
+        isl["radius"] = 0.012
+        islands.append(isl)
+    both = np.concatenate([s] + islands)
+    inp, out = tmp_path / "terrain.ply", tmp_path / "terrain_mesh.ply"
+    plyfile.write_splat_ply(inp, both)
+    r = subprocess.run([exe, "-o", str(out), "--fit-grid", "0.02", "--fit-shape", "plane", "--fit-boundary-limit", "0.5",
+                        "--fit-prune", "0.02", "--levels", "4", "--statistics", str(inp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    stats = dict(line.split(": ") for line in r.stdout.strip().splitlines() if ": " in line)
+    assert int(stats["components.total"]) >= 2 and int(stats["components.kept"]) == 1
+    verts, tris, _ = plyfile.read_mesh_ply(out)
+    assert len(verts) > 5000 and is_manifold(len(verts), tris) == ""
+    assert verts[:, 0].max() < 2.2                        # islands pruned
+    assert np.abs(verts[:, 2] - 0.02 * np.sin(3 * verts[:, 0]) * np.cos(2 * verts[:, 1])).max() < 0.01
+    # open surface: boundary edges exist (outer rim and the hole), and no vertex sits deep inside the hole
+    edges = np.sort(np.concatenate([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [2, 0]]]), axis=1)
+    _, counts = np.unique(edges, axis=0, return_counts=True)
+    assert (counts == 1).sum() > 100 and counts.max() == 2
+    in_hole = (np.abs(verts[:, 0] - 1.0) < 0.15) & (np.abs(verts[:, 1] - 1.2) < 0.1)
+    assert not in_hole.any()

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <sched.h>
 
 namespace mlsb
 {
@@ -82,6 +83,13 @@ int waitStream(mlsb_worker *w)
     {
         MLSB_CUDA(cudaEventRecord(w->syncEvent, w->stream));
         MLSB_CUDA(cudaEventSynchronize(w->syncEvent));
+    }
+    else if (w->yieldingSync)
+    {
+        // poll, giving the core away between polls: for more worker threads than cores
+        cudaError_t e;
+        while ((e = cudaStreamQuery(w->stream)) == cudaErrorNotReady) sched_yield();
+        MLSB_CUDA(e);
     }
     else
         MLSB_CUDA(cudaStreamSynchronize(w->stream));
@@ -174,6 +182,7 @@ int mlsb_worker_create(const mlsb_worker_config *config, mlsb_worker **out)
     {
         const char *mode = getenv("MLSB_SYNC");
         w->blockingSync = mode != nullptr && strcmp(mode, "block") == 0;
+        w->yieldingSync = mode != nullptr && strcmp(mode, "yield") == 0;
         if (cudaEventCreateWithFlags(&w->syncEvent, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
         {
             setError("event creation failed: %s", cudaGetErrorString(cudaGetLastError()));

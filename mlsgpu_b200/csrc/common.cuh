@@ -147,6 +147,7 @@ struct mlsb_worker
     uint64_t launches = 0;
     // host waits: spin (lowest latency) or block on an event (frees the core; MLSB_SYNC=block)
     bool blockingSync = false;
+    bool yieldingSync = false;    // MLSB_SYNC=yield: poll cudaStreamQuery with sched_yield between polls
     cudaEvent_t syncEvent = nullptr;
 };
 

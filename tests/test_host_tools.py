@@ -169,3 +169,78 @@ def test_cli_plane_fit_boundary_and_prune(tmp_path):
     assert (counts == 1).sum() > 100 and counts.max() == 2
     in_hole = (np.abs(verts[:, 0] - 1.0) < 0.15) & (np.abs(verts[:, 1] - 1.2) < 0.1)
     assert not in_hole.any()
+
+
+# ---- the reference's own mesher fixtures (test/test_mesher.cpp:250-340, :671-743, :745-924) ----
+
+def blk(internal, external, keys, indices):
+    v = np.array(list(internal) + list(external), np.float32).reshape(-1, 3)
+    return dict(vertices=v, triangles=np.array(indices, np.uint32).reshape(-1, 3), keys=np.array(keys, np.uint64),
+                num_internal=len(internal))
+
+
+def check_isomorphic(expected_vertices, expected_indices, verts, tris):
+    """checkIsomorphic, test/test_mesher.cpp:450-520: equal up to a permutation of vertices and
+    triangles and a rotation (not reflection) of each triangle; vertices are unique."""
+    ev = [tuple(v) for v in np.array(expected_vertices, np.float32).tolist()]
+    av = [tuple(v) for v in np.asarray(verts).tolist()]
+    assert sorted(ev) == sorted(av) and len(set(av)) == len(av)
+
+    def canon(vs, idx):
+        out = []
+        for t in np.array(idx).reshape(-1, 3).tolist():
+            p = [vs[i] for i in t]
+            k = p.index(min(p))
+            out.append(tuple(p[k:] + p[:k]))
+        return sorted(out)
+    assert canon(ev, expected_indices) == canon(av, tris)
+
+
+def run_mesher(tmp_path, blocks, prune):
+    exe = build("mesher_test")
+    write_blocks(tmp_path / "blocks.bin", blocks)
+    out = tmp_path / "out.ply"
+    subprocess.run([exe, str(tmp_path / "blocks.bin"), repr(prune), str(out)], check=True, capture_output=True)
+    verts, tris, _ = plyfile.read_mesh_ply(out)
+    return verts, tris
+
+
+def test_mesher_reference_weld_fixture(tmp_path):
+    b0 = blk([(0, 0, 1), (0, 0, 2), (0, 0, 3), (0, 0, 4), (0, 0, 5)], [], [], [0, 1, 3, 1, 2, 3, 3, 4, 0])
+    b1 = blk([], [(1, 0, 1), (1, 0, 2), (1, 0, 3), (1, 0, 4)], [0, 0x8000000000000000, 1, 0x8000000000000001],
+             [0, 1, 3, 1, 2, 3, 2, 0, 3])
+    b2 = blk([(0, 1, 0), (0, 2, 0), (0, 3, 0)], [(2, 0, 1), (2, 0, 2)], [0x1234567812345678, 0x12345678],
+             [0, 1, 3, 1, 4, 3, 2, 3, 4, 0, 2, 4, 0, 3, 2])
+    b3 = blk([(3, 3, 3)], [(4, 5, 6), (1, 0, 2), (1, 0, 3), (2, 0, 2)], [100, 0x8000000000000000, 1, 0x12345678],
+             [0, 2, 1, 1, 2, 4, 4, 2, 3])
+    expected_vertices = [(0, 0, 1), (0, 0, 2), (0, 0, 3), (0, 0, 4), (0, 0, 5), (1, 0, 1), (1, 0, 2), (1, 0, 3), (1, 0, 4),
+                         (0, 1, 0), (0, 2, 0), (0, 3, 0), (2, 0, 1), (2, 0, 2), (3, 3, 3), (4, 5, 6)]
+    expected_indices = [0, 1, 3, 1, 2, 3, 3, 4, 0, 5, 6, 8, 6, 7, 8, 7, 5, 8, 9, 10, 12, 10, 13, 12, 11, 12, 13, 9, 11, 13,
+                        9, 12, 11, 14, 6, 15, 15, 6, 13, 13, 6, 7]
+    verts, tris = run_mesher(tmp_path, [b0, b1, b2, b3], 0.0)
+    check_isomorphic(expected_vertices, expected_indices, verts, tris)
+
+
+def test_mesher_reference_prune_fixture(tmp_path):
+    b0 = blk([(0, 0, 0), (1, 0, 0), (2, 0, 0), (3, 0, 0), (4, 0, 0)], [(0, 3, 0), (1, 3, 0), (2, 3, 0)], [0x30, 0x31, 0x32],
+             [0, 4, 1, 1, 4, 2, 2, 4, 3, 5, 7, 6])
+    b1 = blk([(0, 1, 0), (1, 1, 0), (2, 1, 0), (3, 1, 0), (4, 1, 0), (5, 1, 0), (0, 2, 0), (3, 2, 0)],
+             [(2, 2, 0), (4, 2, 0), (0, 3, 0), (2, 3, 0), (4, 3, 0)], [0x22, 0x24, 0x30, 0x32, 0x34],
+             [0, 5, 1, 1, 5, 2, 2, 5, 3, 3, 5, 4, 6, 7, 9, 9, 7, 8, 10, 12, 11])
+    b2 = blk([], [(1, 3, 0), (2, 3, 0), (3, 3, 0)], [0x31, 0x32, 0x33], [0, 1, 2])
+    b3 = blk([(1, 2, 0), (5, 3, 0)], [(2, 2, 0), (3, 3, 0), (4, 2, 0), (4, 3, 0), (2, 3, 0)], [0x22, 0x33, 0x24, 0x34, 0x32],
+             [6, 5, 3, 4, 2, 0, 3, 5, 1])
+    expected_vertices = [(0, 1, 0), (1, 1, 0), (2, 1, 0), (3, 1, 0), (4, 1, 0), (5, 1, 0), (0, 3, 0), (1, 3, 0), (2, 3, 0),
+                         (3, 3, 0), (4, 3, 0), (5, 3, 0)]
+    expected_indices = [0, 5, 1, 1, 5, 2, 2, 5, 3, 3, 5, 4, 6, 8, 7, 7, 8, 9, 9, 8, 10, 9, 10, 11, 6, 10, 8]
+    # 22 vertices in total, threshold 6 (setPruneThreshold(6.5 / 22.0))
+    verts, tris = run_mesher(tmp_path, [b0, b1, b2, b3], 6.5 / 22.0)
+    check_isomorphic(expected_vertices, expected_indices, verts, tris)
+
+
+def test_mesher_reference_empty_fixture(tmp_path):
+    # TestMesherBase::testEmpty: no blocks (or empty blocks) give an empty, well-formed PLY
+    verts, tris = run_mesher(tmp_path, [], 0.0)
+    assert len(verts) == 0 and len(tris) == 0
+    verts, tris = run_mesher(tmp_path, [blk([], [], [], [])], 0.02)
+    assert len(verts) == 0 and len(tris) == 0

@@ -158,7 +158,8 @@ def test_cli_plane_fit_boundary_and_prune(tmp_path):
                         "--fit-prune", "0.02", "--levels", "4", "--statistics", str(inp)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     stats = dict(line.split(": ") for line in r.stdout.strip().splitlines() if ": " in line)
-    assert int(stats["components.total"]) >= 2 and int(stats["components.kept"]) == 1
+    # (with the tightened boundary limit the tiny islands may be rejected by the boundary test already)
+    assert int(stats["components.total"]) >= 1 and int(stats["components.kept"]) == 1
     verts, tris, _ = plyfile.read_mesh_ply(out)
     assert len(verts) > 5000 and is_manifold(len(verts), tris) == ""
     assert verts[:, 0].max() < 2.2                        # islands pruned

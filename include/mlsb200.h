@@ -198,11 +198,18 @@ MLSB_API int mlsb_group_create(const mlsb_worker_config *config, uint32_t numWor
                                int stageSplats, mlsb_group_sink sink, void *user, mlsb_group **out);
 MLSB_API void mlsb_group_destroy(mlsb_group *g);
 /* Queues one bin (WorkerGroup::get + push, src/worker_group.h:137-199); blocks while the queue is
- * full.  size = corners per axis, offset = low extent of the bin in the full grid. */
+ * full.  size = corners per axis, offset = low extent of the bin in the full grid.
+ * Bins are taken in submission order, so with stageSplats the splat memory of the bin submitted
+ * (queueDepth + numWorkers) submits earlier is no longer read once a submit returns: a loader can
+ * cycle through queueDepth + numWorkers + 1 gather buffers. */
 MLSB_API int mlsb_group_submit(mlsb_group *g, const mlsb_splat *splats, uint32_t numSplats,
                                const uint32_t size[3], const int32_t offset[3], uint64_t tag);
 /* Blocks until every queued bin has been processed; returns the first error any worker hit. */
 MLSB_API int mlsb_group_wait(mlsb_group *g);
+/* By default the sink is called by one worker at a time, like the reference's single mesher thread
+ * (MesherGroup, src/workers.h:511-560).  enabled != 0: workers call it concurrently and the
+ * consumer does its own locking (set before the first submit). */
+MLSB_API int mlsb_group_set_concurrent_sink(mlsb_group *g, int enabled);
 /* Worker i of the group (to set scale/bias, boundary limit, profiling; not while bins are queued). */
 MLSB_API int mlsb_group_worker(mlsb_group *g, uint32_t index, mlsb_worker **worker);
 /* Totals since creation: bins and splats processed, bytes of mesh handed to the sink. */

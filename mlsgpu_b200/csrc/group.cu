@@ -39,7 +39,8 @@ struct mlsb_group
 
     mlsb_group_sink sink = nullptr;
     void *user = nullptr;
-    std::mutex sinkMutex;   // meshes are delivered serialised, like the single mesher thread
+    std::mutex sinkMutex;   // meshes are delivered serialised, like the single mesher thread ...
+    bool concurrentSink = false;   // ... unless the consumer does its own locking
 
     std::mutex errorMutex;
     int status = MLSB_OK;
@@ -64,8 +65,13 @@ void groupTrampoline(const mlsb_mesh_sizes *sizes, const void *blob, void *user)
     g->meshBytes += mlsb_mesh_host_bytes(sizes);
     if (g->sink)
     {
-        std::lock_guard<std::mutex> lock(g->sinkMutex);
-        g->sink(ctx->tag, sizes, blob, g->user);
+        if (g->concurrentSink)
+            g->sink(ctx->tag, sizes, blob, g->user);
+        else
+        {
+            std::lock_guard<std::mutex> lock(g->sinkMutex);
+            g->sink(ctx->tag, sizes, blob, g->user);
+        }
     }
 }
 
@@ -204,6 +210,13 @@ int mlsb_group_wait(mlsb_group *g)
     if (st != MLSB_OK) setError("%s", g->message.c_str());
     g->status = MLSB_OK;
     return st;
+}
+
+int mlsb_group_set_concurrent_sink(mlsb_group *g, int enabled)
+{
+    MLSB_REQUIRE(g != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null group");
+    g->concurrentSink = enabled != 0;
+    return MLSB_OK;
 }
 
 int mlsb_group_worker(mlsb_group *g, uint32_t index, mlsb_worker **worker)

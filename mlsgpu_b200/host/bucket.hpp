@@ -44,12 +44,26 @@ inline Grid boundingGrid(const std::vector<mlsb_splat> &splats, float spacing, s
 {
     if (splats.empty()) throw std::runtime_error("no splats");
     double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
-    for (const mlsb_splat &s : splats)
+#pragma omp parallel
+    {
+        double tmn[3] = {1e300, 1e300, 1e300}, tmx[3] = {-1e300, -1e300, -1e300};
+#pragma omp for schedule(static) nowait
+        for (std::int64_t i = 0; i < (std::int64_t) splats.size(); i++)
+        {
+            const mlsb_splat &s = splats[(std::size_t) i];
+            for (int a = 0; a < 3; a++)
+            {
+                tmn[a] = std::min(tmn[a], (double) s.position[a] - s.radius);
+                tmx[a] = std::max(tmx[a], (double) s.position[a] + s.radius);
+            }
+        }
+#pragma omp critical(mlsb_bounding_grid)
         for (int a = 0; a < 3; a++)
         {
-            mn[a] = std::min(mn[a], (double) s.position[a] - s.radius);
-            mx[a] = std::max(mx[a], (double) s.position[a] + s.radius);
+            mn[a] = std::min(mn[a], tmn[a]);
+            mx[a] = std::max(mx[a], tmx[a]);
         }
+    }
     Grid g;
     g.spacing = spacing;
     for (int a = 0; a < 3; a++)
@@ -65,8 +79,10 @@ inline Grid boundingGrid(const std::vector<mlsb_splat> &splats, float spacing, s
 inline void worldToGrid(std::vector<mlsb_splat> &splats, const Grid &g)
 {
     const float inv = 1.0f / g.spacing;
-    for (mlsb_splat &s : splats)
+#pragma omp parallel for schedule(static)
+    for (std::int64_t i = 0; i < (std::int64_t) splats.size(); i++)
     {
+        mlsb_splat &s = splats[(std::size_t) i];
         for (int a = 0; a < 3; a++) s.position[a] = (s.position[a] - 0.0f) * inv - (float) g.lo[a];
         s.radius *= inv;
     }
@@ -113,55 +129,102 @@ inline void split(const std::vector<mlsb_splat> &splats, const std::int64_t lo[3
 /// splats: grid coordinates (after worldToGrid).  Bins come out in z-major block order.
 inline std::vector<Bin> makeBins(const std::vector<mlsb_splat> &splats, const Grid &g, std::int64_t maxCells, std::size_t maxSplats)
 {
-    std::vector<Bin> bins;
     std::int64_t n[3], counts[3];
+    std::vector<float> edges[3];   // block b of axis a spans cells [edges[a][b], edges[a][b + 1]]
     for (int a = 0; a < 3; a++)
     {
         n[a] = std::max<std::int64_t>(g.numCells(a), 1);
         counts[a] = (n[a] + maxCells - 1) / maxCells;
+        for (std::int64_t b = 0; b <= counts[a]; b++) edges[a].push_back((float) (b * n[a] / counts[a]));
     }
-    // candidate lists per block from each splat's bounding box in block units; every thread takes
-    // a contiguous range of splats, so concatenating the per-thread lists keeps ids ascending
     const std::size_t numBlocks = (std::size_t) (counts[0] * counts[1] * counts[2]);
+    const std::int64_t numSplats = (std::int64_t) splats.size();
+
+    // The blocks a splat's ball reaches, per axis (the same closed-interval test as detail::split).
+    auto range = [&](const mlsb_splat &s, int a, std::int64_t &first, std::int64_t &last) {
+        const float l = s.position[a] - s.radius, h = s.position[a] + s.radius;
+        const float scale = (float) counts[a] / (float) n[a];
+        first = std::min(std::max<std::int64_t>((std::int64_t) std::floor(l * scale) - 1, 0), counts[a] - 1);
+        last = std::min(std::max<std::int64_t>((std::int64_t) std::floor(h * scale) + 1, 0), counts[a] - 1);
+        while (first < last && !(h >= edges[a][first] && l <= edges[a][first + 1])) first++;
+        while (last > first && !(h >= edges[a][last] && l <= edges[a][last + 1])) last--;
+        return h >= edges[a][first] && l <= edges[a][first + 1];
+    };
+
+    // Two passes over the splats with the same static schedule: count per (thread, block), then
+    // fill exact-size lists.  Each thread owns a contiguous range of splats and the threads'
+    // segments of a block are laid out in thread order, so the ids of a block come out ascending.
     std::vector<std::vector<std::uint32_t>> blocks(numBlocks);
-    auto edge = [&](int a, std::int64_t b) { return b * n[a] / counts[a]; };
+    std::vector<std::vector<std::size_t>> cursor;
 #pragma omp parallel
     {
-        std::vector<std::vector<std::uint32_t>> mine(numBlocks);
-#pragma omp for schedule(static)
-        for (std::int64_t id = 0; id < (std::int64_t) splats.size(); id++)
+        const int numThreads = omp_get_num_threads(), me = omp_get_thread_num();
+#pragma omp single
+        cursor.assign((std::size_t) numThreads, std::vector<std::size_t>(numBlocks, 0));
+        const std::int64_t begin = numSplats * me / numThreads, end = numSplats * (me + 1) / numThreads;
+        std::vector<std::size_t> &mine = cursor[(std::size_t) me];
+        for (int pass = 0; pass < 2; pass++)
         {
-            const mlsb_splat &s = splats[(std::size_t) id];
-            std::int64_t first[3], last[3];
-            for (int a = 0; a < 3; a++)
+            for (std::int64_t id = begin; id < end; id++)
             {
-                const double l = (double) s.position[a] - s.radius, h = (double) s.position[a] + s.radius;
-                std::int64_t f = (std::int64_t) std::floor(l * counts[a] / n[a]) - 1, t = (std::int64_t) std::floor(h * counts[a] / n[a]) + 1;
-                first[a] = std::min(std::max<std::int64_t>(f, 0), counts[a] - 1);
-                last[a] = std::min(std::max<std::int64_t>(t, 0), counts[a] - 1);
+                const mlsb_splat &s = splats[(std::size_t) id];
+                std::int64_t first[3], last[3];
+                if (!(range(s, 0, first[0], last[0]) && range(s, 1, first[1], last[1]) && range(s, 2, first[2], last[2])))
+                    continue;
+                for (std::int64_t bz = first[2]; bz <= last[2]; bz++)
+                    for (std::int64_t by = first[1]; by <= last[1]; by++)
+                        for (std::int64_t bx = first[0]; bx <= last[0]; bx++)
+                        {
+                            const std::size_t b = (std::size_t) ((bz * counts[1] + by) * counts[0] + bx);
+                            if (pass == 0)
+                                mine[b]++;
+                            else
+                                blocks[b][mine[b]++] = (std::uint32_t) id;
+                        }
             }
-            for (std::int64_t bz = first[2]; bz <= last[2]; bz++)
-                for (std::int64_t by = first[1]; by <= last[1]; by++)
-                    for (std::int64_t bx = first[0]; bx <= last[0]; bx++)
-                        mine[(std::size_t) ((bz * counts[1] + by) * counts[0] + bx)].push_back((std::uint32_t) id);
-        }
-#pragma omp for ordered schedule(static, 1)
-        for (int t = 0; t < omp_get_num_threads(); t++)
-        {
-#pragma omp ordered
-            for (std::size_t b = 0; b < numBlocks; b++) blocks[b].insert(blocks[b].end(), mine[b].begin(), mine[b].end());
+            if (pass == 0)
+            {
+#pragma omp barrier
+#pragma omp for schedule(static)
+                for (std::int64_t b = 0; b < (std::int64_t) numBlocks; b++)
+                {
+                    std::size_t total = 0;
+                    for (int t = 0; t < numThreads; t++)
+                    {
+                        const std::size_t c = cursor[(std::size_t) t][(std::size_t) b];
+                        cursor[(std::size_t) t][(std::size_t) b] = total;
+                        total += c;
+                    }
+                    blocks[(std::size_t) b].resize(total);
+                }   // implicit barrier
+            }
         }
     }
-    // blocks are independent: split them in parallel, then flatten in z-major block order
+    // blocks are independent: a block that fits becomes a bin as it is, the rest are halved
     std::vector<std::vector<Bin>> perBlock(numBlocks);
 #pragma omp parallel for schedule(dynamic, 1)
     for (std::int64_t bi = 0; bi < (std::int64_t) numBlocks; bi++)
     {
+        std::vector<std::uint32_t> &ids = blocks[(std::size_t) bi];
+        if (ids.empty()) continue;
         const std::int64_t bx = bi % counts[0], by = (bi / counts[0]) % counts[1], bz = bi / (counts[0] * counts[1]);
-        const std::int64_t lo[3] = {edge(0, bx), edge(1, by), edge(2, bz)};
-        const std::int64_t hi[3] = {edge(0, bx + 1), edge(1, by + 1), edge(2, bz + 1)};
-        detail::split(splats, lo, hi, blocks[(std::size_t) bi], maxCells, maxSplats, perBlock[(std::size_t) bi]);
+        const std::int64_t lo[3] = {(std::int64_t) edges[0][bx], (std::int64_t) edges[1][by], (std::int64_t) edges[2][bz]};
+        const std::int64_t hi[3] = {(std::int64_t) edges[0][bx + 1], (std::int64_t) edges[1][by + 1], (std::int64_t) edges[2][bz + 1]};
+        if (ids.size() <= maxSplats)   // the block's extent is within maxCells by construction
+        {
+            Bin b;
+            for (int a = 0; a < 3; a++)
+            {
+                b.offset[a] = (std::int32_t) lo[a];
+                b.size[a] = (std::uint32_t) (hi[a] - lo[a] + 1);
+            }
+            b.ids.swap(ids);
+            perBlock[(std::size_t) bi].push_back(std::move(b));
+        }
+        else
+            detail::split(splats, lo, hi, ids, maxCells, maxSplats, perBlock[(std::size_t) bi]);
     }
+    std::vector<Bin> bins;
     for (std::vector<Bin> &v : perBlock)
         for (Bin &b : v) bins.push_back(std::move(b));
     return bins;

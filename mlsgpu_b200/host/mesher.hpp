@@ -10,13 +10,15 @@
 //  * at write time components (root clumps) with fewer than floor(fit-prune x total vertices)
 //    vertices are dropped and the rest are compacted (getStatistics :491-513, write :763-852).
 // The reference streams blocks through temporary files to bound memory; this version keeps the
-// mesh in host memory.
+// mesh in host memory, one chunk per block, and only the seam bookkeeping (external vertices) is
+// serialised: the per-block work runs concurrently on the device workers' threads.
 #ifndef MLSB200_MESHER_HPP
 #define MLSB200_MESHER_HPP
 
 #include <algorithm>
 #include <array>
 #include <cstdint>
+#include <memory>
 #include <unordered_map>
 #include <vector>
 
@@ -31,77 +33,136 @@ public:
     typedef std::array<float, 3> vertex_type;
     typedef std::array<std::uint32_t, 3> triangle_type;
 
-    /// One shipped-out block in the HostKeyMesh layout (src/mesh.cpp:51-60).  Not thread-safe:
-    /// the worker group delivers blocks serialised, like the reference's single mesher thread.
-    void add(const mlsb_mesh_sizes &sizes, const void *blob)
+    /// One shipped-out block (HostKeyMesh layout, src/mesh.cpp:51-60) on its way into the mesh.
+    /// The blob pointers are only used by prepare/commit/complete, i.e. inside the sink call.
+    struct Block
     {
-        const std::size_t nv = sizes.numVertices, nt = sizes.numTriangles, ni = sizes.numInternalVertices;
-        const std::uint64_t *keys = static_cast<const std::uint64_t *>(blob);
-        const vertex_type *verts = reinterpret_cast<const vertex_type *>(keys + (nv - ni));
-        const triangle_type *tris = reinterpret_cast<const triangle_type *>(verts + nv);
+        std::size_t nv = 0, ni = 0, nt = 0;
+        const std::uint64_t *keys = nullptr;
+        const vertex_type *verts = nullptr;
+        const triangle_type *tris = nullptr;
+        std::vector<std::uint32_t> clumpOfLocal;     // local clump index of every vertex of the blob
+        std::vector<std::uint64_t> clumpVertices;    // vertices per local clump
+        std::vector<std::uint32_t> remapExternal;    // global index of every external vertex of the blob
+
+        // what the mesher keeps: the block's internal vertices followed by the external vertices it
+        // was the first to see, numbered firstVertex.. in the welded mesh; its triangles in welded
+        // numbering; the (global) clump of every kept vertex is firstClump + vertexClump[i]
+        std::uint32_t firstVertex = 0, firstClump = 0;
+        std::vector<vertex_type> vertices;
+        std::vector<std::uint32_t> vertexClump;
+        std::vector<triangle_type> triangles;
+    };
+
+    /// Step 1, thread-safe: local components and a private copy of the internal vertices.
+    static std::unique_ptr<Block> prepare(const mlsb_mesh_sizes &sizes, const void *blob)
+    {
+        std::unique_ptr<Block> block(new Block);
+        Block &b = *block;
+        const std::size_t nv = b.nv = sizes.numVertices, nt = b.nt = sizes.numTriangles;
+        const std::size_t ni = b.ni = sizes.numInternalVertices;
+        b.keys = static_cast<const std::uint64_t *>(blob);
+        b.verts = reinterpret_cast<const vertex_type *>(b.keys + (nv - ni));
+        b.tris = reinterpret_cast<const triangle_type *>(b.verts + nv);
 
         // ---- local components ----
+        static thread_local std::vector<std::int32_t> local;
         local.resize(nv);
         for (std::size_t i = 0; i < nv; i++) local[i] = (std::int32_t) i;
         for (std::size_t i = 0; i < nt; i++)
         {
             // two edges are enough: the third is redundant (src/mesher.cpp:230-234)
-            mergeLocal(tris[i][0], tris[i][1]);
-            mergeLocal(tris[i][1], tris[i][2]);
+            mergeLocal(local, b.tris[i][0], b.tris[i][1]);
+            mergeLocal(local, b.tris[i][1], b.tris[i][2]);
         }
         // ---- one clump per local component ----
-        clumpOfLocal.resize(nv);
+        b.clumpOfLocal.resize(nv);
         for (std::size_t i = 0; i < nv; i++)
             if (local[i] == (std::int32_t) i)
             {
-                clumpOfLocal[i] = (std::uint32_t) clumps.size();
-                clumps.push_back(Clump{(std::uint32_t) clumps.size(), 0});
+                b.clumpOfLocal[i] = (std::uint32_t) b.clumpVertices.size();
+                b.clumpVertices.push_back(0);
             }
+        // a root is the smallest index of its component, so its entry is final before any of its
+        // members reads it
         for (std::size_t i = 0; i < nv; i++)
         {
-            const std::uint32_t c = clumpOfLocal[findLocal((std::int32_t) i)];
-            clumpOfLocal[i] = c;
-            clumps[c].vertices++;
+            const std::uint32_t c = b.clumpOfLocal[findLocal(local, (std::int32_t) i)];
+            b.clumpOfLocal[i] = c;
+            b.clumpVertices[c]++;
         }
-        // ---- global vertices: internal ones are new, external ones are looked up by key ----
-        remap.resize(nv);
-        // (no exact-size reserve here: it would defeat the vectors' geometric growth and recopy
-        // the whole mesh for every block)
-        for (std::size_t i = 0; i < ni; i++)
-        {
-            remap[i] = (std::uint32_t) vertices.size();
-            vertices.push_back(verts[i]);
-            vertexClump.push_back(clumpOfLocal[i]);
-        }
+        b.vertices.reserve(nv);
+        b.vertices.assign(b.verts, b.verts + ni);
+        b.vertexClump.reserve(nv);
+        b.vertexClump.assign(b.clumpOfLocal.begin(), b.clumpOfLocal.begin() + ni);
+        return block;
+    }
+
+    /// Step 2, serialised by the caller: numbers the block's vertices and clumps and resolves its
+    /// external vertices through the key map.  The mesher takes ownership of the block.
+    Block &commit(std::unique_ptr<Block> block)
+    {
+        Block &b = *block;
+        const std::size_t nv = b.nv, ni = b.ni;
+        b.firstClump = (std::uint32_t) clumps.size();
+        for (std::size_t c = 0; c < b.clumpVertices.size(); c++)
+            clumps.push_back(Clump{b.firstClump + (std::uint32_t) c, b.clumpVertices[c]});
+        b.firstVertex = (std::uint32_t) totalVertices;
+        b.remapExternal.resize(nv - ni);
         for (std::size_t i = ni; i < nv; i++)
         {
-            auto added = keyMap.insert(std::make_pair(keys[i - ni], (std::uint32_t) vertices.size()));
+            const std::uint32_t clump = b.firstClump + b.clumpOfLocal[i];
+            const Seen fresh = {b.firstVertex + (std::uint32_t) b.vertices.size(), clump};
+            auto added = keyMap.insert(std::make_pair(b.keys[i - ni], fresh));
             if (added.second)
             {
-                vertices.push_back(verts[i]);
-                vertexClump.push_back(clumpOfLocal[i]);
+                b.vertices.push_back(b.verts[i]);
+                b.vertexClump.push_back(b.clumpOfLocal[i]);
             }
             else
             {
                 // the same vertex seen from two blocks: unify their clumps, count it once
-                const std::uint32_t root = mergeClumps(clumpOfLocal[i], vertexClump[added.first->second]);
+                const std::uint32_t root = mergeClumps(clump, added.first->second.clump);
                 clumps[root].vertices--;
             }
-            remap[i] = added.first->second;
+            b.remapExternal[i - ni] = added.first->second.vertex;
         }
-        const std::size_t firstTriangle = triangles.size();
-        triangles.resize(firstTriangle + nt);
-        for (std::size_t i = 0; i < nt; i++)
-            triangles[firstTriangle + i] = {remap[tris[i][0]], remap[tris[i][1]], remap[tris[i][2]]};
+        totalVertices += b.vertices.size();
+        totalTriangles += b.nt;
+        blocks.push_back(std::move(block));
+        return b;
     }
 
-    std::size_t numVertices() const { return vertices.size(); }
-    std::size_t numTriangles() const { return triangles.size(); }
+    /// Step 3, thread-safe (touches only the block): triangles in welded numbering.
+    static void complete(Block &b)
+    {
+        const std::size_t ni = b.ni;
+        const std::uint32_t firstVertex = b.firstVertex;
+        const std::uint32_t *ext = b.remapExternal.data();
+        auto remap = [=](std::uint32_t v) { return v < ni ? firstVertex + v : ext[v - ni]; };
+        b.triangles.resize(b.nt);
+        for (std::size_t i = 0; i < b.nt; i++)
+            b.triangles[i] = {remap(b.tris[i][0]), remap(b.tris[i][1]), remap(b.tris[i][2])};
+        // scratch that is not needed any more
+        std::vector<std::uint32_t>().swap(b.clumpOfLocal);
+        std::vector<std::uint32_t>().swap(b.remapExternal);
+        b.keys = nullptr;
+        b.verts = nullptr;
+        b.tris = nullptr;
+    }
 
+    /// All three steps, for a single-threaded consumer.
+    void add(const mlsb_mesh_sizes &sizes, const void *blob) { complete(commit(prepare(sizes, blob))); }
+
+    std::size_t numVertices() const { return totalVertices; }
+    std::size_t numTriangles() const { return totalTriangles; }
+
+    /// The welded mesh in chunks (one per block); vertex indices run across the chunks in order.
     struct Result
     {
-        std::vector<vertex_type> vertices;
-        std::vector<triangle_type> triangles;
+        std::vector<std::vector<vertex_type>> vertexChunks;
+        std::vector<std::vector<triangle_type>> triangleChunks;
+        std::size_t numVertices = 0, numTriangles = 0;
         std::size_t totalComponents = 0, keptComponents = 0;
         std::uint64_t thresholdVertices = 0;
     };
@@ -110,7 +171,6 @@ public:
     Result finish(double pruneThreshold)
     {
         Result r;
-        const std::size_t n = vertices.size();
         std::uint64_t total = 0;
         for (std::size_t c = 0; c < clumps.size(); c++)
             if (clumps[c].parent == c) total += clumps[c].vertices;
@@ -123,27 +183,62 @@ public:
                 keep[c] = clumps[c].vertices >= r.thresholdVertices;
                 r.keptComponents += keep[c];
             }
+        const std::int64_t numBlocks = (std::int64_t) blocks.size();
+        r.vertexChunks.resize(blocks.size());
+        r.triangleChunks.resize(blocks.size());
         if (r.keptComponents == r.totalComponents)
         {
-            // nothing to prune: hand the mesh over as it is
-            r.vertices.swap(vertices);
-            r.triangles.swap(triangles);
+            // nothing to prune: hand the chunks over as they are
+            for (std::int64_t i = 0; i < numBlocks; i++)
+            {
+                r.vertexChunks[i].swap(blocks[i]->vertices);
+                r.triangleChunks[i].swap(blocks[i]->triangles);
+            }
+            r.numVertices = totalVertices;
+            r.numTriangles = totalTriangles;
             return r;
         }
-        std::vector<std::uint32_t> newIndex(n, UINT32_MAX);
-        for (std::size_t i = 0; i < n; i++)
-            if (keep[findClump(vertexClump[i])])
-            {
-                newIndex[i] = (std::uint32_t) r.vertices.size();
-                r.vertices.push_back(vertices[i]);
-            }
-        r.triangles.reserve(triangles.size());
-        for (const triangle_type &t : triangles)
-            if (newIndex[t[0]] != UINT32_MAX)
-            {
-                triangle_type o = {newIndex[t[0]], newIndex[t[1]], newIndex[t[2]]};
-                r.triangles.push_back(o);
-            }
+        // every clump's verdict, so that the per-block passes below only read
+        std::vector<char> keepClump(clumps.size());
+        for (std::size_t c = 0; c < clumps.size(); c++) keepClump[c] = keep[findClump((std::uint32_t) c)];
+        // pass 1: kept vertices per block; prefix; pass 2: new numbering; pass 3: triangles
+        std::vector<std::size_t> firstKept(blocks.size() + 1, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (std::int64_t i = 0; i < numBlocks; i++)
+        {
+            const Block &b = *blocks[i];
+            std::size_t kept = 0;
+            for (std::uint32_t c : b.vertexClump) kept += keepClump[b.firstClump + c];
+            firstKept[i + 1] = kept;
+        }
+        for (std::int64_t i = 0; i < numBlocks; i++) firstKept[i + 1] += firstKept[i];
+        std::vector<std::uint32_t> newIndex(totalVertices, UINT32_MAX);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (std::int64_t i = 0; i < numBlocks; i++)
+        {
+            const Block &b = *blocks[i];
+            std::vector<vertex_type> &out = r.vertexChunks[i];
+            out.reserve(firstKept[i + 1] - firstKept[i]);
+            for (std::size_t v = 0; v < b.vertices.size(); v++)
+                if (keepClump[b.firstClump + b.vertexClump[v]])
+                {
+                    newIndex[b.firstVertex + v] = (std::uint32_t) (firstKept[i] + out.size());
+                    out.push_back(b.vertices[v]);
+                }
+        }
+#pragma omp parallel for schedule(dynamic, 1)
+        for (std::int64_t i = 0; i < numBlocks; i++)
+        {
+            std::vector<triangle_type> &out = r.triangleChunks[i];
+            for (const triangle_type &t : blocks[i]->triangles)
+                if (newIndex[t[0]] != UINT32_MAX)   // a triangle's vertices share one component
+                {
+                    triangle_type o = {newIndex[t[0]], newIndex[t[1]], newIndex[t[2]]};
+                    out.push_back(o);
+                }
+        }
+        r.numVertices = firstKept[blocks.size()];
+        for (const std::vector<triangle_type> &c : r.triangleChunks) r.numTriangles += c.size();
         return r;
     }
 
@@ -153,8 +248,13 @@ private:
         std::uint32_t parent;
         std::uint64_t vertices;
     };
+    struct Seen
+    {
+        std::uint32_t vertex;   // welded index of an external vertex
+        std::uint32_t clump;    // the clump it belonged to where it was first seen
+    };
 
-    std::int32_t findLocal(std::int32_t x)
+    static std::int32_t findLocal(std::vector<std::int32_t> &local, std::int32_t x)
     {
         while (local[x] != x)
         {
@@ -163,9 +263,9 @@ private:
         }
         return x;
     }
-    void mergeLocal(std::uint32_t a, std::uint32_t b)
+    static void mergeLocal(std::vector<std::int32_t> &local, std::uint32_t a, std::uint32_t b)
     {
-        const std::int32_t ra = findLocal((std::int32_t) a), rb = findLocal((std::int32_t) b);
+        const std::int32_t ra = findLocal(local, (std::int32_t) a), rb = findLocal(local, (std::int32_t) b);
         if (ra != rb) local[std::max(ra, rb)] = std::min(ra, rb);
     }
     std::uint32_t findClump(std::uint32_t x)
@@ -188,13 +288,10 @@ private:
         return lo;
     }
 
-    std::vector<vertex_type> vertices;
-    std::vector<triangle_type> triangles;
-    std::vector<std::uint32_t> vertexClump;   // clump of every global vertex (as first seen)
+    std::vector<std::unique_ptr<Block>> blocks;
     std::vector<Clump> clumps;
-    std::vector<std::int32_t> local;
-    std::vector<std::uint32_t> clumpOfLocal, remap;
-    std::unordered_map<std::uint64_t, std::uint32_t> keyMap;
+    std::unordered_map<std::uint64_t, Seen> keyMap;
+    std::size_t totalVertices = 0, totalTriangles = 0;
 };
 
 }  // namespace mlsb

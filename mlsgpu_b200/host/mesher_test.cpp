@@ -1,10 +1,14 @@
 // Test harness for the host mesher and PLY writer (driven by tests/test_host_tools.py).
-//   mesher_test blocks.bin prune out.ply
+//   mesher_test blocks.bin prune out.ply [threads]
+// With threads > 1 the blocks go through Mesher::prepare / commit / complete from that many threads,
+// the way the device workers' sink drives it in mlsgpu.cpp.
 // blocks.bin: uint64 numBlocks, then per block uint64 nv, nt, ni followed by the HostKeyMesh blob
 // ([keys of external vertices][float3 vertices][uint32x3 triangles]).
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "mesher.hpp"
@@ -13,27 +17,50 @@
 
 int main(int argc, char **argv)
 {
-    if (argc != 4) return 2;
+    if (argc != 4 && argc != 5) return 2;
+    const int threads = argc == 5 ? std::atoi(argv[4]) : 1;
     std::FILE *f = std::fopen(argv[1], "rb");
     if (!f) return 2;
     std::uint64_t numBlocks = 0;
     if (std::fread(&numBlocks, 8, 1, f) != 1) return 2;
     mlsb::Mesher mesher;
+    std::vector<mlsb_mesh_sizes> sizes(numBlocks);
+    std::vector<std::vector<std::uint64_t>> blobs(numBlocks);
     for (std::uint64_t b = 0; b < numBlocks; b++)
     {
         std::uint64_t h[3];
         if (std::fread(h, 8, 3, f) != 3) return 2;
-        mlsb_mesh_sizes sizes{h[0], h[1], h[2]};
-        std::vector<std::uint64_t> blob((mlsb::MeshSizes(sizes).getHostBytes() + 7) / 8 + 1);
+        sizes[b] = mlsb_mesh_sizes{h[0], h[1], h[2]};
+        blobs[b].resize((mlsb::MeshSizes(sizes[b]).getHostBytes() + 7) / 8 + 1);
         const std::size_t bytes = 8 * (h[0] - h[2]) + 12 * h[0] + 12 * h[1];
-        if (bytes && std::fread(blob.data(), 1, bytes, f) != bytes) return 2;
-        mesher.add(sizes, blob.data());
+        if (bytes && std::fread(blobs[b].data(), 1, bytes, f) != bytes) return 2;
     }
     std::fclose(f);
+    if (threads <= 1)
+        for (std::uint64_t b = 0; b < numBlocks; b++) mesher.add(sizes[b], blobs[b].data());
+    else
+    {
+        std::mutex mutex;
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++)
+            pool.emplace_back([&, t] {
+                for (std::uint64_t b = (std::uint64_t) t; b < numBlocks; b += (std::uint64_t) threads)
+                {
+                    std::unique_ptr<mlsb::Mesher::Block> prepared = mlsb::Mesher::prepare(sizes[b], blobs[b].data());
+                    mlsb::Mesher::Block *block;
+                    {
+                        std::lock_guard<std::mutex> lock(mutex);
+                        block = &mesher.commit(std::move(prepared));
+                    }
+                    mlsb::Mesher::complete(*block);
+                }
+            });
+        for (std::thread &t : pool) t.join();
+    }
     mlsb::Mesher::Result r = mesher.finish(std::atof(argv[2]));
     mlsb::PlyWriter writer;
     writer.addComment("mesher_test");
-    writer.write(argv[3], r.vertices, r.triangles);
+    writer.write(argv[3], r.vertexChunks, r.triangleChunks);
     std::cout << mesher.numVertices() << " " << mesher.numTriangles() << " " << r.totalComponents << " " << r.keptComponents
               << " " << r.thresholdVertices << "\n";
     return 0;

@@ -13,10 +13,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <dirent.h>
+#include <future>
 #include <iostream>
 #include <limits>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <sys/stat.h>
 #include <vector>
@@ -183,15 +185,33 @@ double now()
 struct SinkState
 {
     mlsb::Mesher mesher;
-    double seconds = 0.0;   // time spent welding blocks (serialised, on the worker threads)
+    std::mutex mutex;
+    double prepareSeconds = 0.0;   // per-block work, concurrently on the worker threads (summed)
+    double commitSeconds = 0.0;    // seam bookkeeping in the global mesh, serialised
 };
 
+// Called concurrently by the device workers (mlsb_group_set_concurrent_sink): the per-block part of
+// the mesher runs in parallel, only the merge into the global mesh takes the lock.
 void meshSink(std::uint64_t, const mlsb_mesh_sizes *sizes, const void *blob, void *user)
 {
     SinkState *st = static_cast<SinkState *>(user);
-    const double t = now();
-    st->mesher.add(*sizes, blob);
-    st->seconds += now() - t;
+    const double t0 = now();
+    std::unique_ptr<mlsb::Mesher::Block> prepared = mlsb::Mesher::prepare(*sizes, blob);
+    const double t1 = now();
+    mlsb::Mesher::Block *block;
+    double commit;
+    {
+        std::lock_guard<std::mutex> lock(st->mutex);
+        const double t2 = now();
+        block = &st->mesher.commit(std::move(prepared));
+        commit = now() - t2;
+        st->commitSeconds += commit;
+    }
+    const double t3 = now();
+    mlsb::Mesher::complete(*block);
+    const double local = (t1 - t0) + (now() - t3);
+    std::lock_guard<std::mutex> lock(st->mutex);
+    st->prepareSeconds += local;
 }
 
 }  // namespace
@@ -202,6 +222,49 @@ int main(int argc, char **argv)
     {
         const Options o = parse(argc, argv);
         const double t0 = now();
+
+        // ---- device workers: created in the background while the input is read and bucketed.
+        // The buffers are sized from the options alone (--mem-bucket-splats, --levels,
+        // --subsampling), as DeviceWorkerGroup's are (src/mlsgpu_core.cpp:722-735). ----
+        const std::int64_t maxCells = (std::int64_t(1) << (o.levels + o.subsampling - 1)) - 1;   // src/mlsgpu_core.cpp:722
+        const std::size_t maxBucketSplats = (std::size_t) (o.memBucketSplats / sizeof(mlsb_splat));
+        mlsb_worker_config cfg;
+        cfg.device = o.device;
+        cfg.maxLevels = (std::uint32_t) o.levels;
+        cfg.subsampling = (std::uint32_t) o.subsampling;
+        cfg.maxSplats = (std::uint32_t) std::max<std::size_t>(maxBucketSplats, 1);
+        cfg.maxCells = (std::uint32_t) maxCells;
+        cfg.meshBytes = std::max<std::uint64_t>(o.memMesh / (o.deviceThreads + 1), (std::uint64_t) maxCells * maxCells * 872);
+        cfg.shape = o.fitShape == "plane" ? MLSB_SHAPE_PLANE : MLSB_SHAPE_SPHERE;
+        cfg.boundaryLimit = (float) o.fitBoundaryLimit;
+        SinkState state;
+        struct Created
+        {
+            mlsb_group *group = nullptr;
+            int status = MLSB_OK;
+            std::string message;
+            double seconds = 0.0;
+        };
+        std::future<Created> creating = std::async(std::launch::async, [&cfg, &o, &state] {
+            Created c;
+            const double t = now();
+            c.status = mlsb_group_create(&cfg, (std::uint32_t) o.deviceThreads, 0, 1, meshSink, &state, &c.group);
+            if (c.status != MLSB_OK) c.message = mlsb_last_error_string();   // the error string is per thread
+            c.seconds = now() - t;
+            return c;
+        });
+        // whatever happens below, the group is joined and destroyed before state and cfg go away
+        struct GroupGuard
+        {
+            std::future<Created> &creating;
+            mlsb_group *group;
+            explicit GroupGuard(std::future<Created> &c) : creating(c), group(nullptr) {}
+            ~GroupGuard()
+            {
+                if (creating.valid()) group = creating.get().group;
+                mlsb_group_destroy(group);
+            }
+        } guard(creating);
 
         // ---- read and condition (FastPly::Reader) ----
         std::vector<std::string> files;
@@ -218,34 +281,21 @@ int main(int argc, char **argv)
         const double tRead = now();
 
         // ---- grid, bins (doComputeBlobs / doBucket) ----
-        const std::int64_t maxCells = (std::int64_t(1) << (o.levels + o.subsampling - 1)) - 1;   // src/mlsgpu_core.cpp:722
         const std::int64_t bucketSize = std::min<std::int64_t>(o.leafCells, maxCells);             // :600-603
         const mlsb::Grid grid = mlsb::boundingGrid(splats, (float) o.fitGrid, bucketSize);
         for (int a = 0; a < 3; a++)
             if (grid.numCells(a) + 1 > (1 << 20) - 1)   // src/mlsgpu_core.cpp:623-629
                 throw std::runtime_error("The bounding box is too big. Perhaps you have used the wrong units for --fit-grid.");
         mlsb::worldToGrid(splats, grid);
-        const std::size_t maxBucketSplats = (std::size_t) (o.memBucketSplats / sizeof(mlsb_splat));
         std::vector<mlsb::Bin> bins = mlsb::makeBins(splats, grid, maxCells, maxBucketSplats);
-        std::size_t largest = 1;
-        for (const mlsb::Bin &b : bins) largest = std::max(largest, b.ids.size());
         const double tBucket = now();
 
         // ---- device pipeline ----
-        mlsb_worker_config cfg;
-        cfg.device = o.device;
-        cfg.maxLevels = (std::uint32_t) o.levels;
-        cfg.subsampling = (std::uint32_t) o.subsampling;
-        cfg.maxSplats = (std::uint32_t) largest;
-        cfg.maxCells = (std::uint32_t) maxCells;
-        cfg.meshBytes = std::max<std::uint64_t>(o.memMesh / (o.deviceThreads + 1), (std::uint64_t) maxCells * maxCells * 872);
-        cfg.shape = o.fitShape == "plane" ? MLSB_SHAPE_PLANE : MLSB_SHAPE_SPHERE;
-        cfg.boundaryLimit = (float) o.fitBoundaryLimit;
-        SinkState state;
         const double tCreate0 = now();
-        mlsb_group *group = nullptr;
-        mlsb::check(mlsb_group_create(&cfg, (std::uint32_t) o.deviceThreads, 0, 1, meshSink, &state, &group));
-        struct GroupGuard { mlsb_group *g; ~GroupGuard() { mlsb_group_destroy(g); } } guard{group};
+        const Created created = creating.get();
+        mlsb_group *group = guard.group = created.group;
+        if (created.status != MLSB_OK) throw std::runtime_error(created.message);
+        mlsb::check(mlsb_group_set_concurrent_sink(group, 1));
         float origin[3];
         grid.getVertex0(origin);
         for (int i = 0; i < o.deviceThreads; i++)
@@ -254,17 +304,27 @@ int main(int argc, char **argv)
             mlsb::check(mlsb_group_worker(group, (std::uint32_t) i, &w));
             mlsb::check(mlsb_set_scale_bias(w, grid.spacing, origin));   // ScaleBiasFilter::setScaleBias(grid)
         }
-        const double tCreate = now() - tCreate0;
+        const double tCreateWait = now() - tCreate0;   // the part of the creation that was not hidden
         double tGather = 0.0;
-        std::vector<std::vector<mlsb_splat>> staged(bins.size());
+        // Gather buffers are recycled: when a submit returns, at most queueDepth bins are queued and
+        // deviceThreads are being staged, so the buffer used that many submits ago is free again
+        // (see mlsb_group_submit).  Reusing them keeps the gather out of the page-fault path.
+        std::size_t largest = 1;
+        for (const mlsb::Bin &bin : bins) largest = std::max(largest, bin.ids.size());
+        const std::size_t queueDepth = 2 * (std::size_t) o.deviceThreads;   // mlsb_group_create's default
+        std::vector<std::unique_ptr<mlsb_splat[]>> ring(queueDepth + (std::size_t) o.deviceThreads + 1);
         for (std::size_t b = 0; b < bins.size(); b++)
         {
             // BucketLoader::operator(): gather the bin's splats (src/bucket_loader.cpp:104-126)
             const double tg = now();
-            staged[b].resize(bins[b].ids.size());
-            for (std::size_t i = 0; i < bins[b].ids.size(); i++) staged[b][i] = splats[bins[b].ids[i]];
+            const std::vector<std::uint32_t> &ids = bins[b].ids;
+            std::unique_ptr<mlsb_splat[]> &slot = ring[b % ring.size()];
+            if (!slot) slot.reset(new mlsb_splat[largest]);
+            mlsb_splat *dst = slot.get();
+#pragma omp parallel for schedule(static)
+            for (std::int64_t i = 0; i < (std::int64_t) ids.size(); i++) dst[i] = splats[ids[(std::size_t) i]];
             tGather += now() - tg;
-            mlsb::check(mlsb_group_submit(group, staged[b].data(), (std::uint32_t) staged[b].size(), bins[b].size, bins[b].offset, b));
+            mlsb::check(mlsb_group_submit(group, dst, (std::uint32_t) ids.size(), bins[b].size, bins[b].offset, b));
         }
         mlsb::check(mlsb_group_wait(group));
         const double tDevice = now();
@@ -279,7 +339,7 @@ int main(int argc, char **argv)
                           o.fitSmooth, o.fitGrid, o.fitPrune, o.fitBoundaryLimit, o.fitShape.c_str(), o.levels, o.subsampling);
             writer.addComment(buf);
         }
-        writer.write(o.output, mesh.vertices, mesh.triangles);
+        writer.write(o.output, mesh.vertexChunks, mesh.triangleChunks);
         const double tEnd = now();
 
         if (!o.quiet || o.statistics)
@@ -287,10 +347,11 @@ int main(int argc, char **argv)
             std::cout << "files.splats: " << numSplats << "\n"
                       << "bins: " << bins.size() << "\n"
                       << "components.total: " << mesh.totalComponents << "\ncomponents.kept: " << mesh.keptComponents << "\n"
-                      << "output.vertices: " << mesh.vertices.size() << "\noutput.triangles: " << mesh.triangles.size() << "\n";
+                      << "output.vertices: " << mesh.numVertices << "\noutput.triangles: " << mesh.numTriangles << "\n";
             std::printf("read.time: %.3f\nbucket.time: %.3f\ndevice.time: %.3f\nmesher.time: %.3f\nrun.time: %.3f\n",
                         tRead - t0, tBucket - tRead, tDevice - tBucket, tEnd - tDevice, tEnd - t0);
-            std::printf("device.create.time: %.3f\ndevice.gather.time: %.3f\ndevice.weld.time: %.3f\n", tCreate, tGather, state.seconds);
+            std::printf("device.create.time: %.3f\ndevice.create.wait: %.3f\ndevice.gather.time: %.3f\n", created.seconds, tCreateWait, tGather);
+            std::printf("mesher.prepare.time: %.3f\nmesher.commit.time: %.3f\n", state.prepareSeconds, state.commitSeconds);
             std::printf("splats/s end-to-end: %.3g\n", numSplats / (tEnd - t0));
         }
         return 0;

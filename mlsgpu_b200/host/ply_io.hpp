@@ -14,11 +14,14 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <fcntl.h>
 #include <limits>
 #include <map>
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/mlsb200.h"
@@ -175,21 +178,59 @@ class PlyWriter
 public:
     void addComment(const std::string &c) { comments.push_back(c); }
 
-    void write(const std::string &path, const std::vector<std::array<float, 3>> &vertices,
-               const std::vector<std::array<std::uint32_t, 3>> &triangles) const
+    typedef std::array<float, 3> vertex_type;
+    typedef std::array<std::uint32_t, 3> triangle_type;
+
+    void write(const std::string &path, const std::vector<vertex_type> &vertices, const std::vector<triangle_type> &triangles) const
     {
+        write(path, std::vector<std::vector<vertex_type>>(1, vertices), std::vector<std::vector<triangle_type>>(1, triangles));
+    }
+
+    /// Chunked mesh (Mesher::Result): the file is sized up front and mapped, and the chunks are
+    /// packed into it in parallel; file systems that cannot map fall back to buffered writes.
+    void write(const std::string &path, const std::vector<std::vector<vertex_type>> &vertexChunks,
+               const std::vector<std::vector<triangle_type>> &triangleChunks) const
+    {
+        std::vector<std::size_t> vertexStart(vertexChunks.size() + 1, 0), triangleStart(triangleChunks.size() + 1, 0);
+        for (std::size_t i = 0; i < vertexChunks.size(); i++) vertexStart[i + 1] = vertexStart[i] + vertexChunks[i].size();
+        for (std::size_t i = 0; i < triangleChunks.size(); i++) triangleStart[i + 1] = triangleStart[i] + triangleChunks[i].size();
+        const std::size_t numVertices = vertexStart.back(), numTriangles = triangleStart.back();
+        const std::string header = makeHeader(numVertices, numTriangles);
+        const std::size_t vertexOffset = header.size(), faceOffset = vertexOffset + 12 * numVertices;
+        const std::size_t total = faceOffset + faceBytes * numTriangles;
+
+        const int fd = ::open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
+        if (fd < 0) throw std::runtime_error("cannot create " + path);
+        void *map = MAP_FAILED;
+        if (::ftruncate(fd, (off_t) total) == 0) map = ::mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (map != MAP_FAILED)
+        {
+            unsigned char *out = static_cast<unsigned char *>(map);
+            std::memcpy(out, header.data(), header.size());
+#pragma omp parallel for schedule(dynamic, 1)
+            for (std::int64_t i = 0; i < (std::int64_t) vertexChunks.size(); i++)
+                if (!vertexChunks[i].empty())
+                    std::memcpy(out + vertexOffset + 12 * vertexStart[i], vertexChunks[i].data(), 12 * vertexChunks[i].size());
+#pragma omp parallel for schedule(dynamic, 1)
+            for (std::int64_t i = 0; i < (std::int64_t) triangleChunks.size(); i++)
+                packFaces(triangleChunks[i].data(), triangleChunks[i].size(), out + faceOffset + faceBytes * triangleStart[i]);
+            const bool bad = ::munmap(map, total) != 0;
+            if (::close(fd) != 0 || bad) throw std::runtime_error("error writing " + path);
+            return;
+        }
+        ::close(fd);
         std::FILE *f = std::fopen(path.c_str(), "wb");
         if (!f) throw std::runtime_error("cannot create " + path);
-        const std::string header = makeHeader(vertices.size(), triangles.size());
         std::fwrite(header.data(), 1, header.size(), f);
-        if (!vertices.empty()) std::fwrite(vertices.data(), sizeof(vertices[0]), vertices.size(), f);
-        std::vector<unsigned char> faces(triangles.size() * 13);
-        for (std::size_t i = 0; i < triangles.size(); i++)
+        for (const std::vector<vertex_type> &c : vertexChunks)
+            if (!c.empty()) std::fwrite(c.data(), sizeof(c[0]), c.size(), f);
+        std::vector<unsigned char> faces;
+        for (const std::vector<triangle_type> &c : triangleChunks)
         {
-            faces[13 * i] = 3;
-            std::memcpy(&faces[13 * i + 1], triangles[i].data(), 12);
+            faces.resize(c.size() * faceBytes);
+            packFaces(c.data(), c.size(), faces.data());
+            if (!faces.empty()) std::fwrite(faces.data(), 1, faces.size(), f);
         }
-        if (!faces.empty()) std::fwrite(faces.data(), 1, faces.size(), f);
         if (std::fclose(f) != 0) throw std::runtime_error("error writing " + path);
     }
 
@@ -214,6 +255,17 @@ public:
     }
 
 private:
+    static const std::size_t faceBytes = 13;   // uint8 count + 3 x uint32
+
+    static void packFaces(const triangle_type *triangles, std::size_t count, unsigned char *out)
+    {
+        for (std::size_t i = 0; i < count; i++)
+        {
+            out[faceBytes * i] = 3;
+            std::memcpy(out + faceBytes * i + 1, triangles[i].data(), 12);
+        }
+    }
+
     std::vector<std::string> comments;
 };
 

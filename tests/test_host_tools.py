@@ -197,16 +197,21 @@ def check_isomorphic(expected_vertices, expected_indices, verts, tris):
     assert canon(ev, expected_indices) == canon(av, tris)
 
 
-def run_mesher(tmp_path, blocks, prune):
+# threads > 1: the blocks go through Mesher::prepare/commit/complete concurrently, as the CLI's sink does
+THREADS = pytest.mark.parametrize("threads", [1, 3])
+
+
+def run_mesher(tmp_path, blocks, prune, threads=1):
     exe = build("mesher_test")
     write_blocks(tmp_path / "blocks.bin", blocks)
     out = tmp_path / "out.ply"
-    subprocess.run([exe, str(tmp_path / "blocks.bin"), repr(prune), str(out)], check=True, capture_output=True)
+    subprocess.run([exe, str(tmp_path / "blocks.bin"), repr(prune), str(out), str(threads)], check=True, capture_output=True)
     verts, tris, _ = plyfile.read_mesh_ply(out)
     return verts, tris
 
 
-def test_mesher_reference_weld_fixture(tmp_path):
+@THREADS
+def test_mesher_reference_weld_fixture(tmp_path, threads):
     b0 = blk([(0, 0, 1), (0, 0, 2), (0, 0, 3), (0, 0, 4), (0, 0, 5)], [], [], [0, 1, 3, 1, 2, 3, 3, 4, 0])
     b1 = blk([], [(1, 0, 1), (1, 0, 2), (1, 0, 3), (1, 0, 4)], [0, 0x8000000000000000, 1, 0x8000000000000001],
              [0, 1, 3, 1, 2, 3, 2, 0, 3])
@@ -218,11 +223,12 @@ def test_mesher_reference_weld_fixture(tmp_path):
                          (0, 1, 0), (0, 2, 0), (0, 3, 0), (2, 0, 1), (2, 0, 2), (3, 3, 3), (4, 5, 6)]
     expected_indices = [0, 1, 3, 1, 2, 3, 3, 4, 0, 5, 6, 8, 6, 7, 8, 7, 5, 8, 9, 10, 12, 10, 13, 12, 11, 12, 13, 9, 11, 13,
                         9, 12, 11, 14, 6, 15, 15, 6, 13, 13, 6, 7]
-    verts, tris = run_mesher(tmp_path, [b0, b1, b2, b3], 0.0)
+    verts, tris = run_mesher(tmp_path, [b0, b1, b2, b3], 0.0, threads)
     check_isomorphic(expected_vertices, expected_indices, verts, tris)
 
 
-def test_mesher_reference_prune_fixture(tmp_path):
+@THREADS
+def test_mesher_reference_prune_fixture(tmp_path, threads):
     b0 = blk([(0, 0, 0), (1, 0, 0), (2, 0, 0), (3, 0, 0), (4, 0, 0)], [(0, 3, 0), (1, 3, 0), (2, 3, 0)], [0x30, 0x31, 0x32],
              [0, 4, 1, 1, 4, 2, 2, 4, 3, 5, 7, 6])
     b1 = blk([(0, 1, 0), (1, 1, 0), (2, 1, 0), (3, 1, 0), (4, 1, 0), (5, 1, 0), (0, 2, 0), (3, 2, 0)],
@@ -235,13 +241,14 @@ def test_mesher_reference_prune_fixture(tmp_path):
                          (3, 3, 0), (4, 3, 0), (5, 3, 0)]
     expected_indices = [0, 5, 1, 1, 5, 2, 2, 5, 3, 3, 5, 4, 6, 8, 7, 7, 8, 9, 9, 8, 10, 9, 10, 11, 6, 10, 8]
     # 22 vertices in total, threshold 6 (setPruneThreshold(6.5 / 22.0))
-    verts, tris = run_mesher(tmp_path, [b0, b1, b2, b3], 6.5 / 22.0)
+    verts, tris = run_mesher(tmp_path, [b0, b1, b2, b3], 6.5 / 22.0, threads)
     check_isomorphic(expected_vertices, expected_indices, verts, tris)
 
 
-def test_mesher_reference_empty_fixture(tmp_path):
+@THREADS
+def test_mesher_reference_empty_fixture(tmp_path, threads):
     # TestMesherBase::testEmpty: no blocks (or empty blocks) give an empty, well-formed PLY
-    verts, tris = run_mesher(tmp_path, [], 0.0)
+    verts, tris = run_mesher(tmp_path, [], 0.0, threads)
     assert len(verts) == 0 and len(tris) == 0
-    verts, tris = run_mesher(tmp_path, [blk([], [], [], [])], 0.02)
+    verts, tris = run_mesher(tmp_path, [blk([], [], [], [])], 0.02, threads)
     assert len(verts) == 0 and len(tris) == 0

@@ -353,6 +353,9 @@ int main(int argc, char **argv)
             std::printf("device.create.time: %.3f\ndevice.create.wait: %.3f\ndevice.gather.time: %.3f\n", created.seconds, tCreateWait, tGather);
             std::printf("mesher.prepare.time: %.3f\nmesher.commit.time: %.3f\n", state.prepareSeconds, state.commitSeconds);
             std::printf("splats/s end-to-end: %.3g\n", numSplats / (tEnd - t0));
+            // the CUDA driver's start-up (no persistence daemon: the GPU is initialised per process)
+            // is a fixed cost; this is the rate a long run converges to
+            std::printf("splats/s excluding device start-up: %.3g\n", numSplats / (tEnd - t0 - tCreateWait));
         }
         return 0;
     }

@@ -107,6 +107,9 @@ def test_cli_end_to_end_sphere(tmp_path):
     assert int(stats["components.total"]) >= 2 and int(stats["components.kept"]) == 1
     verts, tris, header = plyfile.read_mesh_ply(out)
     assert is_manifold(len(verts), tris) == ""
+    # the acceptance tool of the reference (extras/plymanifold.cpp): closed, one component
+    check = subprocess.run([build("plymanifold"), str(out)], capture_output=True, text=True)
+    assert check.returncode == 0 and "Components: 1\nBoundaries: 0" in check.stdout, check.stdout
     assert np.abs(np.linalg.norm(verts, axis=1) - 1.0).max() < 0.03      # only the big sphere is left
     # the same input through the Python binding, bin by bin, welded by key
     g, bins, lo, spacing = host.prepare(both, 0.025, max_cells=31)
@@ -162,6 +165,9 @@ def test_cli_plane_fit_boundary_and_prune(tmp_path):
     assert int(stats["components.total"]) >= 1 and int(stats["components.kept"]) == 1
     verts, tris, _ = plyfile.read_mesh_ply(out)
     assert len(verts) > 5000 and is_manifold(len(verts), tris) == ""
+    check = subprocess.run([build("plymanifold"), str(out)], capture_output=True, text=True)
+    assert check.returncode == 0 and "Components: 1\n" in check.stdout, check.stdout
+    assert int(check.stdout.strip().rsplit(": ", 1)[1]) >= 2      # boundary loops: outer rim and the hole
     assert verts[:, 0].max() < 2.2                        # islands pruned
     assert np.abs(verts[:, 2] - 0.02 * np.sin(3 * verts[:, 0]) * np.cos(2 * verts[:, 1])).max() < 0.01
     # open surface: boundary edges exist (outer rim and the hole), and no vertex sits deep inside the hole

@@ -17,7 +17,7 @@ def main():
     ap.add_argument("--splats", type=int, default=10_000_000)
     ap.add_argument("--fit-grid", type=float, default=0.002)
     ap.add_argument("--threads", type=int, default=4)
-    ap.add_argument("--check", action="store_true", help="run the manifold check on the output (slow for big meshes)")
+    ap.add_argument("--check", action="store_true", help="run plymanifold on the output")
     args = ap.parse_args()
     from mlsgpu_b200 import host, plyfile
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -38,9 +38,9 @@ def main():
         verts, tris, header = plyfile.read_mesh_ply(out)
         print("output: %d vertices, %d triangles, %.1f MB" % (len(verts), len(tris), os.path.getsize(out) / 1e6))
         if args.check:
-            sys.path.insert(0, os.path.join(root, "tests"))
-            from fixtures import is_manifold
-            print("manifold:", is_manifold(len(verts), tris) or "yes")
+            t0 = time.time()
+            r = subprocess.run([os.path.join(root, "mlsgpu_b200", "host", "plymanifold"), out], capture_output=True, text=True)
+            print("plymanifold (%.1f s): %s" % (time.time() - t0, r.stdout.strip().replace("\n", "; ")))
     return 0
 
 

@@ -36,9 +36,8 @@ OCTREE_STATS = ["kernel.octree.writeEntries.time", "kernel.octree.sort.time", "k
                 "kernel.octree.countCommands.time", "kernel.octree.scan.time", "kernel.octree.writeSplatIds.time",
                 "kernel.octree.writeStart.time"]
 MARCHING_STATS = ["kernel.marching.zero.time", "kernel.marching.genOccupied.time", "kernel.marching.scanElements.time",
-                  "kernel.marching.generateElements.time",
-                  "kernel.marching.sortVertices.time", "kernel.marching.compactVertices.time",
-                  "kernel.marching.reindex.time", "kernel.marching.readback.time"]
+                  "kernel.marching.countUniqueVertices.time", "kernel.marching.compactVertices.time",
+                  "kernel.marching.generateElements.time", "kernel.marching.readback.time"]
 
 
 def log(*a):
@@ -263,7 +262,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--splats", type=int, default=10_000_000)
-    ap.add_argument("--threads", type=int, default=4, help="workers per GPU (--device-threads)")
+    ap.add_argument("--threads", type=int, default=0,
+                    help="workers per GPU (--device-threads); 0 = 8, fewer when the ranks share few host cores (never below 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -274,6 +274,9 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.threads <= 0:
+        # measured on one B200: 3 workers 250, 4: 266, 6: 273, 8: 281 Msplats/s
+        args.threads = max(4, min(8, (os.cpu_count() or 8) // world - 1))
 
     import torch
     import torch.distributed as dist

@@ -149,7 +149,8 @@ int mlsb_worker_resource_usage(const mlsb_worker_config *c, uint64_t *deviceByte
     total += (uint64_t) c->maxSplats * sizeof(mlsb_splat);
     total += maxStart * 4 * 6 + (entries + 2 * ranges) * 4 + entries * 4 * 4;   // octree
     total += dim * dim * dim * 4;                                               // field
-    total += vs * (16 + 4 * 4 + 4 + 12 + 8) + is * 4;                           // marching
+    uint64_t lattice = (2ull * c->maxCells + 1) * (2ull * c->maxCells + 1) * (2 * divUp<uint64_t>(c->maxCells, 32) + 1);
+    total += vs * (12 + 8) + is * 4 + lattice * 12;                             // marching
     *deviceBytes = total;
     return MLSB_OK;
 }
@@ -198,12 +199,12 @@ int mlsb_worker_create(const mlsb_worker_config *config, mlsb_worker **out)
     if ((st = mlsAlloc(w)) != MLSB_OK) return fail(st);
     if ((st = marchingAlloc(w)) != MLSB_OK) return fail(st);
     // shared scan / sort scratch
-    size_t maxSort = std::max<size_t>(8ull * config->maxSplats, w->vertexSpace);
+    size_t maxSort = 8ull * config->maxSplats;
     if ((st = sortScratchAlloc(w->sort, maxSort, 4)) != MLSB_OK) return fail(st);
     uint64_t cells = (uint64_t) config->maxCells * config->maxCells * config->maxCells;
     uint64_t words = std::max<uint64_t>({divUp<uint64_t>(cells, 256) + 2, divUp<uint64_t>(w->numStartMax, 2048) + 2,
                                          divUp<uint64_t>(config->maxSplats, 256) + 2,
-                                         divUp<uint64_t>(w->vertexSpace, 1024) + 2});
+                                         divUp<uint64_t>(w->latticeWords, 2048) + 2});
     w->scanStatusWords = (uint32_t) words;
     if (cudaMalloc(&w->scanStatus, words * sizeof(uint64_t)) != cudaSuccess
         || cudaMalloc(&w->scanTicket, 4 * sizeof(uint32_t)) != cudaSuccess)

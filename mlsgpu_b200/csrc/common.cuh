@@ -118,10 +118,9 @@ struct mlsb_worker
     float *field = nullptr;       // [z][y][x], pitch fieldDim
     uint8_t *blockActive = nullptr;   // [bz][by][bx] per 8x8x8 block of the field: written by the MLS kernel
     uint64_t vertexSpace = 0, indexSpace = 0;
-    float4 *unwelded = nullptr;
-    uint32_t *vertKeys[2] = {nullptr, nullptr};
-    uint32_t *vertIdx[2] = {nullptr, nullptr};
-    uint32_t *indexRemap = nullptr;
+    uint32_t *latMask = nullptr;      // lattice of edge midpoints: 1 bit per possible vertex of a block
+    uint2 *latPrefix = nullptr;       // per lattice word: welded vertices in front of it (unflagged, flagged)
+    size_t latticeWords = 0;
     uint32_t *indices = nullptr;
     float *welded = nullptr;          // packed float3
     uint64_t *weldedKeys = nullptr;

@@ -1,20 +1,28 @@
 // Marching tetrahedra + vertex welding + scale/bias: Marching::generate / addSlices / shipOut
 // (src/marching.cpp:500-824), kernels/marching.cl and kernels/scale_bias.cl, re-designed around
-// a field that is resident for the whole bin (no swathes, no copySlice):
+// a field that is resident for the whole bin (no swathes, no copySlice) and around the fact that
+// a vertex key IS a position on the half-cell lattice of edge midpoints (computeKey,
+// kernels/marching.cl:148-154: 2 * cell + the offsets of the edge's two corners).  The reference
+// emits every vertex once per cell that uses it, sorts (key, vertex) pairs, drops duplicates and
+// re-indexes; here the welded vertex set is a bitmask over that lattice and a vertex's welded index
+// is a prefix popcount, so there is no per-cell vertex, no sort and no re-index pass:
 //
-//   generateCells   genOccupied + scanElements + generateElements in ONE pass: a tile of cells
-//                   is classified, its (vertex, index) counts are block-scanned, the tile's base
-//                   comes from a decoupled look-back, and occupied cells emit their vertices,
-//                   compact 32-bit keys and local indices straight away (kernels/marching.cl:84-258)
-//   radix sort      (compact key, unwelded index) pairs; the 64-bit key of the reference only has
-//                   3 x <=10 live coordinate bits + the external flag, so it packs into <= 31 bits
-//                   and the 16-byte vertex payload is not moved by the sort at all
-//   weldVertices    countUniqueVertices + scan + compactVertices + scaleBiasVertices in one pass
-//                   (kernels/marching.cl:271-326, kernels/scale_bias.cl:32-40)
-//   reindex         kernels/marching.cl:334-340
+//   generateCells<classify>  genOccupied (:84-120) bit-parallel on ballot masks; every warp row
+//                   that holds surface also ORs the lattice bits of its valid cells' crossed edges
+//                   (19 edges = 9 lattice rows x {even, odd} columns, a handful of logic ops each)
+//   scanTiles       per-tile index bases (the role of clogs::Scan at src/marching.cpp:721)
+//   scanLattice     countUniqueVertices + scan (:271-279): exclusive popcount prefix of every
+//                   lattice word in (z, y, x) order = key order, split into unflagged / flagged
+//                   (the external flag is the top key bit, so flagged vertices sort last)
+//   emitVertices    generateElements' interpolation (:130-138, :184-258) + compactVertices
+//                   (:295-326) + scaleBiasVertices (kernels/scale_bias.cl:32-40): one thread per
+//                   non-empty lattice word writes its vertices at their final positions
+//   generateCells<emit>  one thread per index: cell -> edge -> lattice point -> rank (reindex, :334-340)
 //
-// Cells are visited in x-fastest linear order (the reference's atomic order is arbitrary), so the
-// output is deterministic: vertices sorted by key (internal first), triangles in cell order.
+// tests/lattice_model.py states the same identity in numpy and tests/test_lattice_model.py checks
+// it against the oracle bit for bit.  Cells are visited in x-fastest linear order (the reference's
+// atomic order is arbitrary), so the output is deterministic: vertices sorted by key (internal
+// first), triangles in cell order.
 #include "common.cuh"
 #include "scan.cuh"
 #include <algorithm>
@@ -28,19 +36,18 @@ namespace
 
 constexpr int kNumEdges = 19;
 constexpr int kGenThreads = 256;
-constexpr int kWeldThreads = 256;
-constexpr int kWeldItems = 4;
 
 // counters in mlsb_worker::marchCounters
 enum
 {
-    CTR_VERTS = 0,      // unwelded vertices
+    CTR_VERTS = 0,      // per-cell (unwelded) vertices: what the reference sizes its buffers by
     CTR_INDICES = 1,
     CTR_OVERFLOW = 2,
     CTR_WELDED = 3,
     CTR_FIRST_EXTERNAL = 4,
     CTR_CELLS = 5,
     CTR_TILES = 6,      // non-empty tiles
+    CTR_UNFLAGGED = 7,  // welded vertices without the external flag (internal + the top z plane)
     CTR_GEN_TICKET = 8,
     CTR_WELD_TICKET = 9,
     CTR_COUNT = 16
@@ -165,12 +172,14 @@ struct GenParams
     uint32_t zFirst, zLast;        // cells between slices zFirst..zLast
     uint32_t numCells;
     uint3 gridOffset;              // keyOffset: local -> global grid coordinates
-    uint3 top;                     // kernels/marching.cl:151
-    uint32_t keyBits;              // bits per axis of the compact key
     uint32_t vertexSpace, indexSpace;
-    float4 *unwelded;
-    uint32_t *keys, *vidx, *indices;
+    uint32_t *indices;
     uint32_t *counters;
+    // lattice of edge midpoints of this block: [2 * (zLast - zFirst) + 1][latRows][latStride] words,
+    // bit x2 of row (y2, z2) = the edge with midpoint (x2, y2, z2) / 2 carries a vertex
+    uint32_t *latMask;
+    const uint2 *latPrefix;        // per non-empty word: vertices before it (unflagged, flagged)
+    uint32_t latStride, latRows;
     uint64_t *tileTotals;          // per tile: classify writes (v | i << 21 | cells << 42), scanTiles turns it
                                    // into the tile's exclusive base (v | i << 31)
     uint32_t *tileList;            // non-empty tiles in order; count in counters[CTR_TILES]
@@ -217,16 +226,54 @@ __device__ __forceinline__ RowMasks loadRowMasks(const float *__restrict__ row, 
     return m;
 }
 
-// EMIT = false: classify the tile's cells and write its (vertices, indices, cells) totals.
+// 16 bits -> the even bit positions of 32
+__device__ __forceinline__ uint32_t spread16(uint32_t v)
+{
+    v &= 0xFFFFu;
+    v = (v | (v << 8)) & 0x00FF00FFu;
+    v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+// Which bits of lattice word (wcol, y2, z2) carry the external flag of computeKey
+// (kernels/marching.cl:148-154): x2 == 0, y2 == 0, z2 == top.z (the block's first plane),
+// x2 == top.x, y2 == top.y.  The block's LAST plane is external too (key >= minExternalKey,
+// :304) but unflagged: it sorts behind the internal vertices on its own.
+__device__ __forceinline__ uint32_t latticeFlagMask(uint32_t wcol, uint32_t y2, uint32_t z2, uint32_t topX, uint32_t topY)
+{
+    if (z2 == 0 || y2 == 0 || y2 == topY) return 0xFFFFFFFFu;
+    uint32_t m = wcol == 0 ? 1u : 0u;
+    if (wcol == (topX >> 5)) m |= 1u << (topX & 31);
+    return m;
+}
+
+// Welded index of the vertex at lattice point (x2, y2, z2) of the block.
+__device__ __forceinline__ uint32_t latticeRank(const uint32_t *__restrict__ mask, const uint2 *__restrict__ prefix,
+                                                uint32_t stride, uint32_t rows, uint32_t x2, uint32_t y2, uint32_t z2,
+                                                uint32_t topX, uint32_t topY, uint32_t numUnflagged)
+{
+    const uint32_t wcol = x2 >> 5, bit = x2 & 31;
+    const size_t word = ((size_t) z2 * rows + y2) * stride + wcol;
+    const uint32_t m = __ldg(mask + word);
+    const uint2 pre = __ldg(prefix + word);
+    const uint32_t fm = latticeFlagMask(wcol, y2, z2, topX, topY);
+    const uint32_t below = (1u << bit) - 1;
+    return (fm >> bit) & 1 ? numUnflagged + pre.y + __popc(m & fm & below) : pre.x + __popc(m & ~fm & below);
+}
+
+// EMIT = false: classify the tile's cells and write its (vertices, indices, cells) totals; warp
+//               rows that hold surface also OR their crossed edges into the lattice mask.
 // EMIT = true:  re-classify a NON-EMPTY tile (blockIdx.x indexes tileList), list its occupied cells
-//               in shared memory and emit one vertex / one index per thread at the base that
-//               scanTilesKernel computed, so that all stores are contiguous.
+//               in shared memory and emit one index per thread at the base that scanTilesKernel
+//               computed, so that all stores are contiguous.
 // Splitting the pass keeps every CTA free of inter-CTA waits; only the few percent of tiles that
 // hold surface are classified twice.  CHUNKS = ceil(cellsX / 256).
 template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) generateCellsKernel(GenParams P)
 {
     constexpr int kVRows = kGenRows * CHUNKS;
-    extern __shared__ uint32_t sList[];   // EMIT: [3][kVRows * 256]: cell, vertex base, index base
+    extern __shared__ uint32_t sList[];   // EMIT: [2][kVRows * 256]: cell, index base
     __shared__ uint64_t sWarpTot[kVRows * kGenWarps];
     __shared__ uint64_t sScan[33];
 
@@ -303,7 +350,46 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
                                 (uint64_t) (tot & 0x3FF) | ((uint64_t) ((tot >> 10) & 0xFFF) << 21) | ((uint64_t) (tot >> 22) << 42);
                     }
                     else
+                    {
                         mine += (uint64_t) (packed & 0x3FF) | ((uint64_t) ((packed >> 10) & 0xFFF) << 21) | ((uint64_t) (packed >> 22) << 42);
+                        // ---- lattice bits of this row of cells.  With the sign masks a = corner
+                        // (x, y, z), b = (x, y+1, z), c = (x, y, z+1), d = (x, y+1, z+1) and their
+                        // x+1 twins, the 19 edges of a cell fall on 9 lattice rows (oy, oz) in
+                        // {0,1,2}^2 relative to (2y, 2z): odd columns 2x+1 hold the 9 edges with an
+                        // x component, even columns 2x / 2x+2 the 10 without.  Lane oz*3+oy does row
+                        // (oy, oz); contributions from neighbouring cells, rows, slabs meet by OR. ----
+                        const uint32_t a = p0.s0, a1 = p0.s1, b = c0.s0, b1 = c0.s1, cc = p1.s0, cc1 = p1.s1, d = c1.s0, d1 = c1.s1;
+                        const uint32_t valid = pv & cv & inRange;
+                        uint32_t odd = 0, even = 0, evenNext = 0;
+                        switch (lane)
+                        {
+                        case 0: odd = a ^ a1; break;
+                        case 1: odd = a ^ b1; even = a ^ b; evenNext = a1 ^ b1; break;
+                        case 2: odd = b ^ b1; break;
+                        case 3: odd = a ^ cc1; even = a ^ cc; evenNext = a1 ^ cc1; break;
+                        case 4: odd = a ^ d1; even = a ^ d; evenNext = a1 ^ d1; break;
+                        case 5: odd = b ^ d1; even = b ^ d; evenNext = b1 ^ d1; break;
+                        case 6: odd = cc ^ cc1; break;
+                        case 7: odd = cc ^ d1; even = cc ^ d; evenNext = cc1 ^ d1; break;
+                        case 8: odd = d ^ d1; break;
+                        default: break;
+                        }
+                        if (lane < 9)
+                        {
+                            odd &= valid;
+                            // corner x belongs to cells x-1 and x; the one beyond this warp's 32 goes
+                            // to bit 0 of the next word pair
+                            even &= valid | (valid << 1);
+                            const uint32_t carry = (evenNext & valid) >> 31;
+                            const uint32_t y2 = 2 * (y0 + r) + lane % 3, z2 = 2 * (z - P.zFirst) + lane / 3;
+                            uint32_t *const row = P.latMask + ((size_t) z2 * P.latRows + y2) * P.latStride + (x0 >> 4);
+                            const uint32_t w0 = spread16(even) | (spread16(odd) << 1);
+                            const uint32_t w1 = spread16(even >> 16) | (spread16(odd >> 16) << 1);
+                            if (w0) atomicOr(row, w0);
+                            if (w1) atomicOr(row + 1, w1);
+                            if (carry) atomicOr(row + 2, 1u);
+                        }
+                    }
                 }
                 p0 = c0;
                 p1 = c1;
@@ -343,8 +429,8 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
     }
     __syncthreads();
     const uint32_t numCells = (uint32_t) (total >> 42);
-    const uint32_t numVerts = (uint32_t) (total & 0x1FFFFF), numIdx = (uint32_t) ((total >> 21) & 0x1FFFFF);
-    uint32_t *const sCell = sList, *const sVloc = sList + kVRows * kGenThreads, *const sIloc = sList + 2 * kVRows * kGenThreads;
+    const uint32_t numIdx = (uint32_t) ((total >> 21) & 0x1FFFFF);
+    uint32_t *const sCell = sList, *const sIloc = sList + kVRows * kGenThreads;
 #pragma unroll
     for (int v = 0; v < kVRows; v++)
     {
@@ -354,66 +440,36 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
             const uint32_t idx = (uint32_t) (b >> 42) + (excl[v] >> 22);
             const uint32_t x = (v % CHUNKS) * kGenThreads + tid, r = v / CHUNKS;
             sCell[idx] = x | (r << 16) | (codes[v] << 24);
-            sVloc[idx] = (uint32_t) (b & 0x1FFFFF) + (excl[v] & 0x3FF);
             sIloc[idx] = (uint32_t) ((b >> 21) & 0x1FFFFF) + ((excl[v] >> 10) & 0xFFF);
         }
     }
     __syncthreads();
 
-    const uint64_t tileBase = P.tileTotals[tile];
-    const uint32_t vBase = (uint32_t) (tileBase & 0x7FFFFFFFu), iBase = (uint32_t) (tileBase >> 31);
-    if (vBase + numVerts > P.vertexSpace || iBase + numIdx > P.indexSpace)
-    {
-        if (tid == 0) P.counters[CTR_OVERFLOW] = 1;
-        return;
-    }
+    const uint32_t iBase = (uint32_t) (P.tileTotals[tile] >> 31);
+    if (P.counters[CTR_OVERFLOW]) return;   // the block did not fit: the host splits it and starts over
 
-    // ---- generateElements (kernels/marching.cl:184-258): one thread per vertex ----
-    for (uint32_t j = tid; j < numVerts; j += kGenThreads)
-    {
-        // last cell whose first vertex is <= j
-        uint32_t lo = 0, hi = numCells;
-        while (hi - lo > 1)
-        {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (sVloc[mid] <= j) lo = mid; else hi = mid;
-        }
-        const uint32_t cell = sCell[lo], k = j - sVloc[lo];
-        const uint32_t x = cell & 0xFFFF, r = (cell >> 16) & 0xFF, code = cell >> 24;
-        const uint32_t y = y0 + r;
-        const uint32_t e = T.data[T.start[code][0] + k];
-        const uint32_t a = T.edge[e][0], b = T.edge[e][1];
-        const uint32_t oax = a & 1, oay = (a >> 1) & 1, oaz = a >> 2;
-        const uint32_t obx = b & 1, oby = (b >> 1) & 1, obz = b >> 2;
-        const uint32_t dx = obx - oax, dy = oby - oay, dz = obz - oaz;
-        const float isoA = __ldg((oaz ? slice1 : slice0) + (size_t) (r + oay) * P.pitch + x + oax);
-        const float isoB = __ldg((obz ? slice1 : slice0) + (size_t) (r + oby) * P.pitch + x + obx);
-        // interp(), kernels/marching.cl:130-138: no contraction, explicit fma
-        const float inv = __fdiv_rn(1.0f, __fsub_rn(isoA, isoB));
-        const float t = __fmul_rn(isoA, inv);
-        float4 pos;
-        pos.x = __fmaf_rn(t, (float) dx, (float) (x + P.gridOffset.x + oax));
-        pos.y = __fmaf_rn(t, (float) dy, (float) (y + P.gridOffset.y + oay));
-        pos.z = __fmaf_rn(t, (float) dz, (float) (z + P.gridOffset.z + oaz));
-        pos.w = 0.0f;
-        // computeKey(), :148-154, on the compact layout (flag | z | y | x)
-        const uint32_t kx = 2 * x + 2 * oax + dx, ky = 2 * y + 2 * oay + dy, kz = 2 * z + 2 * oaz + dz;
-        uint32_t key = (kz << (2 * P.keyBits)) | (ky << P.keyBits) | kx;
-        if (kx == 0 || ky == 0 || kx == P.top.x || ky == P.top.y || kz == P.top.z) key |= 1u << (3 * P.keyBits);
-        P.unwelded[vBase + j] = pos;
-        P.keys[vBase + j] = key;
-    }
-    // ---- ... and one thread per index ----
+    // ---- generateElements' index half + reindex (kernels/marching.cl:240-258, :334-340): one
+    // thread per index; the vertex it names is a lattice point, its welded index a rank ----
+    const uint32_t numUnflagged = P.counters[CTR_UNFLAGGED];
+    const uint32_t topX = 2 * P.cellsX, topY = 2 * P.cellsY;
     for (uint32_t j = tid; j < numIdx; j += kGenThreads)
     {
+        // last cell whose first index is <= j
         uint32_t lo = 0, hi = numCells;
         while (hi - lo > 1)
         {
             const uint32_t mid = (lo + hi) >> 1;
             if (sIloc[mid] <= j) lo = mid; else hi = mid;
         }
-        const uint32_t code = sCell[lo] >> 24, k = j - sIloc[lo];
-        P.indices[iBase + j] = vBase + sVloc[lo] + T.data[T.start[code][1] + k];
+        const uint32_t cell = sCell[lo], k = j - sIloc[lo];
+        const uint32_t x = cell & 0xFFFF, r = (cell >> 16) & 0xFF, code = cell >> 24;
+        const uint32_t e = T.data[T.start[code][0] + T.data[T.start[code][1] + k]];
+        const uint32_t a = T.edge[e][0], b = T.edge[e][1];
+        // computeKey(), :148-154: twice the cell plus the offsets of the edge's two corners
+        const uint32_t x2 = 2 * x + (a & 1) + (b & 1);
+        const uint32_t y2 = 2 * (y0 + r) + ((a >> 1) & 1) + ((b >> 1) & 1);
+        const uint32_t z2 = 2 * (z - P.zFirst) + (a >> 2) + (b >> 2);
+        P.indices[iBase + j] = latticeRank(P.latMask, P.latPrefix, P.latStride, P.latRows, x2, y2, z2, topX, topY, numUnflagged);
     }
 }
 
@@ -456,100 +512,131 @@ __global__ void __launch_bounds__(1024) scanTilesKernel(uint64_t *tileTotals, ui
     }
 }
 
-struct WeldParams
+struct LatticeParams
 {
-    const uint32_t *keys, *vidx;
-    const float4 *unwelded;
-    float *welded;
-    uint64_t *weldedKeys;
-    uint32_t *indexRemap;
+    const uint32_t *mask;
+    uint2 *prefix;
+    uint32_t stride, rows, planes;   // words per row, rows (y2) per plane, planes (z2)
+    uint32_t totalWords;
+    uint32_t topX, topY;             // 2 * cellsX, 2 * cellsY
     uint32_t *counters;
     volatile uint64_t *status;
-    uint32_t keyBits;
-    uint32_t zMax2;            // 2 * zMax: z coordinates >= this are external (src/marching.cpp:593)
-    uint64_t keyOffset;        // src/marching.cpp:594-599
-    float scale, bx, by, bz;   // ScaleBiasFilter
+    // emitVertices
+    const float *field;
+    uint32_t pitch, zStride, zFirst;
+    uint3 gridOffset;
+    float *welded;
+    uint64_t *weldedKeys;
+    uint64_t keyOffset;              // src/marching.cpp:594-599
+    float scale, bx, by, bz;         // ScaleBiasFilter
 };
 
-__global__ void __launch_bounds__(kWeldThreads) weldVerticesKernel(WeldParams P)
+constexpr int kLatThreads = 256;
+constexpr int kLatItems = 8;
+
+// countUniqueVertices + scan (kernels/marching.cl:271-279, src/marching.cpp:721): exclusive
+// (unflagged, flagged) vertex counts in front of every non-empty lattice word, in key order.
+__global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P)
 {
     __shared__ uint64_t sScan[33];
     __shared__ uint32_t sTile;
     __shared__ uint64_t sPrefix;
-    if (P.counters[CTR_OVERFLOW]) return;   // the block did not fit: the host splits it and starts over
-    const uint32_t n = P.counters[CTR_VERTS];
+    if (P.counters[CTR_OVERFLOW]) return;
     if (threadIdx.x == 0) sTile = atomicAdd(&P.counters[CTR_WELD_TICKET], 1u);
     __syncthreads();
     const uint32_t tile = sTile;
-    const uint32_t tileBase = tile * (kWeldThreads * kWeldItems);
-    if (tileBase >= n) return;   // ticket order: every later tile is out of range too
-    const uint32_t base = tileBase + threadIdx.x * kWeldItems;
+    const uint32_t base = tile * (kLatThreads * kLatItems) + threadIdx.x * kLatItems;
 
-    uint32_t key[kWeldItems + 1];
+    uint32_t row = base / P.stride, wcol = base % P.stride;
+    uint32_t y2 = row % P.rows, z2 = row / P.rows;
+    uint32_t m[kLatItems], u[kLatItems], f[kLatItems];
+    uint32_t nU = 0, nF = 0;
 #pragma unroll
-    for (int i = 0; i <= kWeldItems; i++) key[i] = base + i < n ? P.keys[base + i] : 0xFFFFFFFFu;
-    const uint32_t coordMask = (1u << P.keyBits) - 1;
-    const uint32_t flagBit = 1u << (3 * P.keyBits);
-    uint32_t nUnique = 0, nInternal = 0;
-    bool last[kWeldItems], ext[kWeldItems];
-#pragma unroll
-    for (int i = 0; i < kWeldItems; i++)
+    for (int i = 0; i < kLatItems; i++)
     {
-        bool in = base + i < n;
-        last[i] = in && key[i] != key[i + 1];   // countUniqueVertices, :271-279 (sentinel = UINT_MAX)
-        uint32_t z2 = (key[i] >> (2 * P.keyBits)) & coordMask;
-        ext[i] = (key[i] & flagBit) || z2 >= P.zMax2;
-        nUnique += last[i];
-        nInternal += last[i] && !ext[i];
+        m[i] = base + i < P.totalWords ? P.mask[base + i] : 0u;
+        const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
+        u[i] = nU;
+        f[i] = nF;
+        nU += __popc(m[i] & ~fm);
+        nF += __popc(m[i] & fm);
+        if (++wcol == P.stride)
+        {
+            wcol = 0;
+            if (++y2 == P.rows)
+            {
+                y2 = 0;
+                z2++;
+            }
+        }
     }
-    uint64_t packed = (uint64_t) nUnique | ((uint64_t) nInternal << 31);
     uint64_t total;
-    uint64_t excl = blockExclusiveScan(packed, sScan, &total);
+    const uint64_t excl = blockExclusiveScan((uint64_t) nU | ((uint64_t) nF << 31), sScan, &total);
     if (threadIdx.x < 32)
     {
-        uint64_t p = lookbackExclusive(P.status, tile, total);
+        const uint64_t p = lookbackExclusive(P.status, tile, total);
         if (threadIdx.x == 0) sPrefix = p;
     }
     __syncthreads();
-    uint32_t u = (uint32_t) ((sPrefix + excl) & 0x7FFFFFFFu);
-    if (tileBase + kWeldThreads * kWeldItems >= n && threadIdx.x == kWeldThreads - 1)
-    {
-        uint64_t end = sPrefix + total;
-        P.counters[CTR_WELDED] = (uint32_t) (end & 0x7FFFFFFFu);
-        P.counters[CTR_FIRST_EXTERNAL] = (uint32_t) (end >> 31);
-    }
-
-    // ---- compactVertices (:295-326) + scaleBiasVertices ----
+    const uint64_t mine = sPrefix + excl;
+    const uint32_t preU = (uint32_t) (mine & 0x7FFFFFFFu), preF = (uint32_t) (mine >> 31);
+    const uint32_t lastPlane = (P.planes - 1) * P.rows * P.stride;   // its vertices are external, the ones before it are not
 #pragma unroll
-    for (int i = 0; i < kWeldItems; i++)
+    for (int i = 0; i < kLatItems; i++)
     {
-        if (base + i >= n) break;
-        const uint32_t orig = P.vidx[base + i];
-        P.indexRemap[orig] = u;
-        if (last[i])
-        {
-            const float4 v = P.unwelded[orig];
-            P.welded[3 * (size_t) u + 0] = __fmaf_rn(v.x, P.scale, P.bx);
-            P.welded[3 * (size_t) u + 1] = __fmaf_rn(v.y, P.scale, P.by);
-            P.welded[3 * (size_t) u + 2] = __fmaf_rn(v.z, P.scale, P.bz);
-            if (ext[i])
-            {
-                const uint64_t kx = key[i] & coordMask, ky = (key[i] >> P.keyBits) & coordMask,
-                               kz = (key[i] >> (2 * P.keyBits)) & coordMask;
-                P.weldedKeys[u] = (kx | (ky << kKeyAxisBits) | (kz << (2 * kKeyAxisBits))) + P.keyOffset;
-            }
-            u++;
-        }
+        if (m[i]) P.prefix[base + i] = make_uint2(preU + u[i], preF + f[i]);
+        if (base + i == lastPlane) P.counters[CTR_FIRST_EXTERNAL] = preU + u[i];
+    }
+    if (base + kLatItems >= P.totalWords && base < P.totalWords)
+    {
+        // the thread holding the last word: grand totals
+        P.counters[CTR_UNFLAGGED] = preU + nU;
+        P.counters[CTR_WELDED] = preU + nU + preF + nF;
     }
 }
 
-__global__ void __launch_bounds__(256) reindexKernel(uint32_t *__restrict__ indices, const uint32_t *__restrict__ indexRemap,
-                                                     const uint32_t *__restrict__ counters)
+// One thread per non-empty lattice word: interpolate its vertices (interp(), kernels/marching.cl:
+// 130-138 — the edge runs from its lower corner A = lattice >> 1 along d = lattice & 1, exactly
+// the corner order of the edge table), apply scale/bias and store them at their welded index
+// (compactVertices :295-326, scaleBiasVertices kernels/scale_bias.cl:32-40).
+__global__ void __launch_bounds__(kLatThreads) emitVerticesKernel(LatticeParams P)
 {
-    if (counters[CTR_OVERFLOW]) return;
-    const uint32_t n = counters[CTR_INDICES];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        indices[i] = indexRemap[indices[i]];
+    if (P.counters[CTR_OVERFLOW]) return;
+    const uint32_t word = blockIdx.x * kLatThreads + threadIdx.x;
+    if (word >= P.totalWords) return;
+    uint32_t m = __ldg(P.mask + word);
+    if (m == 0) return;
+    const uint2 pre = P.prefix[word];
+    const uint32_t row = word / P.stride, wcol = word % P.stride;
+    const uint32_t y2 = row % P.rows, z2 = row / P.rows;
+    const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
+    const bool topPlane = z2 == P.planes - 1;
+    uint32_t rankU = pre.x, rankF = P.counters[CTR_UNFLAGGED] + pre.y;
+    const uint32_t ay = y2 >> 1, dy = y2 & 1, az = P.zFirst + (z2 >> 1), dz = z2 & 1;
+    const float *const rowA = P.field + ((size_t) az * P.zStride + ay) * P.pitch;
+    const float *const rowB = P.field + ((size_t) (az + dz) * P.zStride + ay + dy) * P.pitch;
+    const float fy = (float) (ay + P.gridOffset.y), fz = (float) (az + P.gridOffset.z);
+    while (m)
+    {
+        const uint32_t bit = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t x2 = wcol * 32 + bit, ax = x2 >> 1, dx = x2 & 1;
+        const float isoA = __ldg(rowA + ax), isoB = __ldg(rowB + ax + dx);
+        // no contraction, explicit fma: kernels/marching.cl:133
+        const float inv = __fdiv_rn(1.0f, __fsub_rn(isoA, isoB));
+        const float t = __fmul_rn(isoA, inv);
+        const float px = __fmaf_rn(t, (float) dx, (float) (ax + P.gridOffset.x));
+        const float py = __fmaf_rn(t, (float) dy, fy);
+        const float pz = __fmaf_rn(t, (float) dz, fz);
+        const bool flagged = (fm >> bit) & 1;
+        const uint32_t rank = flagged ? rankF++ : rankU++;
+        P.welded[3 * (size_t) rank + 0] = __fmaf_rn(px, P.scale, P.bx);
+        P.welded[3 * (size_t) rank + 1] = __fmaf_rn(py, P.scale, P.by);
+        P.welded[3 * (size_t) rank + 2] = __fmaf_rn(pz, P.scale, P.bz);
+        if (flagged || topPlane)
+            P.weldedKeys[rank] = ((uint64_t) x2 | ((uint64_t) y2 << kKeyAxisBits) | ((uint64_t) (z2 + 2 * P.zFirst) << (2 * kKeyAxisBits)))
+                                 + P.keyOffset;
+    }
 }
 
 }  // namespace
@@ -585,13 +672,11 @@ int marchingAlloc(mlsb_worker *w)
         MLSB_CUDA(cudaMalloc(&w->blockActive, nb * nb * nb + 16));
         MLSB_CUDA(cudaMemset(w->blockActive, 0, nb * nb * nb + 16));
     }
-    MLSB_CUDA(cudaMalloc(&w->unwelded, (w->vertexSpace + 1) * sizeof(float4)));
-    for (int i = 0; i < 2; i++)
-    {
-        MLSB_CUDA(cudaMalloc(&w->vertKeys[i], (w->vertexSpace + 8) * sizeof(uint32_t)));
-        MLSB_CUDA(cudaMalloc(&w->vertIdx[i], (w->vertexSpace + 8) * sizeof(uint32_t)));
-    }
-    MLSB_CUDA(cudaMalloc(&w->indexRemap, (w->vertexSpace + 1) * sizeof(uint32_t)));
+    // lattice of edge midpoints for the largest block: (2 cells + 1)^2 rows of 2 words per 32 cells (+1 carry word)
+    w->latticeWords = (size_t) (2 * c.maxCells + 1) * (2 * c.maxCells + 1) * (2 * divUp(c.maxCells, 32u) + 1);
+    MLSB_REQUIRE(w->latticeWords < (1ull << 32) - kLatThreads * kLatItems, MLSB_ERR_LENGTH, "lattice too large");
+    MLSB_CUDA(cudaMalloc(&w->latMask, w->latticeWords * sizeof(uint32_t)));
+    MLSB_CUDA(cudaMalloc(&w->latPrefix, w->latticeWords * sizeof(uint2)));
     MLSB_CUDA(cudaMalloc(&w->indices, (w->indexSpace + 1) * sizeof(uint32_t)));
     MLSB_CUDA(cudaMalloc(&w->welded, (w->vertexSpace + 1) * 3 * sizeof(float)));
     MLSB_CUDA(cudaMalloc(&w->weldedKeys, (w->vertexSpace + 1) * sizeof(uint64_t)));
@@ -606,7 +691,7 @@ int marchingAlloc(mlsb_worker *w)
     MLSB_CUDA(cudaMallocHost(&w->hostBlob, w->hostBlobBytes));
     MLSB_CUDA(cudaMallocHost(&w->hostCounters, CTR_COUNT * sizeof(uint32_t)));
     MLSB_CUDA(cudaFuncSetAttribute(generateCellsKernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   3 * kGenRows * 2 * kGenThreads * (int) sizeof(uint32_t)));
+                                   2 * kGenRows * 2 * kGenThreads * (int) sizeof(uint32_t)));
     return MLSB_OK;
 }
 
@@ -614,13 +699,8 @@ void marchingFree(mlsb_worker *w)
 {
     cudaFree(w->field);
     cudaFree(w->blockActive);
-    cudaFree(w->unwelded);
-    for (int i = 0; i < 2; i++)
-    {
-        cudaFree(w->vertKeys[i]);
-        cudaFree(w->vertIdx[i]);
-    }
-    cudaFree(w->indexRemap);
+    cudaFree(w->latMask);
+    cudaFree(w->latPrefix);
     cudaFree(w->indices);
     cudaFree(w->welded);
     cudaFree(w->weldedKeys);
@@ -634,13 +714,6 @@ void marchingFree(mlsb_worker *w)
 
 namespace
 {
-
-uint32_t bitLength(uint32_t v)
-{
-    uint32_t b = 0;
-    while (v) { b++; v >>= 1; }
-    return b;
-}
 
 // One shipped-out block: the cells between corner slices zFirst..zLast (Marching::addSlices +
 // shipOut with zTop = zFirst, zMax = zLast).  Returns MLSB_ERR_OVERFLOW if the block does not
@@ -658,9 +731,12 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     const uint32_t tiles = (zLast - zFirst) * divUp(cellsY, (uint32_t) kGenRows);
     const uint32_t chunks = divUp(cellsX, (uint32_t) kGenThreads);
     MLSB_REQUIRE(chunks <= 2, MLSB_ERR_LENGTH, "bin too wide");
-    const size_t genSmem = 3 * (size_t) kGenRows * chunks * kGenThreads * sizeof(uint32_t);
-    const uint32_t weldTilesMax = (uint32_t) divUp(w->vertexSpace, (uint64_t) (kWeldThreads * kWeldItems)) + 1;
-    MLSB_REQUIRE(weldTilesMax <= w->scanStatusWords && tiles <= w->maxTiles, MLSB_ERR_LENGTH, "scan scratch too small");
+    const size_t genSmem = 2 * (size_t) kGenRows * chunks * kGenThreads * sizeof(uint32_t);
+    const uint32_t latStride = 2 * divUp(cellsX, 32u) + 1, latRows = 2 * cellsY + 1, latPlanes = 2 * (zLast - zFirst) + 1;
+    const size_t latWords = (size_t) latPlanes * latRows * latStride;
+    const uint32_t latTiles = (uint32_t) divUp(latWords, (size_t) (kLatThreads * kLatItems));
+    MLSB_REQUIRE(latWords <= w->latticeWords && latTiles <= w->scanStatusWords && tiles <= w->maxTiles, MLSB_ERR_LENGTH,
+                 "scan scratch too small");
 
     GenParams G;
     G.field = w->field;
@@ -672,76 +748,77 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     G.zLast = zLast;
     G.numCells = numCells;
     G.gridOffset = make_uint3(keyOffset[0], keyOffset[1], keyOffset[2]);
-    G.top = make_uint3(2 * cellsX, 2 * cellsY, 2 * zFirst);
-    G.keyBits = bitLength(std::max(std::max(2 * cellsX, 2 * cellsY), 2 * zLast));
     G.vertexSpace = (uint32_t) w->vertexSpace;
     G.indexSpace = (uint32_t) w->indexSpace;
-    G.unwelded = w->unwelded;
-    G.keys = w->vertKeys[0];
-    G.vidx = w->vertIdx[0];
     G.indices = w->indices;
     G.counters = w->marchCounters;
+    G.latMask = w->latMask;
+    G.latPrefix = w->latPrefix;
+    G.latStride = latStride;
+    G.latRows = latRows;
     G.tileTotals = w->tileTotals;
     G.blockActive = useActive ? w->blockActive : nullptr;
     G.activeDim = roundUp(w->fieldDim / kMlsWgs, 4u);
     G.tileList = w->tileList;
     G.tables = reinterpret_cast<const Tables *>(w->tables);
-    MLSB_REQUIRE(3 * G.keyBits + 1 <= 32, MLSB_ERR_LENGTH, "bin too large for the compact vertex key");
+
+    LatticeParams L;
+    L.mask = w->latMask;
+    L.prefix = w->latPrefix;
+    L.stride = latStride;
+    L.rows = latRows;
+    L.planes = latPlanes;
+    L.totalWords = (uint32_t) latWords;
+    L.topX = 2 * cellsX;
+    L.topY = 2 * cellsY;
+    L.counters = w->marchCounters;
+    L.status = w->scanStatus;
+    L.field = w->field;
+    L.pitch = pitch;
+    L.zStride = zStride;
+    L.zFirst = zFirst;
+    L.gridOffset = G.gridOffset;
+    L.welded = w->welded;
+    L.weldedKeys = w->weldedKeys;
+    L.keyOffset = ((uint64_t) keyOffset[2] << (2 * kKeyAxisBits + 1)) | ((uint64_t) keyOffset[1] << (kKeyAxisBits + 1))
+                  | ((uint64_t) keyOffset[0] << 1);
+    L.scale = w->scale;
+    L.bx = w->bias[0];
+    L.by = w->bias[1];
+    L.bz = w->bias[2];
 
     {
         ScopedStat st(w, "kernel.marching.zero.time", 0);
         MLSB_CUDA(cudaMemsetAsync(w->marchCounters, 0, CTR_COUNT * sizeof(uint32_t), s));
+        MLSB_CUDA(cudaMemsetAsync(w->latMask, 0, latWords * sizeof(uint32_t), s));
+        MLSB_CUDA(cudaMemsetAsync(w->scanStatus, 0, (size_t) latTiles * sizeof(uint64_t), s));
     }
     {
         ScopedStat st(w, "kernel.marching.genOccupied.time");
         if (chunks == 1) generateCellsKernel<false, 1><<<tiles, kGenThreads, 0, s>>>(G);
         else generateCellsKernel<false, 2><<<tiles, kGenThreads, 0, s>>>(G);
+        w->launches++;
     }
     {
         ScopedStat st(w, "kernel.marching.scanElements.time");
         scanTilesKernel<<<1, 1024, 0, s>>>(w->tileTotals, w->tileList, tiles, w->marchCounters, (uint32_t) w->vertexSpace,
                                            (uint32_t) w->indexSpace);
+        w->launches++;
+    }
+    {
+        ScopedStat st(w, "kernel.marching.countUniqueVertices.time");
+        scanLatticeKernel<<<latTiles, kLatThreads, 0, s>>>(L);
+        w->launches++;
+    }
+    {
+        ScopedStat st(w, "kernel.marching.compactVertices.time");
+        emitVerticesKernel<<<(uint32_t) divUp(latWords, (size_t) kLatThreads), kLatThreads, 0, s>>>(L);
+        w->launches++;
     }
     {
         ScopedStat st(w, "kernel.marching.generateElements.time");
         if (chunks == 1) generateCellsKernel<true, 1><<<tiles, kGenThreads, genSmem, s>>>(G);
         else generateCellsKernel<true, 2><<<tiles, kGenThreads, genSmem, s>>>(G);
-        w->launches += 3;
-    }
-    MLSB_CUDA(cudaGetLastError());
-
-    // Sizes are only known on the device; the sort runs on the device-side count.
-    int cur = 0;
-    MLSB_TRY(radixSortPairsDeviceCount(w, w->vertKeys, w->vertIdx, (uint32_t) w->vertexSpace,
-                                       w->marchCounters + CTR_VERTS, 3 * G.keyBits + 1, &cur,
-                                       "kernel.marching.sortVertices.time", true));
-
-    WeldParams W;
-    W.keys = w->vertKeys[cur];
-    W.vidx = w->vertIdx[cur];
-    W.unwelded = w->unwelded;
-    W.welded = w->welded;
-    W.weldedKeys = w->weldedKeys;
-    W.indexRemap = w->indexRemap;
-    W.counters = w->marchCounters;
-    W.status = w->scanStatus;
-    W.keyBits = G.keyBits;
-    W.zMax2 = 2 * zLast;
-    W.keyOffset = ((uint64_t) keyOffset[2] << (2 * kKeyAxisBits + 1)) | ((uint64_t) keyOffset[1] << (kKeyAxisBits + 1))
-                  | ((uint64_t) keyOffset[0] << 1);
-    W.scale = w->scale;
-    W.bx = w->bias[0];
-    W.by = w->bias[1];
-    W.bz = w->bias[2];
-    {
-        ScopedStat st(w, "kernel.marching.compactVertices.time");
-        MLSB_CUDA(cudaMemsetAsync(w->scanStatus, 0, (size_t) weldTilesMax * sizeof(uint64_t), s));
-        weldVerticesKernel<<<weldTilesMax, kWeldThreads, 0, s>>>(W);
-        w->launches++;
-    }
-    {
-        ScopedStat st(w, "kernel.marching.reindex.time");
-        reindexKernel<<<148 * 8, 256, 0, s>>>(w->indices, w->indexRemap, w->marchCounters);
         w->launches++;
     }
     MLSB_CUDA(cudaGetLastError());

@@ -199,11 +199,14 @@ MLSB_API int mlsb_group_create(const mlsb_worker_config *config, uint32_t numWor
 MLSB_API void mlsb_group_destroy(mlsb_group *g);
 /* Queues one bin (WorkerGroup::get + push, src/worker_group.h:137-199); blocks while the queue is
  * full.  size = corners per axis, offset = low extent of the bin in the full grid.
- * Bins are taken in submission order, so with stageSplats the splat memory of the bin submitted
- * (queueDepth + numWorkers) submits earlier is no longer read once a submit returns: a loader can
- * cycle through queueDepth + numWorkers + 1 gather buffers. */
+ * The splat memory must stay valid until the bin is released, see mlsb_group_released. */
 MLSB_API int mlsb_group_submit(mlsb_group *g, const mlsb_splat *splats, uint32_t numSplats,
                                const uint32_t size[3], const int32_t offset[3], uint64_t tag);
+/* count = the number of leading submits (in submission order) whose splat memory the group will
+ * not read again: with stageSplats a bin is released as soon as a worker has copied it into its
+ * staging buffer, otherwise when its upload has completed.  A loader that recycles gather buffers
+ * (BucketLoader's circular buffer, src/bucket_loader.cpp:104-126) polls this before reusing one. */
+MLSB_API int mlsb_group_released(mlsb_group *g, uint64_t *count);
 /* Blocks until every queued bin has been processed; returns the first error any worker hit. */
 MLSB_API int mlsb_group_wait(mlsb_group *g);
 /* By default the sink is called by one worker at a time, like the reference's single mesher thread

@@ -75,6 +75,7 @@ API = {
     "mlsb_group_submit": (C.c_int, [_P, _P, C.c_uint32, _P, _P, C.c_uint64]),
     "mlsb_group_wait": (C.c_int, [_P]),
     "mlsb_group_set_concurrent_sink": (C.c_int, [_P, C.c_int]),
+    "mlsb_group_released": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "mlsb_group_worker": (C.c_int, [_P, C.c_uint32, C.POINTER(_P)]),
     "mlsb_group_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "mlsb_worker_set_profiling": (C.c_int, [_P, C.c_int]),

@@ -150,7 +150,7 @@ int mlsb_worker_resource_usage(const mlsb_worker_config *c, uint64_t *deviceByte
     total += maxStart * 4 * 6 + (entries + 2 * ranges) * 4 + entries * 4 * 4;   // octree
     total += dim * dim * dim * 4;                                               // field
     uint64_t lattice = (2ull * c->maxCells + 1) * (2ull * c->maxCells + 1) * (2 * divUp<uint64_t>(c->maxCells, 32) + 1);
-    total += vs * (12 + 8) + is * 4 + lattice * 12;                             // marching
+    total += vs * 2 * (12 + 8) + is * 4 + lattice * 12;                         // marching
     *deviceBytes = total;
     return MLSB_OK;
 }

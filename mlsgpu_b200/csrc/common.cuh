@@ -124,6 +124,8 @@ struct mlsb_worker
     uint32_t *indices = nullptr;
     float *welded = nullptr;          // packed float3
     uint64_t *weldedKeys = nullptr;
+    float *weldedFlagged = nullptr;   // vertices carrying the external flag: they follow all others in the output
+    uint64_t *weldedKeysFlagged = nullptr;
     uint32_t *marchCounters = nullptr;   // device: see marching.cu
     uint64_t *tileTotals = nullptr;      // per marching tile: totals, then exclusive bases
     uint32_t *tileList = nullptr;        // non-empty marching tiles

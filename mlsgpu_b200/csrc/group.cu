@@ -24,6 +24,7 @@ struct mlsb_group
         uint32_t size[3];
         int32_t offset[3];
         uint64_t tag;
+        uint64_t sequence;   // position in submission order
     };
 
     std::vector<mlsb_worker *> workers;
@@ -34,6 +35,9 @@ struct mlsb_group
     std::condition_variable canPush, canPop, idle;
     size_t maxQueue = 0;
     size_t inFlight = 0;
+    uint64_t submitted = 0;          // bins submitted so far
+    uint64_t releasedUpTo = 0;       // the splat memory of every bin with sequence < this is no longer read
+    std::vector<uint64_t> releasedLater;   // released out of order (workers overtake each other)
     bool stopping = false;
     bool stage = true;
 
@@ -75,6 +79,31 @@ void groupTrampoline(const mlsb_mesh_sizes *sizes, const void *blob, void *user)
     }
 }
 
+// The caller's splat memory of bin `sequence` will not be read again.
+void releaseSplats(mlsb_group *g, uint64_t sequence)
+{
+    std::lock_guard<std::mutex> lock(g->mutex);
+    if (sequence != g->releasedUpTo)
+    {
+        g->releasedLater.push_back(sequence);
+        return;
+    }
+    g->releasedUpTo++;
+    for (bool found = true; found;)
+    {
+        found = false;
+        for (size_t i = 0; i < g->releasedLater.size(); i++)
+            if (g->releasedLater[i] == g->releasedUpTo)
+            {
+                g->releasedLater[i] = g->releasedLater.back();
+                g->releasedLater.pop_back();
+                g->releasedUpTo++;
+                found = true;
+                break;
+            }
+    }
+}
+
 void workerLoop(mlsb_group *g, size_t index)
 {
     mlsb_worker *w = g->workers[index];
@@ -98,6 +127,7 @@ void workerLoop(mlsb_group *g, size_t index)
             memcpy(g->staging[index], item.splats, (size_t) item.numSplats * sizeof(mlsb_splat));
             src = g->staging[index];
         }
+        if (g->stage) releaseSplats(g, item.sequence);
         int st = mlsb_splats_upload_async(w, src, 0, item.numSplats);
         // DeviceWorkerGroupBase::Worker::operator(), src/workers.cpp:232-286
         SinkContext ctx{g, item.tag};
@@ -111,6 +141,7 @@ void workerLoop(mlsb_group *g, size_t index)
                 g->message = mlsb_last_error_string();
             }
         }
+        if (!g->stage) releaseSplats(g, item.sequence);   // process_bin has waited for the upload
         g->bins++;
         g->splats += item.numSplats;
         {
@@ -192,6 +223,7 @@ int mlsb_group_submit(mlsb_group *g, const mlsb_splat *splats, uint32_t numSplat
     {
         std::unique_lock<std::mutex> lock(g->mutex);
         g->canPush.wait(lock, [g] { return g->queue.size() < g->maxQueue; });   // WorkerGroup::get blocks likewise
+        item.sequence = g->submitted++;
         g->queue.push_back(item);
     }
     g->canPop.notify_one();
@@ -210,6 +242,14 @@ int mlsb_group_wait(mlsb_group *g)
     if (st != MLSB_OK) setError("%s", g->message.c_str());
     g->status = MLSB_OK;
     return st;
+}
+
+int mlsb_group_released(mlsb_group *g, uint64_t *count)
+{
+    MLSB_REQUIRE(g != nullptr && count != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
+    std::lock_guard<std::mutex> lock(g->mutex);
+    *count = g->releasedUpTo;
+    return MLSB_OK;
 }
 
 int mlsb_group_set_concurrent_sink(mlsb_group *g, int enabled)

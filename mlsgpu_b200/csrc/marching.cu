@@ -11,12 +11,13 @@
 //                   that holds surface also ORs the lattice bits of its valid cells' crossed edges
 //                   (19 edges = 9 lattice rows x {even, odd} columns, a handful of logic ops each)
 //   scanTiles       per-tile index bases (the role of clogs::Scan at src/marching.cpp:721)
-//   scanLattice     countUniqueVertices + scan (:271-279): exclusive popcount prefix of every
-//                   lattice word in (z, y, x) order = key order, split into unflagged / flagged
-//                   (the external flag is the top key bit, so flagged vertices sort last)
-//   emitVertices    generateElements' interpolation (:130-138, :184-258) + compactVertices
-//                   (:295-326) + scaleBiasVertices (kernels/scale_bias.cl:32-40): one thread per
-//                   non-empty lattice word writes its vertices at their final positions
+//   scanLattice     countUniqueVertices + scan + compactVertices + scaleBiasVertices (:271-326,
+//                   kernels/scale_bias.cl:32-40) with generateElements' interpolation (:130-138):
+//                   one decoupled look-back scan over the lattice words in (z, y, x) order = key
+//                   order gives every word its exclusive vertex count, split into unflagged /
+//                   flagged (the external flag is the top key bit, so flagged vertices sort last),
+//                   and the thread that holds a non-empty word writes its vertices straight to
+//                   their final positions
 //   generateCells<emit>  one thread per index: cell -> edge -> lattice point -> rank (reindex, :334-340)
 //
 // tests/lattice_model.py states the same identity in numpy and tests/test_lattice_model.py checks
@@ -356,24 +357,20 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
                         // (x, y, z), b = (x, y+1, z), c = (x, y, z+1), d = (x, y+1, z+1) and their
                         // x+1 twins, the 19 edges of a cell fall on 9 lattice rows (oy, oz) in
                         // {0,1,2}^2 relative to (2y, 2z): odd columns 2x+1 hold the 9 edges with an
-                        // x component, even columns 2x / 2x+2 the 10 without.  Lane oz*3+oy does row
-                        // (oy, oz); contributions from neighbouring cells, rows, slabs meet by OR. ----
+                        // x component, even columns 2x / 2x+2 the 10 without.  Contributions from
+                        // neighbouring cells, rows and slabs meet by OR. ----
                         const uint32_t a = p0.s0, a1 = p0.s1, b = c0.s0, b1 = c0.s1, cc = p1.s0, cc1 = p1.s1, d = c1.s0, d1 = c1.s1;
                         const uint32_t valid = pv & cv & inRange;
-                        uint32_t odd = 0, even = 0, evenNext = 0;
-                        switch (lane)
-                        {
-                        case 0: odd = a ^ a1; break;
-                        case 1: odd = a ^ b1; even = a ^ b; evenNext = a1 ^ b1; break;
-                        case 2: odd = b ^ b1; break;
-                        case 3: odd = a ^ cc1; even = a ^ cc; evenNext = a1 ^ cc1; break;
-                        case 4: odd = a ^ d1; even = a ^ d; evenNext = a1 ^ d1; break;
-                        case 5: odd = b ^ d1; even = b ^ d; evenNext = b1 ^ d1; break;
-                        case 6: odd = cc ^ cc1; break;
-                        case 7: odd = cc ^ d1; even = cc ^ d; evenNext = cc1 ^ d1; break;
-                        case 8: odd = d ^ d1; break;
-                        default: break;
-                        }
+                        // lane L handles row (oy, oz) = (L % 3, L / 3): its edges run from corner row
+                        // (y + ly, z + lz) to (y + hy, z + hz), where an offset of 0 / 1 / 2 means
+                        // (0,0) / (0,1) / (1,1); when both offsets are even lo == hi and the even
+                        // columns are empty by themselves
+                        const uint32_t oy = lane % 3, oz = (lane / 3) % 3;
+                        const bool ly = oy == 2, hy = oy >= 1, lz = oz == 2, hz = oz >= 1;
+                        const uint32_t lo = lz ? (ly ? d : cc) : (ly ? b : a), lo1 = lz ? (ly ? d1 : cc1) : (ly ? b1 : a1);
+                        const uint32_t hi = hz ? (hy ? d : cc) : (hy ? b : a), hi1 = hz ? (hy ? d1 : cc1) : (hy ? b1 : a1);
+                        uint32_t odd = lo ^ hi1, even = lo ^ hi;
+                        const uint32_t evenNext = lo1 ^ hi1;
                         if (lane < 9)
                         {
                             odd &= valid;
@@ -381,7 +378,7 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
                             // to bit 0 of the next word pair
                             even &= valid | (valid << 1);
                             const uint32_t carry = (evenNext & valid) >> 31;
-                            const uint32_t y2 = 2 * (y0 + r) + lane % 3, z2 = 2 * (z - P.zFirst) + lane / 3;
+                            const uint32_t y2 = 2 * (y0 + r) + oy, z2 = 2 * (z - P.zFirst) + oz;
                             uint32_t *const row = P.latMask + ((size_t) z2 * P.latRows + y2) * P.latStride + (x0 >> 4);
                             const uint32_t w0 = spread16(even) | (spread16(odd) << 1);
                             const uint32_t w1 = spread16(even >> 16) | (spread16(odd >> 16) << 1);
@@ -525,8 +522,8 @@ struct LatticeParams
     const float *field;
     uint32_t pitch, zStride, zFirst;
     uint3 gridOffset;
-    float *welded;
-    uint64_t *weldedKeys;
+    float *welded, *weldedFlagged;   // unflagged vertices by rank; flagged ones by their own rank
+    uint64_t *weldedKeys, *weldedKeysFlagged;
     uint64_t keyOffset;              // src/marching.cpp:594-599
     float scale, bx, by, bz;         // ScaleBiasFilter
 };
@@ -534,32 +531,28 @@ struct LatticeParams
 constexpr int kLatThreads = 256;
 constexpr int kLatItems = 8;
 
-// countUniqueVertices + scan (kernels/marching.cl:271-279, src/marching.cpp:721): exclusive
-// (unflagged, flagged) vertex counts in front of every non-empty lattice word, in key order.
+// countUniqueVertices + scan + compactVertices + scaleBiasVertices in one pass
+// (kernels/marching.cl:271-326, src/marching.cpp:721, kernels/scale_bias.cl:32-40): the exclusive
+// (unflagged, flagged) vertex counts in front of every non-empty lattice word, in key order, and
+// the vertices themselves.  A vertex is interpolated from the lower corner A = lattice >> 1 of its
+// edge along d = lattice & 1 — the corner order of the edge table — as interp() does (:130-138).
+// Flagged vertices follow ALL unflagged ones in the output; their count is only known at the end
+// of the scan, so they go to a buffer of their own and the readback concatenates the two.
 __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P)
 {
     __shared__ uint64_t sScan[33];
     __shared__ uint32_t sTile;
     __shared__ uint64_t sPrefix;
-    if (P.counters[CTR_OVERFLOW]) return;
+    if (P.counters[CTR_OVERFLOW]) return;   // the block did not fit: the host splits it and starts over
     if (threadIdx.x == 0) sTile = atomicAdd(&P.counters[CTR_WELD_TICKET], 1u);
     __syncthreads();
     const uint32_t tile = sTile;
     const uint32_t base = tile * (kLatThreads * kLatItems) + threadIdx.x * kLatItems;
 
-    uint32_t row = base / P.stride, wcol = base % P.stride;
-    uint32_t y2 = row % P.rows, z2 = row / P.rows;
-    uint32_t m[kLatItems], u[kLatItems], f[kLatItems];
-    uint32_t nU = 0, nF = 0;
-#pragma unroll
-    for (int i = 0; i < kLatItems; i++)
-    {
-        m[i] = base + i < P.totalWords ? P.mask[base + i] : 0u;
-        const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
-        u[i] = nU;
-        f[i] = nF;
-        nU += __popc(m[i] & ~fm);
-        nF += __popc(m[i] & fm);
+    const uint32_t row0 = base / P.stride, wcol0 = base % P.stride;
+    const uint32_t y20 = row0 % P.rows, z20 = row0 / P.rows;
+    uint32_t wcol = wcol0, y2 = y20, z2 = z20;
+    auto advance = [&]() {
         if (++wcol == P.stride)
         {
             wcol = 0;
@@ -569,6 +562,20 @@ __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P
                 z2++;
             }
         }
+    };
+    uint32_t m[kLatItems];
+    uint32_t nU = 0, nF = 0, any = 0, beforeLastPlane = 0;
+    const uint32_t lastPlane = (P.planes - 1) * P.rows * P.stride;   // its vertices are external, the ones before it are not
+#pragma unroll
+    for (int i = 0; i < kLatItems; i++)
+    {
+        m[i] = base + i < P.totalWords ? P.mask[base + i] : 0u;
+        if (base + i == lastPlane) beforeLastPlane = nU;
+        const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
+        nU += __popc(m[i] & ~fm);
+        nF += __popc(m[i] & fm);
+        any |= m[i];
+        advance();
     }
     uint64_t total;
     const uint64_t excl = blockExclusiveScan((uint64_t) nU | ((uint64_t) nF << 31), sScan, &total);
@@ -579,63 +586,52 @@ __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P
     }
     __syncthreads();
     const uint64_t mine = sPrefix + excl;
-    const uint32_t preU = (uint32_t) (mine & 0x7FFFFFFFu), preF = (uint32_t) (mine >> 31);
-    const uint32_t lastPlane = (P.planes - 1) * P.rows * P.stride;   // its vertices are external, the ones before it are not
-#pragma unroll
-    for (int i = 0; i < kLatItems; i++)
-    {
-        if (m[i]) P.prefix[base + i] = make_uint2(preU + u[i], preF + f[i]);
-        if (base + i == lastPlane) P.counters[CTR_FIRST_EXTERNAL] = preU + u[i];
-    }
+    uint32_t rankU = (uint32_t) (mine & 0x7FFFFFFFu), rankF = (uint32_t) (mine >> 31);
+    // internal vertices = unflagged ones in front of the last plane
+    if (base <= lastPlane && lastPlane < base + kLatItems) P.counters[CTR_FIRST_EXTERNAL] = rankU + beforeLastPlane;
     if (base + kLatItems >= P.totalWords && base < P.totalWords)
     {
         // the thread holding the last word: grand totals
-        P.counters[CTR_UNFLAGGED] = preU + nU;
-        P.counters[CTR_WELDED] = preU + nU + preF + nF;
+        P.counters[CTR_UNFLAGGED] = rankU + nU;
+        P.counters[CTR_WELDED] = rankU + nU + rankF + nF;
     }
-}
+    if (!any) return;
 
-// One thread per non-empty lattice word: interpolate its vertices (interp(), kernels/marching.cl:
-// 130-138 — the edge runs from its lower corner A = lattice >> 1 along d = lattice & 1, exactly
-// the corner order of the edge table), apply scale/bias and store them at their welded index
-// (compactVertices :295-326, scaleBiasVertices kernels/scale_bias.cl:32-40).
-__global__ void __launch_bounds__(kLatThreads) emitVerticesKernel(LatticeParams P)
-{
-    if (P.counters[CTR_OVERFLOW]) return;
-    const uint32_t word = blockIdx.x * kLatThreads + threadIdx.x;
-    if (word >= P.totalWords) return;
-    uint32_t m = __ldg(P.mask + word);
-    if (m == 0) return;
-    const uint2 pre = P.prefix[word];
-    const uint32_t row = word / P.stride, wcol = word % P.stride;
-    const uint32_t y2 = row % P.rows, z2 = row / P.rows;
-    const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
-    const bool topPlane = z2 == P.planes - 1;
-    uint32_t rankU = pre.x, rankF = P.counters[CTR_UNFLAGGED] + pre.y;
-    const uint32_t ay = y2 >> 1, dy = y2 & 1, az = P.zFirst + (z2 >> 1), dz = z2 & 1;
-    const float *const rowA = P.field + ((size_t) az * P.zStride + ay) * P.pitch;
-    const float *const rowB = P.field + ((size_t) (az + dz) * P.zStride + ay + dy) * P.pitch;
-    const float fy = (float) (ay + P.gridOffset.y), fz = (float) (az + P.gridOffset.z);
-    while (m)
+    wcol = wcol0, y2 = y20, z2 = z20;
+#pragma unroll
+    for (int i = 0; i < kLatItems; i++, advance())
     {
-        const uint32_t bit = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t x2 = wcol * 32 + bit, ax = x2 >> 1, dx = x2 & 1;
-        const float isoA = __ldg(rowA + ax), isoB = __ldg(rowB + ax + dx);
-        // no contraction, explicit fma: kernels/marching.cl:133
-        const float inv = __fdiv_rn(1.0f, __fsub_rn(isoA, isoB));
-        const float t = __fmul_rn(isoA, inv);
-        const float px = __fmaf_rn(t, (float) dx, (float) (ax + P.gridOffset.x));
-        const float py = __fmaf_rn(t, (float) dy, fy);
-        const float pz = __fmaf_rn(t, (float) dz, fz);
-        const bool flagged = (fm >> bit) & 1;
-        const uint32_t rank = flagged ? rankF++ : rankU++;
-        P.welded[3 * (size_t) rank + 0] = __fmaf_rn(px, P.scale, P.bx);
-        P.welded[3 * (size_t) rank + 1] = __fmaf_rn(py, P.scale, P.by);
-        P.welded[3 * (size_t) rank + 2] = __fmaf_rn(pz, P.scale, P.bz);
-        if (flagged || topPlane)
-            P.weldedKeys[rank] = ((uint64_t) x2 | ((uint64_t) y2 << kKeyAxisBits) | ((uint64_t) (z2 + 2 * P.zFirst) << (2 * kKeyAxisBits)))
-                                 + P.keyOffset;
+        uint32_t bits = m[i];
+        if (bits == 0) continue;
+        P.prefix[base + i] = make_uint2(rankU, rankF);
+        const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
+        const bool topPlane = z2 == P.planes - 1;
+        const uint32_t ay = y2 >> 1, dy = y2 & 1, az = P.zFirst + (z2 >> 1), dz = z2 & 1;
+        const float *const rowA = P.field + ((size_t) az * P.zStride + ay) * P.pitch;
+        const float *const rowB = P.field + ((size_t) (az + dz) * P.zStride + ay + dy) * P.pitch;
+        const float fy = (float) (ay + P.gridOffset.y), fz = (float) (az + P.gridOffset.z);
+        while (bits)
+        {
+            const uint32_t bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint32_t x2 = wcol * 32 + bit, ax = x2 >> 1, dx = x2 & 1;
+            const float isoA = __ldg(rowA + ax), isoB = __ldg(rowB + ax + dx);
+            // no contraction, explicit fma: kernels/marching.cl:133
+            const float inv = __fdiv_rn(1.0f, __fsub_rn(isoA, isoB));
+            const float t = __fmul_rn(isoA, inv);
+            const float px = __fmaf_rn(t, (float) dx, (float) (ax + P.gridOffset.x));
+            const float py = __fmaf_rn(t, (float) dy, fy);
+            const float pz = __fmaf_rn(t, (float) dz, fz);
+            const bool flagged = (fm >> bit) & 1;
+            const uint32_t rank = flagged ? rankF++ : rankU++;
+            float *const out = (flagged ? P.weldedFlagged : P.welded) + 3 * (size_t) rank;
+            out[0] = __fmaf_rn(px, P.scale, P.bx);
+            out[1] = __fmaf_rn(py, P.scale, P.by);
+            out[2] = __fmaf_rn(pz, P.scale, P.bz);
+            if (flagged || topPlane)
+                (flagged ? P.weldedKeysFlagged : P.weldedKeys)[rank] =
+                    ((uint64_t) x2 | ((uint64_t) y2 << kKeyAxisBits) | ((uint64_t) (z2 + 2 * P.zFirst) << (2 * kKeyAxisBits))) + P.keyOffset;
+        }
     }
 }
 
@@ -680,6 +676,8 @@ int marchingAlloc(mlsb_worker *w)
     MLSB_CUDA(cudaMalloc(&w->indices, (w->indexSpace + 1) * sizeof(uint32_t)));
     MLSB_CUDA(cudaMalloc(&w->welded, (w->vertexSpace + 1) * 3 * sizeof(float)));
     MLSB_CUDA(cudaMalloc(&w->weldedKeys, (w->vertexSpace + 1) * sizeof(uint64_t)));
+    MLSB_CUDA(cudaMalloc(&w->weldedFlagged, (w->vertexSpace + 1) * 3 * sizeof(float)));
+    MLSB_CUDA(cudaMalloc(&w->weldedKeysFlagged, (w->vertexSpace + 1) * sizeof(uint64_t)));
     MLSB_CUDA(cudaMalloc(&w->marchCounters, CTR_COUNT * sizeof(uint32_t)));
     w->maxTiles = c.maxCells * divUp(c.maxCells, (uint32_t) kGenRows);
     MLSB_CUDA(cudaMalloc(&w->tileTotals, (size_t) w->maxTiles * sizeof(uint64_t)));
@@ -704,6 +702,8 @@ void marchingFree(mlsb_worker *w)
     cudaFree(w->indices);
     cudaFree(w->welded);
     cudaFree(w->weldedKeys);
+    cudaFree(w->weldedFlagged);
+    cudaFree(w->weldedKeysFlagged);
     cudaFree(w->marchCounters);
     cudaFree(w->tileTotals);
     cudaFree(w->tileList);
@@ -780,6 +780,8 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     L.gridOffset = G.gridOffset;
     L.welded = w->welded;
     L.weldedKeys = w->weldedKeys;
+    L.weldedFlagged = w->weldedFlagged;
+    L.weldedKeysFlagged = w->weldedKeysFlagged;
     L.keyOffset = ((uint64_t) keyOffset[2] << (2 * kKeyAxisBits + 1)) | ((uint64_t) keyOffset[1] << (kKeyAxisBits + 1))
                   | ((uint64_t) keyOffset[0] << 1);
     L.scale = w->scale;
@@ -806,13 +808,8 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
         w->launches++;
     }
     {
-        ScopedStat st(w, "kernel.marching.countUniqueVertices.time");
-        scanLatticeKernel<<<latTiles, kLatThreads, 0, s>>>(L);
-        w->launches++;
-    }
-    {
         ScopedStat st(w, "kernel.marching.compactVertices.time");
-        emitVerticesKernel<<<(uint32_t) divUp(latWords, (size_t) kLatThreads), kLatThreads, 0, s>>>(L);
+        scanLatticeKernel<<<latTiles, kLatThreads, 0, s>>>(L);
         w->launches++;
     }
     {
@@ -835,6 +832,9 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
 
     mlsb_mesh_sizes sizes{hc[CTR_WELDED], hc[CTR_INDICES] / 3, hc[CTR_FIRST_EXTERNAL]};
     const uint64_t numExternal = sizes.numVertices - sizes.numInternalVertices;
+    // unflagged vertices (internal, then the top plane) and flagged ones live in two buffers
+    const uint64_t numUnflagged = hc[CTR_UNFLAGGED], numFlagged = sizes.numVertices - numUnflagged;
+    const uint64_t numTop = numUnflagged - sizes.numInternalVertices;
     // HostKeyMesh layout, src/mesh.cpp:51-60
     uint8_t *blob = static_cast<uint8_t *>(w->hostBlob);
     uint8_t *hKeys = blob;
@@ -842,10 +842,17 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     uint8_t *hTris = hVerts + sizes.numVertices * 3 * sizeof(float);
     // enqueueReadMesh, src/mesh.cpp:62-102
     MLSB_CUDA(cudaMemcpyAsync(hTris, w->indices, sizes.numTriangles * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    if (numExternal)
-        MLSB_CUDA(cudaMemcpyAsync(hKeys, w->weldedKeys + sizes.numInternalVertices, numExternal * sizeof(uint64_t),
+    if (numTop)
+        MLSB_CUDA(cudaMemcpyAsync(hKeys, w->weldedKeys + sizes.numInternalVertices, numTop * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (numFlagged)
+    {
+        MLSB_CUDA(cudaMemcpyAsync(hKeys + numTop * sizeof(uint64_t), w->weldedKeysFlagged, numFlagged * sizeof(uint64_t),
                                   cudaMemcpyDeviceToHost, s));
-    MLSB_CUDA(cudaMemcpyAsync(hVerts, w->welded, sizes.numVertices * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        MLSB_CUDA(cudaMemcpyAsync(hVerts + numUnflagged * 3 * sizeof(float), w->weldedFlagged, numFlagged * 3 * sizeof(float),
+                                  cudaMemcpyDeviceToHost, s));
+    }
+    if (numUnflagged)
+        MLSB_CUDA(cudaMemcpyAsync(hVerts, w->welded, numUnflagged * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
     MLSB_TRY(waitStream(w));
     if (sink) sink(&sizes, blob, user);
     return MLSB_OK;

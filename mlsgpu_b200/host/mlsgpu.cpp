@@ -21,6 +21,7 @@
 #include <mutex>
 #include <string>
 #include <sys/stat.h>
+#include <thread>
 #include <vector>
 
 #include "bucket.hpp"
@@ -306,9 +307,8 @@ int main(int argc, char **argv)
         }
         const double tCreateWait = now() - tCreate0;   // the part of the creation that was not hidden
         double tGather = 0.0;
-        // Gather buffers are recycled: when a submit returns, at most queueDepth bins are queued and
-        // deviceThreads are being staged, so the buffer used that many submits ago is free again
-        // (see mlsb_group_submit).  Reusing them keeps the gather out of the page-fault path.
+        // Gather buffers are recycled (BucketLoader's circular buffer): a slot is reused once the
+        // group has released the bin that used it, which keeps the gather out of the page-fault path.
         std::size_t largest = 1;
         for (const mlsb::Bin &bin : bins) largest = std::max(largest, bin.ids.size());
         const std::size_t queueDepth = 2 * (std::size_t) o.deviceThreads;   // mlsb_group_create's default
@@ -320,8 +320,15 @@ int main(int argc, char **argv)
             const std::vector<std::uint32_t> &ids = bins[b].ids;
             std::unique_ptr<mlsb_splat[]> &slot = ring[b % ring.size()];
             if (!slot) slot.reset(new mlsb_splat[largest]);
+            for (std::uint64_t released = 0; b >= ring.size();)
+            {
+                mlsb::check(mlsb_group_released(group, &released));
+                if (released > b - ring.size()) break;
+                std::this_thread::yield();
+            }
             mlsb_splat *dst = slot.get();
-#pragma omp parallel for schedule(static)
+            // a few threads are enough and leave the cores to the device workers
+#pragma omp parallel for schedule(static) num_threads(4)
             for (std::int64_t i = 0; i < (std::int64_t) ids.size(); i++) dst[i] = splats[ids[(std::size_t) i]];
             tGather += now() - tg;
             mlsb::check(mlsb_group_submit(group, dst, (std::uint32_t) ids.size(), bins[b].size, bins[b].offset, b));

@@ -448,6 +448,15 @@ class WorkerGroup:
         _check(lib().mlsb_group_wait(self.h))
         self._keep.clear()
 
+    def released(self):
+        """Leading submits whose splat memory the group will not read again (mlsb_group_released)."""
+        n = C.c_uint64()
+        _check(lib().mlsb_group_released(self.h, C.byref(n)))
+        return n.value
+
+    def set_concurrent_sink(self, enabled=True):
+        _check(lib().mlsb_group_set_concurrent_sink(self.h, int(enabled)))
+
     def counters(self):
         b, s, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
         _check(lib().mlsb_group_counters(self.h, C.byref(b), C.byref(s), C.byref(m)))

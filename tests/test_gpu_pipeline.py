@@ -94,6 +94,7 @@ def test_worker_group_matches_single_worker(orc):
         grp.wait()
         nb, ns, mesh_bytes = grp.counters()
         assert nb == len(bins) and ns == sum(len(b["ids"]) for b in bins) and mesh_bytes > 0
+        assert grp.released() == len(bins)      # every bin's splat memory has been handed back
         # an oversized bin is reported by wait(), not swallowed
         with pytest.raises(m.MlsbError):
             grp.submit(np.ascontiguousarray(g[bins[0]["ids"]]), (400, 8, 8), bins[0]["offset"], tag=99)

@@ -263,7 +263,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--splats", type=int, default=10_000_000)
     ap.add_argument("--threads", type=int, default=0,
-                    help="workers per GPU (--device-threads); 0 = 8, fewer when the ranks share few host cores (never below 4)")
+                    help="workers per GPU (--device-threads); 0 = 12, fewer when the ranks share few host cores (never below 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -275,8 +275,9 @@ def main():
         run_reference(args, rank, world)
         return
     if args.threads <= 0:
-        # measured on one B200: 3 workers 250, 4: 266, 6: 273, 8: 281 Msplats/s
-        args.threads = max(4, min(8, (os.cpu_count() or 8) // world - 1))
+        # measured on one B200: 3 workers 250, 4: 266, 6: 273, 8: 281 Msplats/s (sort-based marching);
+        # with the lattice weld and stream priorities 8: 308, 12: 314
+        args.threads = max(4, min(12, (os.cpu_count() or 8) // world - 1))
 
     import torch
     import torch.distributed as dist

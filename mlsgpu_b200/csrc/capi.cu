@@ -173,7 +173,14 @@ int mlsb_worker_create(const mlsb_worker_config *config, mlsb_worker **out)
     w->boundaryFactor = boundaryFactorOf(config->boundaryLimit);
     int st = MLSB_OK;
     auto fail = [&](int code) { mlsb_worker_destroy(w); return code; };
-    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess
+    const char *priority = getenv("MLSB_PRIORITY");
+    const bool split = priority == nullptr || strcmp(priority, "0") != 0;   // on unless MLSB_PRIORITY=0
+    int least = 0, greatest = 0;
+    if (split) cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    if (cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, split ? greatest : 0) != cudaSuccess
+        || (split && (cudaStreamCreateWithPriority(&w->mlsStream, cudaStreamNonBlocking, least) != cudaSuccess
+                      || cudaEventCreateWithFlags(&w->mlsBefore, cudaEventDisableTiming) != cudaSuccess
+                      || cudaEventCreateWithFlags(&w->mlsAfter, cudaEventDisableTiming) != cudaSuccess))
         || cudaStreamCreateWithFlags(&w->copyStream, cudaStreamNonBlocking) != cudaSuccess
         || cudaEventCreateWithFlags(&w->copyEvent, cudaEventDisableTiming) != cudaSuccess)
     {
@@ -222,6 +229,7 @@ void mlsb_worker_destroy(mlsb_worker *w)
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     if (w->copyStream) cudaStreamSynchronize(w->copyStream);
+    if (w->mlsStream) cudaStreamSynchronize(w->mlsStream);
     collectStats(w);
     for (cudaEvent_t e : w->eventPool) cudaEventDestroy(e);
     cudaFree(w->splats);
@@ -233,7 +241,10 @@ void mlsb_worker_destroy(mlsb_worker *w)
     cudaFree(w->scanTicket);
     if (w->copyEvent) cudaEventDestroy(w->copyEvent);
     if (w->syncEvent) cudaEventDestroy(w->syncEvent);
+    if (w->mlsBefore) cudaEventDestroy(w->mlsBefore);
+    if (w->mlsAfter) cudaEventDestroy(w->mlsAfter);
     if (w->stream) cudaStreamDestroy(w->stream);
+    if (w->mlsStream) cudaStreamDestroy(w->mlsStream);
     if (w->copyStream) cudaStreamDestroy(w->copyStream);
     delete w;
 }

@@ -501,18 +501,30 @@ int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &
     dim3 grid(width / kMlsWgs, height / kMlsWgs, divUp(sw.zLast - sw.zFirst + 1, (uint32_t) kMlsWgs));
     ScopedStat st(w, "kernel.mls.processCorners.time", 1, 1);
     const bool count = w->countWork;
+    cudaStream_t s = w->stream;
+    if (w->mlsStream)
+    {
+        MLSB_CUDA(cudaEventRecord(w->mlsBefore, w->stream));
+        MLSB_CUDA(cudaStreamWaitEvent(w->mlsStream, w->mlsBefore, 0));
+        s = w->mlsStream;
+    }
     if (w->cfg.shape == MLSB_SHAPE_SPHERE)
     {
-        if (count) processCornersKernel<MLSB_SHAPE_SPHERE, true><<<grid, kThreads, 0, w->stream>>>(P);
-        else processCornersKernel<MLSB_SHAPE_SPHERE, false><<<grid, kThreads, 0, w->stream>>>(P);
+        if (count) processCornersKernel<MLSB_SHAPE_SPHERE, true><<<grid, kThreads, 0, s>>>(P);
+        else processCornersKernel<MLSB_SHAPE_SPHERE, false><<<grid, kThreads, 0, s>>>(P);
     }
     else
     {
-        if (count) processCornersKernel<MLSB_SHAPE_PLANE, true><<<grid, kThreads, 0, w->stream>>>(P);
-        else processCornersKernel<MLSB_SHAPE_PLANE, false><<<grid, kThreads, 0, w->stream>>>(P);
+        if (count) processCornersKernel<MLSB_SHAPE_PLANE, true><<<grid, kThreads, 0, s>>>(P);
+        else processCornersKernel<MLSB_SHAPE_PLANE, false><<<grid, kThreads, 0, s>>>(P);
     }
     w->launches++;
     MLSB_CUDA(cudaGetLastError());
+    if (w->mlsStream)
+    {
+        MLSB_CUDA(cudaEventRecord(w->mlsAfter, w->mlsStream));
+        MLSB_CUDA(cudaStreamWaitEvent(w->stream, w->mlsAfter, 0));
+    }
     return MLSB_OK;
 }
 

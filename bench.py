@@ -111,7 +111,7 @@ class Runner:
     """`threads` workers on one GPU (the reference's --device-threads), bins handed out
     round-robin; each worker thread uploads its bin and runs mlsb_worker_process_bin."""
 
-    def __init__(self, wl, device, threads):
+    def __init__(self, wl, device, threads, order="largest-first"):
         import mlsgpu_b200 as m
         from mlsgpu_b200.capi import DeviceBuffer, PinnedBuffer, MESH_SINK
         self.m = m
@@ -119,6 +119,10 @@ class Runner:
         self.bins = wl["bins"]
         total = len(wl["splats"])
         self.max_bin = max(b["n"] for b in self.bins)
+        # the workers take bins from one queue; handing out the big ones first keeps the end of a
+        # step from waiting on a single large bin (the reference's copy stage is free to pick, too)
+        self.order = sorted(range(len(self.bins)), key=lambda i: -self.bins[i]["n"]) if order == "largest-first" \
+            else list(range(len(self.bins)))
         # the native worker group (CopyGroup + DeviceWorkerGroup): `threads` worker threads, bins are
         # copied straight from the pointer given to submit (pinned host memory or HBM)
         self.group = m.WorkerGroup(num_workers=threads, stage=False, sink=None, device=device,
@@ -158,7 +162,8 @@ class Runner:
                                                  self.sink, None))
             return
         before = self.group.counters()[2]
-        for i, b in enumerate(self.bins):
+        for i in self.order:
+            b = self.bins[i]
             self.group.submit((base + 32 * b["first"], b["n"]), b["size"], b["offset"], tag=i)
         self.group.wait()
         self.mesh_bytes += self.group.counters()[2] - before
@@ -250,7 +255,7 @@ def workload_config(wl, args):
     return {"workload": "C2: %d-splat synthetic bumpy torus, fit-grid %.3g, sphere fit, smooth %.0f, levels 6, "
                         "subsampling 3, %d bins <=255 cells" % (wl["num_splats"], FIT_GRID, SMOOTH, len(wl["bins"])),
             "splats": wl["num_splats"], "bins": len(wl["bins"]), "splat_instances": int(len(wl["splats"])),
-            "device_threads": args.threads,
+            "device_threads": args.threads, "bin_order": args.order,
             "l2": "inputs larger than L2: %.0f MB of splats and a 64 MiB field per bin cycle through a 126 MB L2"
                   % (len(wl["splats"]) * 32 / 1e6)}
 
@@ -264,6 +269,8 @@ def main():
     ap.add_argument("--splats", type=int, default=10_000_000)
     ap.add_argument("--threads", type=int, default=0,
                     help="workers per GPU (--device-threads); 0 = 12, fewer when the ranks share few host cores (never below 4)")
+    ap.add_argument("--order", default="largest-first", choices=["largest-first", "bucket"],
+                    help="order in which the bins are handed to the worker group")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -271,13 +278,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
     if args.threads <= 0:
         # measured on one B200: 3 workers 250, 4: 266, 6: 273, 8: 281 Msplats/s (sort-based marching);
         # with the lattice weld and stream priorities 8: 308, 12: 314
         args.threads = max(4, min(12, (os.cpu_count() or 8) // world - 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
 
     import torch
     import torch.distributed as dist
@@ -300,7 +307,7 @@ def main():
     import mlsgpu_b200 as m
     wl = make_workload(args.splats, 2 + rank)
     peak_inst = m.measure_fp32_peak(local)
-    runner = Runner(wl, local, args.threads)
+    runner = Runner(wl, local, args.threads, args.order)
 
     def barrier():
         runner.sync()

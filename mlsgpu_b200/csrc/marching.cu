@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P
         }
     };
     uint32_t m[kLatItems];
-    uint32_t nU = 0, nF = 0, any = 0, beforeLastPlane = 0;
+    uint32_t nU = 0, nF = 0, beforeLastPlane = 0;
     const uint32_t lastPlane = (P.planes - 1) * P.rows * P.stride;   // its vertices are external, the ones before it are not
 #pragma unroll
     for (int i = 0; i < kLatItems; i++)
@@ -574,7 +574,6 @@ __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P
         const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
         nU += __popc(m[i] & ~fm);
         nF += __popc(m[i] & fm);
-        any |= m[i];
         advance();
     }
     uint64_t total;
@@ -595,43 +594,75 @@ __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P
         P.counters[CTR_UNFLAGGED] = rankU + nU;
         P.counters[CTR_WELDED] = rankU + nU + rankF + nF;
     }
-    if (!any) return;
-
-    wcol = wcol0, y2 = y20, z2 = z20;
-#pragma unroll
-    for (int i = 0; i < kLatItems; i++, advance())
+    // ---- the tile's vertices, one per thread: the words are listed in shared memory with their
+    // exclusive vertex count inside the tile, thread j finds the word that holds the tile's j-th
+    // vertex and the bit inside it.  (Letting the owner of a word emit all its vertices leaves the
+    // work — two dependent field loads per vertex — to a handful of threads.) ----
+    __shared__ uint32_t sMask[kLatThreads * kLatItems], sCount[kLatThreads * kLatItems];
+    __shared__ uint32_t sRankU[kLatThreads * kLatItems], sRankF[kLatThreads * kLatItems];
+    const uint32_t tileVerts = (uint32_t) (total & 0x7FFFFFFFu) + (uint32_t) (total >> 31);
+    if (tileVerts == 0) return;   // uniform over the CTA
     {
-        uint32_t bits = m[i];
-        if (bits == 0) continue;
-        P.prefix[base + i] = make_uint2(rankU, rankF);
-        const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
-        const bool topPlane = z2 == P.planes - 1;
-        const uint32_t ay = y2 >> 1, dy = y2 & 1, az = P.zFirst + (z2 >> 1), dz = z2 & 1;
-        const float *const rowA = P.field + ((size_t) az * P.zStride + ay) * P.pitch;
-        const float *const rowB = P.field + ((size_t) (az + dz) * P.zStride + ay + dy) * P.pitch;
-        const float fy = (float) (ay + P.gridOffset.y), fz = (float) (az + P.gridOffset.z);
-        while (bits)
+        uint32_t c = (uint32_t) (excl & 0x7FFFFFFFu) + (uint32_t) (excl >> 31);
+        wcol = wcol0, y2 = y20, z2 = z20;
+#pragma unroll
+        for (int i = 0; i < kLatItems; i++, advance())
         {
-            const uint32_t bit = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const uint32_t x2 = wcol * 32 + bit, ax = x2 >> 1, dx = x2 & 1;
-            const float isoA = __ldg(rowA + ax), isoB = __ldg(rowB + ax + dx);
-            // no contraction, explicit fma: kernels/marching.cl:133
-            const float inv = __fdiv_rn(1.0f, __fsub_rn(isoA, isoB));
-            const float t = __fmul_rn(isoA, inv);
-            const float px = __fmaf_rn(t, (float) dx, (float) (ax + P.gridOffset.x));
-            const float py = __fmaf_rn(t, (float) dy, fy);
-            const float pz = __fmaf_rn(t, (float) dz, fz);
-            const bool flagged = (fm >> bit) & 1;
-            const uint32_t rank = flagged ? rankF++ : rankU++;
-            float *const out = (flagged ? P.weldedFlagged : P.welded) + 3 * (size_t) rank;
-            out[0] = __fmaf_rn(px, P.scale, P.bx);
-            out[1] = __fmaf_rn(py, P.scale, P.by);
-            out[2] = __fmaf_rn(pz, P.scale, P.bz);
-            if (flagged || topPlane)
-                (flagged ? P.weldedKeysFlagged : P.weldedKeys)[rank] =
-                    ((uint64_t) x2 | ((uint64_t) y2 << kKeyAxisBits) | ((uint64_t) (z2 + 2 * P.zFirst) << (2 * kKeyAxisBits))) + P.keyOffset;
+            const uint32_t l = threadIdx.x * kLatItems + i;
+            sMask[l] = m[i];
+            sCount[l] = c;
+            sRankU[l] = rankU;
+            sRankF[l] = rankF;
+            if (m[i])
+            {
+                P.prefix[base + i] = make_uint2(rankU, rankF);
+                const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
+                const uint32_t f = __popc(m[i] & fm), u = __popc(m[i]) - f;
+                c += u + f;
+                rankU += u;
+                rankF += f;
+            }
         }
+    }
+    __syncthreads();
+    const uint32_t tileBase = tile * (kLatThreads * kLatItems);
+    for (uint32_t j = threadIdx.x; j < tileVerts; j += kLatThreads)
+    {
+        // last word whose exclusive count is <= j (empty words share the count of their successor)
+        uint32_t lo = 0, hi = kLatThreads * kLatItems;
+        while (hi - lo > 1)
+        {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sCount[mid] <= j) lo = mid; else hi = mid;
+        }
+        const uint32_t bits = sMask[lo];
+        uint32_t rest = bits;
+        for (uint32_t k = j - sCount[lo]; k > 0; k--) rest &= rest - 1;   // drop the k lowest set bits
+        const uint32_t bit = __ffs(rest) - 1;
+        const uint32_t word = tileBase + lo;
+        const uint32_t row = word / P.stride, wc = word % P.stride;
+        const uint32_t vy2 = row % P.rows, vz2 = row / P.rows;
+        const uint32_t fm = latticeFlagMask(wc, vy2, vz2, P.topX, P.topY);
+        const uint32_t below = (1u << bit) - 1;
+        const bool flagged = (fm >> bit) & 1;
+        const uint32_t rank = flagged ? sRankF[lo] + __popc(bits & fm & below) : sRankU[lo] + __popc(bits & ~fm & below);
+        const uint32_t x2 = wc * 32 + bit, ax = x2 >> 1, dx = x2 & 1;
+        const uint32_t ay = vy2 >> 1, dy = vy2 & 1, az = P.zFirst + (vz2 >> 1), dz = vz2 & 1;
+        const float isoA = __ldg(P.field + ((size_t) az * P.zStride + ay) * P.pitch + ax);
+        const float isoB = __ldg(P.field + ((size_t) (az + dz) * P.zStride + ay + dy) * P.pitch + ax + dx);
+        // no contraction, explicit fma: kernels/marching.cl:133
+        const float inv = __fdiv_rn(1.0f, __fsub_rn(isoA, isoB));
+        const float t = __fmul_rn(isoA, inv);
+        const float px = __fmaf_rn(t, (float) dx, (float) (ax + P.gridOffset.x));
+        const float py = __fmaf_rn(t, (float) dy, (float) (ay + P.gridOffset.y));
+        const float pz = __fmaf_rn(t, (float) dz, (float) (az + P.gridOffset.z));
+        float *const out = (flagged ? P.weldedFlagged : P.welded) + 3 * (size_t) rank;
+        out[0] = __fmaf_rn(px, P.scale, P.bx);
+        out[1] = __fmaf_rn(py, P.scale, P.by);
+        out[2] = __fmaf_rn(pz, P.scale, P.bz);
+        if (flagged || vz2 == P.planes - 1)
+            (flagged ? P.weldedKeysFlagged : P.weldedKeys)[rank] =
+                ((uint64_t) x2 | ((uint64_t) vy2 << kKeyAxisBits) | ((uint64_t) (vz2 + 2 * P.zFirst) << (2 * kKeyAxisBits))) + P.keyOffset;
     }
 }
 

@@ -323,7 +323,9 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
                         w = __fmul_rn(w, w);
                         w = __fmul_rn(w, nq.w);
                         w = hit[j] ? w : 0.0f;
-                        const float ppj = hit[j] ? pp[j] : 0.0f;
+                        // (pp needs no such guard: w = 0 times a finite pp adds nothing, and pp is
+                        // finite for every position a 2^20-cell grid can hold)
+                        const float ppj = pp[j];
                         Accum &a = acc[j];
                         a.sumW = __fadd_rn(a.sumW, w);
                         a.sumWpx = __fmaf_rn(w, px[j], a.sumWpx);
@@ -334,7 +336,10 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
                         a.sumWnz = __fmaf_rn(w, nq.z, a.sumWnz);
                         a.sumWpp = __fmaf_rn(w, ppj, a.sumWpp);
                         a.sumWpn = __fmaf_rn(w, __fmaf_rn(nq.x, px[j], u), a.sumWpn);
-                        a.hits += hit[j];
+                        // one predicated add (left to itself the compiler builds hits + 1, a
+                        // predicated copy back and a move for one of the two slots)
+                        asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}"
+                            : "+r"(a.hits) : "f"(pp[j]), "f"(s.w));
                     }
                 }
 #else

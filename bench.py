@@ -368,11 +368,12 @@ def main():
     mls_s, mls_n = runner.stat_sum([MLS_STAT])
     clocks = sampler.stop()
 
-    # ---- per-stage breakdown (untimed pass with every kernel timed) ----
+    # ---- per-stage breakdown: an untimed pass of the lone worker with every kernel timed, so that
+    # the stage times are kernel times and not inflated by other workers' kernels on the same SMs ----
     for w in runner.all_workers():
         w.set_profiling(2)
         w.reset_statistics()
-    runner.step(False)
+    runner.step(False, single=True)
     runner.sync()
     oct_s, _ = runner.stat_sum(OCTREE_STATS)
     mar_s, _ = runner.stat_sum(MARCHING_STATS)
@@ -395,7 +396,7 @@ def main():
     # DRAM bytes per processCorners launch from the committed ncu --set full capture (profiles/)
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1b_processCorners_ncu.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1c_processCorners_ncu.json")) as f:
             traffic = json.load(f)["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         pass
@@ -410,7 +411,7 @@ def main():
         "mls_corners_per_s": corners * args.steps / mls_s if mls_s > 0 else None,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_note": "DRAM bytes per launch on a large bin, ncu --set full "
-                     "(profiles/r1b_processCorners_ncu.json); the kernel is FP32-issue-bound, not HBM-bound",
+                     "(profiles/r1c_processCorners_ncu.json); the kernel is FP32-issue-bound, not HBM-bound",
                      "kernel": "processCornersKernel",
                      "model": "7*T + 16*H FP32 pipe instructions per step (SURVEY 8d), 2 flop each",
                      "pair_tests": int(T), "hits": int(H), "kernel_ms_per_step": 1e3 * mls_per_step,
@@ -422,10 +423,15 @@ def main():
                      "peak_source": "measured here: dependent-free FFMA stream, %.2f T lane-inst/s "
                                     "(MEASURED_PEAKS.json has no FP32 figure)" % (peak_inst / 1e12)},
         "stages_ms_per_step": {"octree": 1e3 * oct_s, "mls": 1e3 * mls2_s, "marching": 1e3 * mar_s,
-                               "wall": wall_dev / args.steps},
+                               "wall": wall_dev / args.steps,
+                               "note": "kernel times of one worker running alone (CUDA events around every launch); "
+                                       "wall = the timed step of the worker group"},
         "rooflines_hbm": {
             "octree": {"model_bytes": 472 * inst_bytes, "achieved_gbs": 472 * inst_bytes / oct_s / 1e9 if oct_s else None,
-                       "peak_gbs": 6541.1, "note": "472 B/splat model of SURVEY 8d, measured copy peak"}},
+                       "peak_gbs": 6541.1,
+                       "note": "472 B/splat model of SURVEY 8d against the measured copy peak; C2's bins hold ~150 k splats, "
+                               "so the stage's 11 launches per bin are latency-bound (tools/bench_stages.py: 45 % of the "
+                               "peak on a 2 M-splat bin)"}},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, done, ns, dt = cpu_baseline(wl)

@@ -37,6 +37,7 @@ struct Bin
 {
     std::int32_t offset[3];
     std::uint32_t size[3];              // corners per axis
+    std::uint32_t chunk[3] = {0, 0, 0}; // output chunk the bin belongs to (--split; ChunkId::coords, src/chunk_id.h)
     std::vector<std::uint32_t> ids;     // ascending indices into the grid-space splat array
 };
 
@@ -92,7 +93,7 @@ namespace detail
 {
 inline void split(const std::vector<mlsb_splat> &splats, const std::int64_t lo[3], const std::int64_t hi[3],
                   const std::vector<std::uint32_t> &candidates, std::int64_t maxCells, std::size_t maxSplats,
-                  std::vector<Bin> &bins)
+                  const std::uint32_t chunk[3], std::vector<Bin> &bins)
 {
     std::vector<std::uint32_t> ids;
     for (std::uint32_t id : candidates)
@@ -113,6 +114,7 @@ inline void split(const std::vector<mlsb_splat> &splats, const std::int64_t lo[3
         {
             b.offset[a] = (std::int32_t) lo[a];
             b.size[a] = (std::uint32_t) (ext[a] + 1);
+            b.chunk[a] = chunk[a];
         }
         b.ids.swap(ids);
         bins.push_back(std::move(b));
@@ -121,21 +123,37 @@ inline void split(const std::vector<mlsb_splat> &splats, const std::int64_t lo[3
     if (ext[axis] <= 1) throw std::runtime_error("too many splats over a single cell (DensityError upstream)");
     std::int64_t hi0[3] = {hi[0], hi[1], hi[2]}, lo1[3] = {lo[0], lo[1], lo[2]};
     hi0[axis] = lo1[axis] = lo[axis] + ext[axis] / 2;
-    split(splats, lo, hi0, ids, maxCells, maxSplats, bins);
-    split(splats, lo1, hi, ids, maxCells, maxSplats, bins);
+    split(splats, lo, hi0, ids, maxCells, maxSplats, chunk, bins);
+    split(splats, lo1, hi, ids, maxCells, maxSplats, chunk, bins);
 }
 }  // namespace detail
 
 /// splats: grid coordinates (after worldToGrid).  Bins come out in z-major block order.
-inline std::vector<Bin> makeBins(const std::vector<mlsb_splat> &splats, const Grid &g, std::int64_t maxCells, std::size_t maxSplats)
+/// chunkCells > 0 (--split): the grid is first cut into output chunks of that many cells per side,
+/// counted from the grid's low corner, and no bin crosses a chunk boundary (Bucket::bucket's
+/// chunkCells, src/bucket.h); every bin records its chunk.
+inline std::vector<Bin> makeBins(const std::vector<mlsb_splat> &splats, const Grid &g, std::int64_t maxCells, std::size_t maxSplats,
+                                 std::int64_t chunkCells = 0)
 {
     std::int64_t n[3], counts[3];
-    std::vector<float> edges[3];   // block b of axis a spans cells [edges[a][b], edges[a][b + 1]]
+    std::vector<float> edges[3];             // block b of axis a spans cells [edges[a][b], edges[a][b + 1]]
+    std::vector<std::uint32_t> chunkOf[3];   // chunk coordinate of block b
     for (int a = 0; a < 3; a++)
     {
         n[a] = std::max<std::int64_t>(g.numCells(a), 1);
-        counts[a] = (n[a] + maxCells - 1) / maxCells;
-        for (std::int64_t b = 0; b <= counts[a]; b++) edges[a].push_back((float) (b * n[a] / counts[a]));
+        const std::int64_t chunkLen = chunkCells > 0 ? chunkCells : n[a];
+        for (std::int64_t c0 = 0, chunk = 0; c0 < n[a]; c0 += chunkLen, chunk++)
+        {
+            // a chunk is cut into equal blocks of at most maxCells cells
+            const std::int64_t len = std::min(chunkLen, n[a] - c0), parts = (len + maxCells - 1) / maxCells;
+            for (std::int64_t b = 0; b < parts; b++)
+            {
+                edges[a].push_back((float) (c0 + b * len / parts));
+                chunkOf[a].push_back((std::uint32_t) chunk);
+            }
+        }
+        edges[a].push_back((float) n[a]);
+        counts[a] = (std::int64_t) chunkOf[a].size();
     }
     const std::size_t numBlocks = (std::size_t) (counts[0] * counts[1] * counts[2]);
     const std::int64_t numSplats = (std::int64_t) splats.size();
@@ -143,12 +161,11 @@ inline std::vector<Bin> makeBins(const std::vector<mlsb_splat> &splats, const Gr
     // The blocks a splat's ball reaches, per axis (the same closed-interval test as detail::split).
     auto range = [&](const mlsb_splat &s, int a, std::int64_t &first, std::int64_t &last) {
         const float l = s.position[a] - s.radius, h = s.position[a] + s.radius;
-        const float scale = (float) counts[a] / (float) n[a];
-        first = std::min(std::max<std::int64_t>((std::int64_t) std::floor(l * scale) - 1, 0), counts[a] - 1);
-        last = std::min(std::max<std::int64_t>((std::int64_t) std::floor(h * scale) + 1, 0), counts[a] - 1);
-        while (first < last && !(h >= edges[a][first] && l <= edges[a][first + 1])) first++;
-        while (last > first && !(h >= edges[a][last] && l <= edges[a][last + 1])) last--;
-        return h >= edges[a][first] && l <= edges[a][first + 1];
+        const std::vector<float> &e = edges[a];
+        // blocks b with h >= e[b] and l <= e[b + 1]
+        first = std::lower_bound(e.begin() + 1, e.end(), l) - (e.begin() + 1);      // first b with e[b + 1] >= l
+        last = (std::upper_bound(e.begin(), e.end() - 1, h) - e.begin()) - 1;      // last b with e[b] <= h
+        return first <= last && first < counts[a] && last >= 0;
     };
 
     // Two passes over the splats with the same static schedule: count per (thread, block), then
@@ -210,6 +227,7 @@ inline std::vector<Bin> makeBins(const std::vector<mlsb_splat> &splats, const Gr
         const std::int64_t bx = bi % counts[0], by = (bi / counts[0]) % counts[1], bz = bi / (counts[0] * counts[1]);
         const std::int64_t lo[3] = {(std::int64_t) edges[0][bx], (std::int64_t) edges[1][by], (std::int64_t) edges[2][bz]};
         const std::int64_t hi[3] = {(std::int64_t) edges[0][bx + 1], (std::int64_t) edges[1][by + 1], (std::int64_t) edges[2][bz + 1]};
+        const std::uint32_t chunk[3] = {chunkOf[0][(std::size_t) bx], chunkOf[1][(std::size_t) by], chunkOf[2][(std::size_t) bz]};
         if (ids.size() <= maxSplats)   // the block's extent is within maxCells by construction
         {
             Bin b;
@@ -217,12 +235,13 @@ inline std::vector<Bin> makeBins(const std::vector<mlsb_splat> &splats, const Gr
             {
                 b.offset[a] = (std::int32_t) lo[a];
                 b.size[a] = (std::uint32_t) (hi[a] - lo[a] + 1);
+                b.chunk[a] = chunk[a];
             }
             b.ids.swap(ids);
             perBlock[(std::size_t) bi].push_back(std::move(b));
         }
         else
-            detail::split(splats, lo, hi, ids, maxCells, maxSplats, perBlock[(std::size_t) bi]);
+            detail::split(splats, lo, hi, ids, maxCells, maxSplats, chunk, perBlock[(std::size_t) bi]);
     }
     std::vector<Bin> bins;
     for (std::vector<Bin> &v : perBlock)

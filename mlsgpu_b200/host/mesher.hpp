@@ -10,15 +10,22 @@
 //  * at write time components (root clumps) with fewer than floor(fit-prune x total vertices)
 //    vertices are dropped and the rest are compacted (getStatistics :491-513, write :763-852).
 // The reference streams blocks through temporary files to bound memory; this version keeps the
-// mesh in host memory, one chunk per block, and only the seam bookkeeping (external vertices) is
+// mesh in host memory, one piece per block, and only the seam bookkeeping (external vertices) is
 // serialised: the per-block work runs concurrently on the device workers' threads.
+//
+// --split (src/mesher.h:169-179, testChunk in test/test_mesher.cpp:924-993): every block belongs
+// to an output chunk; vertices are welded within a chunk only (a vertex on a chunk boundary is
+// written to both files), while components — and therefore pruning — are global.
 #ifndef MLSB200_MESHER_HPP
 #define MLSB200_MESHER_HPP
 
 #include <algorithm>
 #include <array>
 #include <cstdint>
+#include <cstdio>
+#include <map>
 #include <memory>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -32,6 +39,10 @@ class Mesher
 public:
     typedef std::array<float, 3> vertex_type;
     typedef std::array<std::uint32_t, 3> triangle_type;
+    typedef std::array<std::uint32_t, 3> chunk_type;   // ChunkId::coords
+
+    /// split = true: blocks of different chunks share components but not vertices.
+    explicit Mesher(bool split = false) : split(split) {}
 
     /// One shipped-out block (HostKeyMesh layout, src/mesh.cpp:51-60) on its way into the mesh.
     /// The blob pointers are only used by prepare/commit/complete, i.e. inside the sink call.
@@ -46,8 +57,9 @@ public:
         std::vector<std::uint32_t> remapExternal;    // global index of every external vertex of the blob
 
         // what the mesher keeps: the block's internal vertices followed by the external vertices it
-        // was the first to see, numbered firstVertex.. in the welded mesh; its triangles in welded
-        // numbering; the (global) clump of every kept vertex is firstClump + vertexClump[i]
+        // was the first of its chunk to see, numbered firstVertex.. in the chunk's welded mesh; its
+        // triangles in welded numbering; the (global) clump of every kept vertex is
+        // firstClump + vertexClump[i]
         std::uint32_t firstVertex = 0, firstClump = 0;
         std::vector<vertex_type> vertices;
         std::vector<std::uint32_t> vertexClump;
@@ -100,36 +112,56 @@ public:
 
     /// Step 2, serialised by the caller: numbers the block's vertices and clumps and resolves its
     /// external vertices through the key map.  The mesher takes ownership of the block.
-    Block &commit(std::unique_ptr<Block> block)
+    Block &commit(std::unique_ptr<Block> block, const chunk_type &chunkId = chunk_type{{0, 0, 0}})
     {
         Block &b = *block;
         const std::size_t nv = b.nv, ni = b.ni;
+        auto found = chunkIndex.find(chunkId);
+        if (found == chunkIndex.end())
+        {
+            found = chunkIndex.insert(std::make_pair(chunkId, chunks.size())).first;
+            chunks.emplace_back(new Chunk);
+            chunks.back()->id = chunkId;
+        }
+        Chunk &chunk = *chunks[found->second];
         b.firstClump = (std::uint32_t) clumps.size();
         for (std::size_t c = 0; c < b.clumpVertices.size(); c++)
             clumps.push_back(Clump{b.firstClump + (std::uint32_t) c, b.clumpVertices[c]});
-        b.firstVertex = (std::uint32_t) totalVertices;
+        b.firstVertex = (std::uint32_t) chunk.totalVertices;
         b.remapExternal.resize(nv - ni);
         for (std::size_t i = ni; i < nv; i++)
         {
             const std::uint32_t clump = b.firstClump + b.clumpOfLocal[i];
+            const std::uint64_t key = b.keys[i - ni];
             const Seen fresh = {b.firstVertex + (std::uint32_t) b.vertices.size(), clump};
-            auto added = keyMap.insert(std::make_pair(b.keys[i - ni], fresh));
+            auto added = chunk.keyMap.insert(std::make_pair(key, fresh));
+            std::uint32_t earlierClump = added.first->second.clump;
+            bool seenBefore = !added.second;
             if (added.second)
             {
                 b.vertices.push_back(b.verts[i]);
                 b.vertexClump.push_back(b.clumpOfLocal[i]);
+                if (split)
+                {
+                    // new to this chunk's file, but another chunk may hold the same vertex
+                    auto global = globalKeyClump.insert(std::make_pair(key, clump));
+                    seenBefore = !global.second;
+                    earlierClump = global.first->second;
+                }
             }
-            else
+            if (seenBefore)
             {
                 // the same vertex seen from two blocks: unify their clumps, count it once
-                const std::uint32_t root = mergeClumps(clump, added.first->second.clump);
+                const std::uint32_t root = mergeClumps(clump, earlierClump);
                 clumps[root].vertices--;
             }
             b.remapExternal[i - ni] = added.first->second.vertex;
         }
+        chunk.totalVertices += b.vertices.size();
+        chunk.totalTriangles += b.nt;
         totalVertices += b.vertices.size();
         totalTriangles += b.nt;
-        blocks.push_back(std::move(block));
+        chunk.blocks.push_back(std::move(block));
         return b;
     }
 
@@ -157,9 +189,11 @@ public:
     std::size_t numVertices() const { return totalVertices; }
     std::size_t numTriangles() const { return totalTriangles; }
 
-    /// The welded mesh in chunks (one per block); vertex indices run across the chunks in order.
+    /// One output file: the welded mesh of a chunk in pieces (one per block); vertex indices run
+    /// across the pieces in order.  The component counts describe the whole mesh, not the chunk.
     struct Result
     {
+        chunk_type chunk = chunk_type{{0, 0, 0}};
         std::vector<std::vector<vertex_type>> vertexChunks;
         std::vector<std::vector<triangle_type>> triangleChunks;
         std::size_t numVertices = 0, numTriangles = 0;
@@ -167,10 +201,59 @@ public:
         std::uint64_t thresholdVertices = 0;
     };
 
-    /// Prune and compact.  pruneThreshold = --fit-prune (fraction of all welded vertices).
+    /// Prune and compact; one Result for the whole mesh (no --split).
     Result finish(double pruneThreshold)
     {
-        Result r;
+        std::vector<Result> all = finishChunks(pruneThreshold);
+        if (all.empty())
+        {
+            Result r;
+            countComponents(pruneThreshold, r, nullptr);
+            return r;
+        }
+        return std::move(all[0]);
+    }
+
+    /// Prune and compact, one Result per chunk in chunk order.  pruneThreshold = --fit-prune
+    /// (fraction of all welded vertices, counted over the whole mesh).
+    std::vector<Result> finishChunks(double pruneThreshold)
+    {
+        Result counts;
+        std::vector<char> keepClump;
+        countComponents(pruneThreshold, counts, &keepClump);
+        std::vector<Result> out;
+        for (const auto &entry : chunkIndex)   // std::map: sorted by chunk coordinates
+        {
+            Result r = counts;
+            r.chunk = entry.first;
+            finishChunk(*chunks[entry.second], keepClump, r);
+            out.push_back(std::move(r));
+        }
+        return out;
+    }
+
+private:
+    struct Clump
+    {
+        std::uint32_t parent;
+        std::uint64_t vertices;
+    };
+    struct Seen
+    {
+        std::uint32_t vertex;   // welded index of an external vertex within its chunk
+        std::uint32_t clump;    // the clump it belonged to where it was first seen
+    };
+    struct Chunk
+    {
+        chunk_type id;
+        std::unordered_map<std::uint64_t, Seen> keyMap;
+        std::vector<std::unique_ptr<Block>> blocks;
+        std::size_t totalVertices = 0, totalTriangles = 0;
+    };
+
+    /// getStatistics, src/mesher.cpp:491-513.  keepClump (optional): every clump's verdict.
+    void countComponents(double pruneThreshold, Result &r, std::vector<char> *keepClump)
+    {
         std::uint64_t total = 0;
         for (std::size_t c = 0; c < clumps.size(); c++)
             if (clumps[c].parent == c) total += clumps[c].vertices;
@@ -183,12 +266,23 @@ public:
                 keep[c] = clumps[c].vertices >= r.thresholdVertices;
                 r.keptComponents += keep[c];
             }
+        if (keepClump && r.keptComponents != r.totalComponents)
+        {
+            keepClump->resize(clumps.size());
+            for (std::size_t c = 0; c < clumps.size(); c++) (*keepClump)[c] = keep[findClump((std::uint32_t) c)];
+        }
+    }
+
+    void finishChunk(Chunk &chunk, const std::vector<char> &keepClump, Result &r)
+    {
+        std::vector<std::unique_ptr<Block>> &blocks = chunk.blocks;
+        const std::size_t totalVertices = chunk.totalVertices, totalTriangles = chunk.totalTriangles;
         const std::int64_t numBlocks = (std::int64_t) blocks.size();
         r.vertexChunks.resize(blocks.size());
         r.triangleChunks.resize(blocks.size());
         if (r.keptComponents == r.totalComponents)
         {
-            // nothing to prune: hand the chunks over as they are
+            // nothing to prune: hand the pieces over as they are
             for (std::int64_t i = 0; i < numBlocks; i++)
             {
                 r.vertexChunks[i].swap(blocks[i]->vertices);
@@ -196,11 +290,8 @@ public:
             }
             r.numVertices = totalVertices;
             r.numTriangles = totalTriangles;
-            return r;
+            return;
         }
-        // every clump's verdict, so that the per-block passes below only read
-        std::vector<char> keepClump(clumps.size());
-        for (std::size_t c = 0; c < clumps.size(); c++) keepClump[c] = keep[findClump((std::uint32_t) c)];
         // pass 1: kept vertices per block; prefix; pass 2: new numbering; pass 3: triangles
         std::vector<std::size_t> firstKept(blocks.size() + 1, 0);
 #pragma omp parallel for schedule(dynamic, 1)
@@ -239,20 +330,7 @@ public:
         }
         r.numVertices = firstKept[blocks.size()];
         for (const std::vector<triangle_type> &c : r.triangleChunks) r.numTriangles += c.size();
-        return r;
     }
-
-private:
-    struct Clump
-    {
-        std::uint32_t parent;
-        std::uint64_t vertices;
-    };
-    struct Seen
-    {
-        std::uint32_t vertex;   // welded index of an external vertex
-        std::uint32_t clump;    // the clump it belonged to where it was first seen
-    };
 
     static std::int32_t findLocal(std::vector<std::int32_t> &local, std::int32_t x)
     {
@@ -288,11 +366,21 @@ private:
         return lo;
     }
 
-    std::vector<std::unique_ptr<Block>> blocks;
+    bool split;
+    std::map<chunk_type, std::size_t> chunkIndex;
+    std::vector<std::unique_ptr<Chunk>> chunks;
     std::vector<Clump> clumps;
-    std::unordered_map<std::uint64_t, Seen> keyMap;
+    std::unordered_map<std::uint64_t, std::uint32_t> globalKeyClump;   // split only: key -> clump where first seen
     std::size_t totalVertices = 0, totalTriangles = 0;
 };
+
+/// ChunkNamer (src/mesher.cpp:88-96): base_XXXX_YYYY_ZZZZ.ply, at least four digits per coordinate.
+inline std::string chunkName(const std::string &baseName, const Mesher::chunk_type &chunk)
+{
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), "_%04u_%04u_%04u.ply", chunk[0], chunk[1], chunk[2]);
+    return baseName + buf;
+}
 
 }  // namespace mlsb
 

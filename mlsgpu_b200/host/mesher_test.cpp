@@ -2,6 +2,10 @@
 //   mesher_test blocks.bin prune out.ply [threads]
 // With threads > 1 the blocks go through Mesher::prepare / commit / complete from that many threads,
 // the way the device workers' sink drives it in mlsgpu.cpp.
+// If blocks.bin continues after the last block with uint32 x 3 chunk coordinates per block, the
+// mesher runs in --split mode and out.ply is the base name of the chunk files
+// (base_XXXX_YYYY_ZZZZ.ply, ChunkNamer, src/mesher.cpp:88-96); one line per written file follows
+// the summary line.
 // blocks.bin: uint64 numBlocks, then per block uint64 nv, nt, ni followed by the HostKeyMesh blob
 // ([keys of external vertices][float3 vertices][uint32x3 triangles]).
 #include <cstdio>
@@ -35,9 +39,13 @@ int main(int argc, char **argv)
         const std::size_t bytes = 8 * (h[0] - h[2]) + 12 * h[0] + 12 * h[1];
         if (bytes && std::fread(blobs[b].data(), 1, bytes, f) != bytes) return 2;
     }
+    std::vector<mlsb::Mesher::chunk_type> chunkIds(numBlocks, mlsb::Mesher::chunk_type{{0, 0, 0}});
+    const bool split = numBlocks > 0 && std::fread(chunkIds.data(), 12, numBlocks, f) == numBlocks;
     std::fclose(f);
+    if (split) mesher = mlsb::Mesher(true);
     if (threads <= 1)
-        for (std::uint64_t b = 0; b < numBlocks; b++) mesher.add(sizes[b], blobs[b].data());
+        for (std::uint64_t b = 0; b < numBlocks; b++)
+            mlsb::Mesher::complete(mesher.commit(mlsb::Mesher::prepare(sizes[b], blobs[b].data()), chunkIds[b]));
     else
     {
         std::mutex mutex;
@@ -50,18 +58,32 @@ int main(int argc, char **argv)
                     mlsb::Mesher::Block *block;
                     {
                         std::lock_guard<std::mutex> lock(mutex);
-                        block = &mesher.commit(std::move(prepared));
+                        block = &mesher.commit(std::move(prepared), chunkIds[b]);
                     }
                     mlsb::Mesher::complete(*block);
                 }
             });
         for (std::thread &t : pool) t.join();
     }
-    mlsb::Mesher::Result r = mesher.finish(std::atof(argv[2]));
     mlsb::PlyWriter writer;
     writer.addComment("mesher_test");
-    writer.write(argv[3], r.vertexChunks, r.triangleChunks);
-    std::cout << mesher.numVertices() << " " << mesher.numTriangles() << " " << r.totalComponents << " " << r.keptComponents
-              << " " << r.thresholdVertices << "\n";
+    if (!split)
+    {
+        mlsb::Mesher::Result r = mesher.finish(std::atof(argv[2]));
+        writer.write(argv[3], r.vertexChunks, r.triangleChunks);
+        std::cout << mesher.numVertices() << " " << mesher.numTriangles() << " " << r.totalComponents << " " << r.keptComponents
+                  << " " << r.thresholdVertices << "\n";
+        return 0;
+    }
+    std::vector<mlsb::Mesher::Result> all = mesher.finishChunks(std::atof(argv[2]));
+    std::cout << mesher.numVertices() << " " << mesher.numTriangles() << " " << (all.empty() ? 0 : all[0].totalComponents) << " "
+              << (all.empty() ? 0 : all[0].keptComponents) << " " << (all.empty() ? 0 : all[0].thresholdVertices) << "\n";
+    for (const mlsb::Mesher::Result &r : all)
+    {
+        if (r.numTriangles == 0) continue;   // only files with at least one triangle are written
+        const std::string name = mlsb::chunkName(argv[3], r.chunk);
+        writer.write(name, r.vertexChunks, r.triangleChunks);
+        std::cout << name << " " << r.numVertices << " " << r.numTriangles << "\n";
+    }
     return 0;
 }

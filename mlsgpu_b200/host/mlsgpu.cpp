@@ -9,16 +9,19 @@
 // MPI) are accepted and ignored so that existing command lines keep working.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <dirent.h>
+#include <fstream>
 #include <future>
 #include <iostream>
 #include <limits>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <sstream>
 #include <string>
 #include <sys/stat.h>
 #include <thread>
@@ -48,7 +51,9 @@ struct Options
     std::uint64_t memBucketSplats = 64ull << 20;   // bytes
     std::uint64_t memMesh = 512ull << 20;
     int device = 0;
-    bool quiet = false, statistics = false;
+    bool quiet = false, statistics = false, statisticsCL = false, split = false;
+    std::uint64_t splitSize = 100ull << 20;   // src/mlsgpu_core.cpp:162
+    std::string statisticsFile;
     std::string output;
     std::vector<std::string> inputs;
 };
@@ -73,7 +78,11 @@ void usage()
         "  --mem-bucket-splats SIZE    device memory for splats of one bin, K/M/G suffix (64M)\n"
         "  --mem-mesh SIZE             device memory for raw mesh data (512M)\n"
         "  --device N                  CUDA device ordinal (replaces --cl-device)\n"
-        "  --statistics                print statistics at the end\n";
+        "  --split                     split the output into a grid of files BASE_XXXX_YYYY_ZZZZ.ply (-o gives BASE)\n"
+        "  --split-size SIZE           approximate size of the output chunks (100M)\n"
+        "  --statistics                print statistics at the end\n"
+        "  --statistics-file FILE      direct statistics to FILE instead of stdout (implies --statistics)\n"
+        "  --statistics-cl             collect timings for the device kernels (kernel.*.time)\n";
 }
 
 // Capacity, src/options.cpp:38-69
@@ -94,11 +103,11 @@ Options parse(int argc, char **argv)
     Options o;
     // accepted for compatibility, value ignored
     static const std::map<std::string, bool> ignored = {
-        {"--response-file", true}, {"--tmp-dir", true}, {"--statistics-file", true}, {"--statistics-cl", false},
+        {"--response-file", true}, {"--tmp-dir", true},
         {"--timeplot", true}, {"--max-split", true}, {"--reader", true}, {"--writer", true}, {"--omp-threads", true},
         {"--decache", false}, {"--checkpoint", true}, {"--resume", true}, {"--mem-load-splats", true},
-        {"--mem-host-splats", true}, {"--mem-reorder", true}, {"--mem-gather", true}, {"--split", false},
-        {"--split-size", true}, {"--cl-device", true}, {"--cl-gpu", false}, {"--cl-cpu", false}, {"--debug", false}};
+        {"--mem-host-splats", true}, {"--mem-reorder", true}, {"--mem-gather", true},
+        {"--cl-device", true}, {"--cl-gpu", false}, {"--cl-cpu", false}, {"--debug", false}};
     for (int i = 1; i < argc; i++)
     {
         std::string a = argv[i], v;
@@ -132,6 +141,10 @@ Options parse(int argc, char **argv)
         else if (a == "--mem-mesh") o.memMesh = parseCapacity(value());
         else if (a == "--device") o.device = std::stoi(value());
         else if (a == "--statistics") o.statistics = true;
+        else if (a == "--statistics-file") { o.statisticsFile = value(); o.statistics = true; }
+        else if (a == "--statistics-cl") o.statisticsCL = true;
+        else if (a == "--split") o.split = true;
+        else if (a == "--split-size") o.splitSize = parseCapacity(value());
         else if (ignored.count(a)) { if (ignored.at(a)) (void) value(); }
         else if (a.rfind("-", 0) == 0) throw std::invalid_argument("unknown option " + a);
         else o.inputs.push_back(a);
@@ -185,7 +198,9 @@ double now()
 
 struct SinkState
 {
+    explicit SinkState(bool split) : mesher(split) {}
     mlsb::Mesher mesher;
+    const std::vector<mlsb::Bin> *bins = nullptr;   // the sink's tag is the bin's index: its chunk is looked up here
     std::mutex mutex;
     double prepareSeconds = 0.0;   // per-block work, concurrently on the worker threads (summed)
     double commitSeconds = 0.0;    // seam bookkeeping in the global mesh, serialised
@@ -193,9 +208,11 @@ struct SinkState
 
 // Called concurrently by the device workers (mlsb_group_set_concurrent_sink): the per-block part of
 // the mesher runs in parallel, only the merge into the global mesh takes the lock.
-void meshSink(std::uint64_t, const mlsb_mesh_sizes *sizes, const void *blob, void *user)
+void meshSink(std::uint64_t tag, const mlsb_mesh_sizes *sizes, const void *blob, void *user)
 {
     SinkState *st = static_cast<SinkState *>(user);
+    const mlsb::Bin &bin = (*st->bins)[(std::size_t) tag];
+    const mlsb::Mesher::chunk_type chunk = {{bin.chunk[0], bin.chunk[1], bin.chunk[2]}};
     const double t0 = now();
     std::unique_ptr<mlsb::Mesher::Block> prepared = mlsb::Mesher::prepare(*sizes, blob);
     const double t1 = now();
@@ -204,7 +221,7 @@ void meshSink(std::uint64_t, const mlsb_mesh_sizes *sizes, const void *blob, voi
     {
         std::lock_guard<std::mutex> lock(st->mutex);
         const double t2 = now();
-        block = &st->mesher.commit(std::move(prepared));
+        block = &st->mesher.commit(std::move(prepared), chunk);
         commit = now() - t2;
         st->commitSeconds += commit;
     }
@@ -238,7 +255,7 @@ int main(int argc, char **argv)
         cfg.meshBytes = std::max<std::uint64_t>(o.memMesh / (o.deviceThreads + 1), (std::uint64_t) maxCells * maxCells * 872);
         cfg.shape = o.fitShape == "plane" ? MLSB_SHAPE_PLANE : MLSB_SHAPE_SPHERE;
         cfg.boundaryLimit = (float) o.fitBoundaryLimit;
-        SinkState state;
+        SinkState state(o.split);
         struct Created
         {
             mlsb_group *group = nullptr;
@@ -288,7 +305,12 @@ int main(int argc, char **argv)
             if (grid.numCells(a) + 1 > (1 << 20) - 1)   // src/mlsgpu_core.cpp:623-629
                 throw std::runtime_error("The bounding box is too big. Perhaps you have used the wrong units for --fit-grid.");
         mlsb::worldToGrid(splats, grid);
-        std::vector<mlsb::Bin> bins = mlsb::makeBins(splats, grid, maxCells, maxBucketSplats);
+        // --split: chunks of about --split-size bytes, assuming a surface cuts a chunk of x cells per
+        // side in ~20 x^2 vertices of 38 bytes each (src/mlsgpu_core.cpp:635-652)
+        std::int64_t chunkCells = 0;
+        if (o.split) chunkCells = std::max<std::int64_t>(1, (std::int64_t) std::ceil(std::sqrt(o.splitSize / 760.0)));
+        const std::vector<mlsb::Bin> bins = mlsb::makeBins(splats, grid, maxCells, maxBucketSplats, chunkCells);
+        state.bins = &bins;
         const double tBucket = now();
 
         // ---- device pipeline ----
@@ -304,6 +326,7 @@ int main(int argc, char **argv)
             mlsb_worker *w = nullptr;
             mlsb::check(mlsb_group_worker(group, (std::uint32_t) i, &w));
             mlsb::check(mlsb_set_scale_bias(w, grid.spacing, origin));   // ScaleBiasFilter::setScaleBias(grid)
+            if (o.statisticsCL) mlsb::check(mlsb_worker_set_profiling(w, 2));   // src/mlsgpu_core.cpp:225-228
         }
         const double tCreateWait = now() - tCreate0;   // the part of the creation that was not hidden
         double tGather = 0.0;
@@ -337,7 +360,6 @@ int main(int argc, char **argv)
         const double tDevice = now();
 
         // ---- mesher: prune, write (OOCMesher::write) ----
-        mlsb::Mesher::Result mesh = state.mesher.finish(o.fitPrune);
         mlsb::PlyWriter writer;
         {
             // options are echoed as comments, src/mlsgpu_core.cpp:680-685
@@ -346,23 +368,92 @@ int main(int argc, char **argv)
                           o.fitSmooth, o.fitGrid, o.fitPrune, o.fitBoundaryLimit, o.fitShape.c_str(), o.levels, o.subsampling);
             writer.addComment(buf);
         }
-        writer.write(o.output, mesh.vertexChunks, mesh.triangleChunks);
+        mlsb::Mesher::Result mesh;        // without --split: the mesh; with: the totals over the chunks
+        std::size_t outputFiles = 0;
+        if (!o.split)
+        {
+            mesh = state.mesher.finish(o.fitPrune);
+            writer.write(o.output, mesh.vertexChunks, mesh.triangleChunks);
+            outputFiles = 1;
+        }
+        else
+        {
+            // one file per chunk that holds at least one triangle, named by ChunkNamer (src/mesher.cpp:88-96)
+            std::vector<mlsb::Mesher::Result> chunks = state.mesher.finishChunks(o.fitPrune);
+            for (const mlsb::Mesher::Result &c : chunks)
+            {
+                mesh.totalComponents = c.totalComponents;
+                mesh.keptComponents = c.keptComponents;
+                mesh.numVertices += c.numVertices;
+                mesh.numTriangles += c.numTriangles;
+                if (c.numTriangles == 0) continue;
+                writer.write(mlsb::chunkName(o.output, c.chunk), c.vertexChunks, c.triangleChunks);
+                outputFiles++;
+            }
+        }
         const double tEnd = now();
 
         if (!o.quiet || o.statistics)
         {
-            std::cout << "files.splats: " << numSplats << "\n"
-                      << "bins: " << bins.size() << "\n"
-                      << "components.total: " << mesh.totalComponents << "\ncomponents.kept: " << mesh.keptComponents << "\n"
-                      << "output.vertices: " << mesh.numVertices << "\noutput.triangles: " << mesh.numTriangles << "\n";
-            std::printf("read.time: %.3f\nbucket.time: %.3f\ndevice.time: %.3f\nmesher.time: %.3f\nrun.time: %.3f\n",
-                        tRead - t0, tBucket - tRead, tDevice - tBucket, tEnd - tDevice, tEnd - t0);
-            std::printf("device.create.time: %.3f\ndevice.create.wait: %.3f\ndevice.gather.time: %.3f\n", created.seconds, tCreateWait, tGather);
-            std::printf("mesher.prepare.time: %.3f\nmesher.commit.time: %.3f\n", state.prepareSeconds, state.commitSeconds);
-            std::printf("splats/s end-to-end: %.3g\n", numSplats / (tEnd - t0));
+            // writeStatistics, src/mlsgpu_core.cpp:313-352: "name: value" lines, to --statistics-file if given
+            std::ostringstream out;
+            out << "mlsgpu version: " << mlsb_version() << "\n"
+                << "files.splats: " << numSplats << "\n"
+                << "bins: " << bins.size() << "\n"
+                << "components.total: " << mesh.totalComponents << "\ncomponents.kept: " << mesh.keptComponents << "\n"
+                << "output.vertices: " << mesh.numVertices << "\noutput.triangles: " << mesh.numTriangles << "\n"
+                << "output.files: " << outputFiles << "\n";
+            char buf[512];
+            std::snprintf(buf, sizeof(buf), "read.time: %.3f\nbucket.time: %.3f\ndevice.time: %.3f\nmesher.time: %.3f\nrun.time: %.3f\n",
+                          tRead - t0, tBucket - tRead, tDevice - tBucket, tEnd - tDevice, tEnd - t0);
+            out << buf;
+            std::snprintf(buf, sizeof(buf), "device.create.time: %.3f\ndevice.create.wait: %.3f\ndevice.gather.time: %.3f\n"
+                          "mesher.prepare.time: %.3f\nmesher.commit.time: %.3f\n",
+                          created.seconds, tCreateWait, tGather, state.prepareSeconds, state.commitSeconds);
+            out << buf;
+            if (o.statisticsCL)
+            {
+                // Statistics::Variable::write (src/statistics.cpp:175-182): "sum : mean [n]", summed over the workers
+                static const char *const names[] = {
+                    "kernel.octree.writeEntries.time", "kernel.octree.sort.time", "kernel.octree.fill.time",
+                    "kernel.octree.countCommands.time", "kernel.octree.scan.time", "kernel.octree.writeSplatIds.time",
+                    "kernel.octree.writeStart.time", "kernel.mls.processCorners.time", "kernel.marching.zero.time",
+                    "kernel.marching.genOccupied.time", "kernel.marching.scanElements.time",
+                    "kernel.marching.compactVertices.time", "kernel.marching.generateElements.time",
+                    "kernel.marching.readback.time"};
+                for (const char *name : names)
+                {
+                    double sum = 0.0;
+                    std::uint64_t count = 0;
+                    for (int i = 0; i < o.deviceThreads; i++)
+                    {
+                        mlsb_worker *w = nullptr;
+                        double s1 = 0.0;
+                        std::uint64_t c1 = 0;
+                        mlsb::check(mlsb_group_worker(group, (std::uint32_t) i, &w));
+                        mlsb::check(mlsb_worker_get_statistic(w, name, &s1, &c1));
+                        sum += s1;
+                        count += c1;
+                    }
+                    if (count == 0) continue;
+                    std::snprintf(buf, sizeof(buf), "%s: %.9g : %.9g [%llu]\n", name, sum, sum / (double) count, (unsigned long long) count);
+                    out << buf;
+                }
+            }
+            std::snprintf(buf, sizeof(buf), "splats/s end-to-end: %.3g\n", numSplats / (tEnd - t0));
+            out << buf;
             // the CUDA driver's start-up (no persistence daemon: the GPU is initialised per process)
             // is a fixed cost; this is the rate a long run converges to
-            std::printf("splats/s excluding device start-up: %.3g\n", numSplats / (tEnd - t0 - tCreateWait));
+            std::snprintf(buf, sizeof(buf), "splats/s excluding device start-up: %.3g\n", numSplats / (tEnd - t0 - tCreateWait));
+            out << buf;
+            if (!o.statisticsFile.empty())
+            {
+                std::ofstream file(o.statisticsFile.c_str());
+                file << out.str();
+                if (!file) throw std::runtime_error("Could not write statistics to " + o.statisticsFile);
+            }
+            else
+                std::cout << out.str();
         }
         return 0;
     }

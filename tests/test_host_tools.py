@@ -26,12 +26,15 @@ def tetra(offset, keys=None):
     return dict(vertices=v, triangles=t, keys=keys, num_internal=4 - len(keys))
 
 
-def write_blocks(path, blocks):
+def write_blocks(path, blocks, chunks=None):
+    """chunks: one (x, y, z) output chunk per block -> the harness runs the mesher in --split mode."""
     with open(path, "wb") as f:
         f.write(np.uint64(len(blocks)).tobytes())
         for b in blocks:
             f.write(np.array([len(b["vertices"]), len(b["triangles"]), b["num_internal"]], np.uint64).tobytes())
             f.write(b["keys"].tobytes() + b["vertices"].tobytes() + b["triangles"].tobytes())
+        if chunks is not None:
+            f.write(np.asarray(chunks, np.uint32).reshape(len(blocks), 3).tobytes())
 
 
 def test_mesher_welds_by_key_and_prunes(tmp_path):
@@ -127,6 +130,34 @@ def test_cli_end_to_end_sphere(tmp_path):
     keep = np.linalg.norm(pv, axis=1) < 1.3                      # drop the island, as --fit-prune did
     assert keep.sum() == len(verts) and keep[pt[:, 0]].sum() == len(tris)
 
+    # --split: a grid of chunk files that together hold exactly the same triangles (by position);
+    # vertices on chunk borders appear in both neighbours; the island is pruned globally
+    base = tmp_path / "split"
+    r = subprocess.run([exe, "-o", str(base), "--fit-grid", "0.025", "--levels", "3", "--fit-prune", "0.02",
+                        "--device-threads", "3", "--split", "--split-size", str(760 * 40 * 40), "--statistics", str(inp)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    stats = dict(line.split(": ", 1) for line in r.stdout.strip().splitlines() if ": " in line)
+    names = sorted(tmp_path.glob("split_*.ply"))
+    assert len(names) == int(stats["output.files"]) >= 8 and int(stats["components.kept"]) == 1
+    assert all(len(n.name) == len("split_0000_0000_0000.ply") for n in names)
+
+    def soup(v, t):
+        p = v[t]                                                  # (n, 3, 3) corner positions
+        first = np.lexsort((p[:, :, 2], p[:, :, 1], p[:, :, 0]), axis=1)[:, 0]      # rotate the smallest corner first
+        p = np.stack([np.roll(tri, -k, axis=0) for tri, k in zip(p, first)])
+        return np.unique(p.reshape(len(p), 9), axis=0)
+    parts, nverts = [], 0
+    for n in names:
+        v, t, _ = plyfile.read_mesh_ply(n)
+        assert len(t) > 0 and t.max() < len(v) and is_manifold(len(v), t) == ""
+        parts.append(soup(v, t))
+        nverts += len(v)
+    whole = soup(verts, tris)
+    np.testing.assert_array_equal(np.unique(np.concatenate(parts), axis=0), whole)
+    assert sum(len(p) for p in parts) == len(whole) == len(tris)          # no triangle twice
+    assert nverts > len(verts) and nverts == int(stats["output.vertices"])  # border vertices are duplicated
+
 
 @pytest.mark.gpu
 def test_cli_plane_fit_boundary_and_prune(tmp_path):
@@ -158,10 +189,17 @@ def test_cli_plane_fit_boundary_and_prune(tmp_path):
     both = np.concatenate([s] + islands)
     inp, out = tmp_path / "terrain.ply", tmp_path / "terrain_mesh.ply"
     plyfile.write_splat_ply(inp, both)
+    stats_file = tmp_path / "stats.txt"
     r = subprocess.run([exe, "-o", str(out), "--fit-grid", "0.02", "--fit-shape", "plane", "--fit-boundary-limit", "0.5",
-                        "--fit-prune", "0.02", "--levels", "4", "--statistics", str(inp)], capture_output=True, text=True)
+                        "--fit-prune", "0.02", "--levels", "4", "--statistics-file", str(stats_file), "--statistics-cl",
+                        str(inp)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    stats = dict(line.split(": ") for line in r.stdout.strip().splitlines() if ": " in line)
+    assert r.stdout == ""                                   # --statistics-file: nothing on stdout
+    stats = dict(line.split(": ", 1) for line in stats_file.read_text().strip().splitlines() if ": " in line)
+    # --statistics-cl: per-kernel device times under the reference's names, "sum : mean [n]"
+    total, mean, count = stats["kernel.mls.processCorners.time"].replace("[", "").replace("]", "").replace(" : ", " ").split()
+    assert float(total) > 0 and int(count) == int(stats["bins"]) and abs(float(total) / int(count) - float(mean)) < 1e-6
+    assert "kernel.octree.sort.time" in stats and "kernel.marching.generateElements.time" in stats
     # (with the tightened boundary limit the tiny islands may be rejected by the boundary test already)
     assert int(stats["components.total"]) >= 1 and int(stats["components.kept"]) == 1
     verts, tris, _ = plyfile.read_mesh_ply(out)
@@ -232,6 +270,68 @@ def test_mesher_reference_weld_fixture(tmp_path, threads):
                         9, 12, 11, 14, 6, 15, 15, 6, 13, 13, 6, 7]
     verts, tris = run_mesher(tmp_path, [b0, b1, b2, b3], 0.0, threads)
     check_isomorphic(expected_vertices, expected_indices, verts, tris)
+
+
+WELD_BLOCKS = [
+    blk([(0, 0, 1), (0, 0, 2), (0, 0, 3), (0, 0, 4), (0, 0, 5)], [], [], [0, 1, 3, 1, 2, 3, 3, 4, 0]),
+    blk([], [(1, 0, 1), (1, 0, 2), (1, 0, 3), (1, 0, 4)], [0, 0x8000000000000000, 1, 0x8000000000000001],
+        [0, 1, 3, 1, 2, 3, 2, 0, 3]),
+    blk([(0, 1, 0), (0, 2, 0), (0, 3, 0)], [(2, 0, 1), (2, 0, 2)], [0x1234567812345678, 0x12345678],
+        [0, 1, 3, 1, 4, 3, 2, 3, 4, 0, 2, 4, 0, 3, 2]),
+    blk([(3, 3, 3)], [(4, 5, 6), (1, 0, 2), (1, 0, 3), (2, 0, 2)], [100, 0x8000000000000000, 1, 0x12345678],
+        [0, 2, 1, 1, 2, 4, 4, 2, 3])]
+
+
+def run_split(tmp_path, blocks, chunks, prune, threads=1, base="chunk"):
+    exe = build("mesher_test")
+    write_blocks(tmp_path / "blocks.bin", blocks, chunks)
+    res = subprocess.run([exe, str(tmp_path / "blocks.bin"), repr(prune), str(tmp_path / base), str(threads)],
+                         check=True, capture_output=True, text=True)
+    lines = res.stdout.strip().splitlines()
+    files = {}
+    for line in lines[1:]:
+        name, nv, nt = line.rsplit(" ", 2)
+        verts, tris, _ = plyfile.read_mesh_ply(name)
+        assert len(verts) == int(nv) and len(tris) == int(nt)
+        files[os.path.basename(name)] = (verts, tris)
+    return [int(x) for x in lines[0].split()], files
+
+
+@THREADS
+def test_mesher_reference_chunk_fixture(tmp_path, threads):
+    """testChunk, test/test_mesher.cpp:924-993: the blocks of the weld fixture, each in a chunk of its
+    own: every file holds its block's vertices, external ones included (no welding across files)."""
+    chunks = [(i, i * i, 1) for i in range(4)]
+    _, files = run_split(tmp_path, WELD_BLOCKS, chunks, 0.0, threads)
+    assert sorted(files) == ["chunk_0000_0000_0001.ply", "chunk_0001_0001_0001.ply", "chunk_0002_0004_0001.ply",
+                             "chunk_0003_0009_0001.ply"]
+    for b, (x, y, z) in zip(WELD_BLOCKS, chunks):
+        verts, tris = files["chunk_%04d_%04d_%04d.ply" % (x, y, z)]
+        check_isomorphic(b["vertices"], b["triangles"].ravel(), verts, tris)
+
+
+def test_mesher_split_names_and_global_components(tmp_path):
+    """ChunkNamer (testSimple / testBig, test/test_mesher.cpp:101-122) and what --split keeps global:
+    components and pruning span the chunk files, vertices do not."""
+    # a chain of tetrahedra welded through keys, laid over three chunks, plus a small island in a fourth
+    chain = [tetra((3 * i, 0, 0), keys=[100 + i, 101 + i]) for i in range(12)]
+    island = tetra((-50, 0, 0))
+    chunks = [(0, 5, 3000)] * 4 + [(100, 123456, 2345678)] * 4 + [(1, 1, 1)] * 4 + [(7, 7, 7)]
+    for prune, kept in ((0.0, 2), (0.2, 1)):
+        (nv, nt, total, kept_components, threshold), files = run_split(tmp_path, chain + [island], chunks, prune, 2, base="foo")
+        # 4 tetrahedra per chunk share 3 keys inside the chunk; the keys on chunk borders stay in both files
+        assert nv == 3 * (16 - 3) + 4 and nt == 13 * 4
+        # ... but count once for the components: 12 * 4 - 11 chained vertices + 4
+        assert total == 2 and kept_components == kept and threshold == int((12 * 4 - 11 + 4) * prune)
+        expected = ["foo_0000_0005_3000.ply", "foo_0001_0001_0001.ply", "foo_0100_123456_2345678.ply"]
+        if kept == 2:
+            expected.append("foo_0007_0007_0007.ply")       # the island's file exists only if it survives
+        assert sorted(files) == sorted(expected)
+        for name in expected[:3]:
+            verts, tris = files[name]
+            assert len(verts) == 13 and len(tris) == 16 and tris.max() < len(verts)
+        for f in tmp_path.glob("foo_*.ply"):
+            f.unlink()
 
 
 @THREADS

@@ -170,10 +170,7 @@ struct GenParams
     const float *field;
     uint32_t pitch, zStride;
     uint32_t cellsX, cellsY;       // W-1, H-1
-    uint32_t zFirst, zLast;        // cells between slices zFirst..zLast
-    uint32_t numCells;
-    uint3 gridOffset;              // keyOffset: local -> global grid coordinates
-    uint32_t vertexSpace, indexSpace;
+    uint32_t zFirst;               // first corner slice of the block: tile 0 holds the cells between zFirst and zFirst + 1
     uint32_t *indices;
     uint32_t *counters;
     // lattice of edge midpoints of this block: [2 * (zLast - zFirst) + 1][latRows][latStride] words,
@@ -758,7 +755,6 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     const uint64_t numCells64 = (uint64_t) cellsX * cellsY * (zLast - zFirst);
     if (numCells64 == 0) return MLSB_OK;
     MLSB_REQUIRE(numCells64 < (1ull << 32) - kGenThreads, MLSB_ERR_LENGTH, "too many cells");
-    const uint32_t numCells = (uint32_t) numCells64;
     const uint32_t tiles = (zLast - zFirst) * divUp(cellsY, (uint32_t) kGenRows);
     const uint32_t chunks = divUp(cellsX, (uint32_t) kGenThreads);
     MLSB_REQUIRE(chunks <= 2, MLSB_ERR_LENGTH, "bin too wide");
@@ -776,11 +772,6 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     G.cellsX = cellsX;
     G.cellsY = cellsY;
     G.zFirst = zFirst;
-    G.zLast = zLast;
-    G.numCells = numCells;
-    G.gridOffset = make_uint3(keyOffset[0], keyOffset[1], keyOffset[2]);
-    G.vertexSpace = (uint32_t) w->vertexSpace;
-    G.indexSpace = (uint32_t) w->indexSpace;
     G.indices = w->indices;
     G.counters = w->marchCounters;
     G.latMask = w->latMask;
@@ -808,7 +799,7 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     L.pitch = pitch;
     L.zStride = zStride;
     L.zFirst = zFirst;
-    L.gridOffset = G.gridOffset;
+    L.gridOffset = make_uint3(keyOffset[0], keyOffset[1], keyOffset[2]);
     L.welded = w->welded;
     L.weldedKeys = w->weldedKeys;
     L.weldedFlagged = w->weldedFlagged;

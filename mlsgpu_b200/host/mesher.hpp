@@ -23,8 +23,12 @@
 #include <array>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <istream>
 #include <map>
 #include <memory>
+#include <ostream>
+#include <stdexcept>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -188,6 +192,81 @@ public:
 
     std::size_t numVertices() const { return totalVertices; }
     std::size_t numTriangles() const { return totalTriangles; }
+    bool isSplit() const { return split; }
+
+    /// --checkpoint (OOCMesher::checkpoint, src/mesher.cpp:854-874): everything finish() needs —
+    /// clumps, and per chunk its blocks' vertices, clumps and triangles — so that pruning and writing
+    /// can run later, possibly with another --fit-prune.  Call after the last block has completed.
+    void save(std::ostream &out) const
+    {
+        out.write(checkpointMagic(), 8);
+        put<std::uint64_t>(out, split);
+        put<std::uint64_t>(out, totalVertices);
+        put<std::uint64_t>(out, totalTriangles);
+        put<std::uint64_t>(out, clumps.size());
+        for (const Clump &c : clumps)
+        {
+            put<std::uint64_t>(out, c.parent);
+            put<std::uint64_t>(out, c.vertices);
+        }
+        put<std::uint64_t>(out, chunks.size());
+        for (const auto &entry : chunkIndex)
+        {
+            const Chunk &chunk = *chunks[entry.second];
+            for (int a = 0; a < 3; a++) put<std::uint64_t>(out, chunk.id[a]);
+            put<std::uint64_t>(out, chunk.totalVertices);
+            put<std::uint64_t>(out, chunk.totalTriangles);
+            put<std::uint64_t>(out, chunk.blocks.size());
+            for (const std::unique_ptr<Block> &b : chunk.blocks)
+            {
+                put<std::uint64_t>(out, b->firstVertex);
+                put<std::uint64_t>(out, b->firstClump);
+                putVector(out, b->vertices);
+                putVector(out, b->vertexClump);
+                putVector(out, b->triangles);
+            }
+        }
+        if (!out) throw std::runtime_error("could not write the checkpoint");
+    }
+
+    /// --resume (OOCMesher::resume, src/mesher.cpp:876-898): replaces the state with a saved one.
+    void load(std::istream &in)
+    {
+        char magic[8];
+        in.read(magic, 8);
+        if (!in || std::memcmp(magic, checkpointMagic(), 8) != 0) throw std::runtime_error("not a mesher checkpoint");
+        *this = Mesher(get<std::uint64_t>(in) != 0);
+        totalVertices = (std::size_t) get<std::uint64_t>(in);
+        totalTriangles = (std::size_t) get<std::uint64_t>(in);
+        clumps.resize((std::size_t) get<std::uint64_t>(in));
+        for (Clump &c : clumps)
+        {
+            c.parent = (std::uint32_t) get<std::uint64_t>(in);
+            c.vertices = get<std::uint64_t>(in);
+        }
+        const std::uint64_t numChunks = get<std::uint64_t>(in);
+        for (std::uint64_t i = 0; i < numChunks; i++)
+        {
+            chunks.emplace_back(new Chunk);
+            Chunk &chunk = *chunks.back();
+            for (int a = 0; a < 3; a++) chunk.id[a] = (std::uint32_t) get<std::uint64_t>(in);
+            chunkIndex[chunk.id] = chunks.size() - 1;
+            chunk.totalVertices = (std::size_t) get<std::uint64_t>(in);
+            chunk.totalTriangles = (std::size_t) get<std::uint64_t>(in);
+            chunk.blocks.resize((std::size_t) get<std::uint64_t>(in));
+            for (std::unique_ptr<Block> &b : chunk.blocks)
+            {
+                b.reset(new Block);
+                b->firstVertex = (std::uint32_t) get<std::uint64_t>(in);
+                b->firstClump = (std::uint32_t) get<std::uint64_t>(in);
+                getVector(in, b->vertices);
+                getVector(in, b->vertexClump);
+                getVector(in, b->triangles);
+                b->nt = b->triangles.size();
+            }
+        }
+        if (!in) throw std::runtime_error("truncated mesher checkpoint");
+    }
 
     /// One output file: the welded mesh of a chunk in pieces (one per block); vertex indices run
     /// across the pieces in order.  The component counts describe the whole mesh, not the chunk.
@@ -233,6 +312,26 @@ public:
     }
 
 private:
+    static const char *checkpointMagic() { return "MLSBCKP1"; }
+    template <typename T> static void put(std::ostream &out, T value) { out.write(reinterpret_cast<const char *>(&value), sizeof(T)); }
+    template <typename T> static T get(std::istream &in)
+    {
+        T value = T();
+        in.read(reinterpret_cast<char *>(&value), sizeof(T));
+        if (!in) throw std::runtime_error("truncated mesher checkpoint");
+        return value;
+    }
+    template <typename T> static void putVector(std::ostream &out, const std::vector<T> &v)
+    {
+        put<std::uint64_t>(out, v.size());
+        if (!v.empty()) out.write(reinterpret_cast<const char *>(v.data()), (std::streamsize) (v.size() * sizeof(T)));
+    }
+    template <typename T> static void getVector(std::istream &in, std::vector<T> &v)
+    {
+        v.resize((std::size_t) get<std::uint64_t>(in));
+        if (!v.empty()) in.read(reinterpret_cast<char *>(v.data()), (std::streamsize) (v.size() * sizeof(T)));
+    }
+
     struct Clump
     {
         std::uint32_t parent;

@@ -1,5 +1,7 @@
 // Test harness for the host mesher and PLY writer (driven by tests/test_host_tools.py).
-//   mesher_test blocks.bin prune out.ply [threads]
+//   mesher_test blocks.bin prune out.ply [threads [checkpoint]]
+// With a checkpoint file name the mesher's state goes through Mesher::save and Mesher::load (into a
+// fresh object) before it is finished: --checkpoint / --resume.
 // With threads > 1 the blocks go through Mesher::prepare / commit / complete from that many threads,
 // the way the device workers' sink drives it in mlsgpu.cpp.
 // If blocks.bin continues after the last block with uint32 x 3 chunk coordinates per block, the
@@ -10,6 +12,7 @@
 // ([keys of external vertices][float3 vertices][uint32x3 triangles]).
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <iostream>
 #include <mutex>
 #include <thread>
@@ -21,8 +24,8 @@
 
 int main(int argc, char **argv)
 {
-    if (argc != 4 && argc != 5) return 2;
-    const int threads = argc == 5 ? std::atoi(argv[4]) : 1;
+    if (argc < 4 || argc > 6) return 2;
+    const int threads = argc >= 5 ? std::atoi(argv[4]) : 1;
     std::FILE *f = std::fopen(argv[1], "rb");
     if (!f) return 2;
     std::uint64_t numBlocks = 0;
@@ -64,6 +67,18 @@ int main(int argc, char **argv)
                 }
             });
         for (std::thread &t : pool) t.join();
+    }
+    if (argc == 6)
+    {
+        {
+            std::ofstream out(argv[5], std::ios::binary);
+            mesher.save(out);
+        }
+        const std::size_t nv = mesher.numVertices(), nt = mesher.numTriangles();
+        mesher = mlsb::Mesher();
+        std::ifstream in(argv[5], std::ios::binary);
+        mesher.load(in);
+        if (mesher.numVertices() != nv || mesher.numTriangles() != nt) return 3;
     }
     mlsb::PlyWriter writer;
     writer.addComment("mesher_test");

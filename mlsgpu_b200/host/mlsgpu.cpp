@@ -53,6 +53,7 @@ struct Options
     int device = 0;
     bool quiet = false, statistics = false, statisticsCL = false, split = false;
     std::uint64_t splitSize = 100ull << 20;   // src/mlsgpu_core.cpp:162
+    std::string checkpoint, resume;           // src/mlsgpu_core.cpp:121-122
     std::string statisticsFile;
     std::string output;
     std::vector<std::string> inputs;
@@ -80,6 +81,8 @@ void usage()
         "  --device N                  CUDA device ordinal (replaces --cl-device)\n"
         "  --split                     split the output into a grid of files BASE_XXXX_YYYY_ZZZZ.ply (-o gives BASE)\n"
         "  --split-size SIZE           approximate size of the output chunks (100M)\n"
+        "  --checkpoint FILE           save the mesher's state to FILE instead of writing the output\n"
+        "  --resume FILE               write the output from a checkpoint (no input is read, no device is used)\n"
         "  --statistics                print statistics at the end\n"
         "  --statistics-file FILE      direct statistics to FILE instead of stdout (implies --statistics)\n"
         "  --statistics-cl             collect timings for the device kernels (kernel.*.time)\n";
@@ -105,7 +108,7 @@ Options parse(int argc, char **argv)
     static const std::map<std::string, bool> ignored = {
         {"--response-file", true}, {"--tmp-dir", true},
         {"--timeplot", true}, {"--max-split", true}, {"--reader", true}, {"--writer", true}, {"--omp-threads", true},
-        {"--decache", false}, {"--checkpoint", true}, {"--resume", true}, {"--mem-load-splats", true},
+        {"--decache", false}, {"--mem-load-splats", true},
         {"--mem-host-splats", true}, {"--mem-reorder", true}, {"--mem-gather", true},
         {"--cl-device", true}, {"--cl-gpu", false}, {"--cl-cpu", false}, {"--debug", false}};
     for (int i = 1; i < argc; i++)
@@ -143,6 +146,8 @@ Options parse(int argc, char **argv)
         else if (a == "--statistics") o.statistics = true;
         else if (a == "--statistics-file") { o.statisticsFile = value(); o.statistics = true; }
         else if (a == "--statistics-cl") o.statisticsCL = true;
+        else if (a == "--checkpoint") o.checkpoint = value();
+        else if (a == "--resume") o.resume = value();
         else if (a == "--split") o.split = true;
         else if (a == "--split-size") o.splitSize = parseCapacity(value());
         else if (ignored.count(a)) { if (ignored.at(a)) (void) value(); }
@@ -151,7 +156,7 @@ Options parse(int argc, char **argv)
     }
     // validateOptions, src/mlsgpu_core.cpp:398-457
     if (o.output.empty()) throw std::invalid_argument("the option '--output-file' is required but missing");
-    if (o.inputs.empty()) throw std::invalid_argument("At least one input file must be specified.");
+    if (o.inputs.empty() && o.resume.empty()) throw std::invalid_argument("At least one input file must be specified.");
     if (o.levels < 1 || o.levels > 10) throw std::invalid_argument("Value of --levels must be in the range 1 to 10.");
     if (o.subsampling < 3) throw std::invalid_argument("Value of --subsampling must be at least 3.");
     if (o.levels + o.subsampling > 14) throw std::invalid_argument("Sum of --subsampling and --levels is too large.");
@@ -194,6 +199,42 @@ void collectInputs(const std::vector<std::string> &args, std::vector<std::string
 double now()
 {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct Written
+{
+    mlsb::Mesher::Result totals;   // component counts; vertices and triangles summed over the files
+    std::size_t files = 0;
+};
+
+// OOCMesher::write (src/mesher.cpp:763-852): prune, then one file — or, for a mesher in --split
+// mode, one file per chunk that holds at least one triangle, named by ChunkNamer (:88-96).
+Written writeMesh(mlsb::Mesher &mesher, bool split, const std::string &output, double fitPrune, const mlsb::PlyWriter &writer)
+{
+    Written w;
+    if (!split)
+    {
+        mlsb::Mesher::Result mesh = mesher.finish(fitPrune);
+        writer.write(output, mesh.vertexChunks, mesh.triangleChunks);
+        w.totals.totalComponents = mesh.totalComponents;
+        w.totals.keptComponents = mesh.keptComponents;
+        w.totals.numVertices = mesh.numVertices;
+        w.totals.numTriangles = mesh.numTriangles;
+        w.files = 1;
+        return w;
+    }
+    const std::vector<mlsb::Mesher::Result> chunks = mesher.finishChunks(fitPrune);
+    for (const mlsb::Mesher::Result &c : chunks)
+    {
+        w.totals.totalComponents = c.totalComponents;
+        w.totals.keptComponents = c.keptComponents;
+        w.totals.numVertices += c.numVertices;
+        w.totals.numTriangles += c.numTriangles;
+        if (c.numTriangles == 0) continue;
+        writer.write(mlsb::chunkName(output, c.chunk), c.vertexChunks, c.triangleChunks);
+        w.files++;
+    }
+    return w;
 }
 
 struct SinkState
@@ -240,6 +281,36 @@ int main(int argc, char **argv)
     {
         const Options o = parse(argc, argv);
         const double t0 = now();
+
+        if (!o.resume.empty())
+        {
+            // --resume: the mesher's state comes from a checkpoint; only pruning and writing are left
+            // (src/mlsgpu.cpp:105-109).  --fit-prune applies now; the chunking is the checkpoint's.
+            std::ifstream file(o.resume.c_str(), std::ios::binary);
+            if (!file) throw std::runtime_error("Could not open " + o.resume);
+            mlsb::Mesher mesher;
+            mesher.load(file);
+            mlsb::PlyWriter writer;
+            writer.addComment("mlsgpu (mlsb200) resumed from " + o.resume);
+            const Written written = writeMesh(mesher, mesher.isSplit(), o.output, o.fitPrune, writer);
+            if (!o.quiet || o.statistics)
+            {
+                std::ostringstream out;
+                out << "mlsgpu version: " << mlsb_version() << "\n"
+                    << "components.total: " << written.totals.totalComponents << "\ncomponents.kept: " << written.totals.keptComponents << "\n"
+                    << "output.vertices: " << written.totals.numVertices << "\noutput.triangles: " << written.totals.numTriangles << "\n"
+                    << "output.files: " << written.files << "\n"
+                    << "run.time: " << now() - t0 << "\n";
+                if (!o.statisticsFile.empty())
+                {
+                    std::ofstream stats(o.statisticsFile.c_str());
+                    stats << out.str();
+                }
+                else
+                    std::cout << out.str();
+            }
+            return 0;
+        }
 
         // ---- device workers: created in the background while the input is read and bucketed.
         // The buffers are sized from the options alone (--mem-bucket-splats, --levels,
@@ -368,29 +439,18 @@ int main(int argc, char **argv)
                           o.fitSmooth, o.fitGrid, o.fitPrune, o.fitBoundaryLimit, o.fitShape.c_str(), o.levels, o.subsampling);
             writer.addComment(buf);
         }
-        mlsb::Mesher::Result mesh;        // without --split: the mesh; with: the totals over the chunks
-        std::size_t outputFiles = 0;
-        if (!o.split)
+        Written written;
+        if (!o.checkpoint.empty())
         {
-            mesh = state.mesher.finish(o.fitPrune);
-            writer.write(o.output, mesh.vertexChunks, mesh.triangleChunks);
-            outputFiles = 1;
+            // --checkpoint: keep the mesher's state instead of writing (src/mlsgpu.cpp:171-175)
+            std::ofstream file(o.checkpoint.c_str(), std::ios::binary);
+            if (!file) throw std::runtime_error("Could not open " + o.checkpoint);
+            state.mesher.save(file);
         }
         else
-        {
-            // one file per chunk that holds at least one triangle, named by ChunkNamer (src/mesher.cpp:88-96)
-            std::vector<mlsb::Mesher::Result> chunks = state.mesher.finishChunks(o.fitPrune);
-            for (const mlsb::Mesher::Result &c : chunks)
-            {
-                mesh.totalComponents = c.totalComponents;
-                mesh.keptComponents = c.keptComponents;
-                mesh.numVertices += c.numVertices;
-                mesh.numTriangles += c.numTriangles;
-                if (c.numTriangles == 0) continue;
-                writer.write(mlsb::chunkName(o.output, c.chunk), c.vertexChunks, c.triangleChunks);
-                outputFiles++;
-            }
-        }
+            written = writeMesh(state.mesher, o.split, o.output, o.fitPrune, writer);
+        const mlsb::Mesher::Result &mesh = written.totals;
+        const std::size_t outputFiles = written.files;
         const double tEnd = now();
 
         if (!o.quiet || o.statistics)

@@ -130,6 +130,21 @@ def test_cli_end_to_end_sphere(tmp_path):
     keep = np.linalg.norm(pv, axis=1) < 1.3                      # drop the island, as --fit-prune did
     assert keep.sum() == len(verts) and keep[pt[:, 0]].sum() == len(tris)
 
+    # --checkpoint, then --resume without input or device: the same mesh (meshdiff), and with
+    # --fit-prune 0 at resume time the island comes back
+    ckpt = tmp_path / "sphere.ckpt"
+    r = subprocess.run([exe, "-o", str(tmp_path / "unused.ply"), "--fit-grid", "0.025", "--levels", "3", "--device-threads", "3",
+                        "--checkpoint", str(ckpt), "-q", str(inp)], capture_output=True, text=True)
+    assert r.returncode == 0 and ckpt.stat().st_size > 0 and not (tmp_path / "unused.ply").exists(), r.stderr
+    resumed = tmp_path / "resumed.ply"
+    r = subprocess.run([exe, "-o", str(resumed), "--resume", str(ckpt), "--fit-prune", "0.02", "-q"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    d = subprocess.run([build("meshdiff"), str(out), str(resumed)], capture_output=True, text=True)
+    assert d.returncode == 0 and "identical up to ordering" in d.stdout, d.stdout
+    r = subprocess.run([exe, "-o", str(resumed), "--resume", str(ckpt), "--fit-prune", "0", "--statistics"], capture_output=True, text=True)
+    assert r.returncode == 0 and "components.kept: 2" in r.stdout
+    assert len(plyfile.read_mesh_ply(resumed)[0]) == len(pv)
+
     # --split: a grid of chunk files that together hold exactly the same triangles (by position);
     # vertices on chunk borders appear in both neighbours; the island is pruned globally
     base = tmp_path / "split"
@@ -332,6 +347,48 @@ def test_mesher_split_names_and_global_components(tmp_path):
             assert len(verts) == 13 and len(tris) == 16 and tris.max() < len(verts)
         for f in tmp_path.glob("foo_*.ply"):
             f.unlink()
+
+
+def test_checkpoint_and_resume(tmp_path):
+    """--checkpoint / --resume (OOCMesher::checkpoint / resume, src/mesher.cpp:854-898): the mesher's state
+    survives a save/load round trip, and `mlsgpu --resume` writes the output from it without input,
+    device or bins — with the pruning threshold of the resuming command line."""
+    exe, cli = build("mesher_test"), build("mlsgpu")
+    chain = [tetra((3 * i, 0, 0), keys=[100 + i, 101 + i]) for i in range(12)]
+    blocks = chain + [tetra((-50, 0, 0))]
+    write_blocks(tmp_path / "blocks.bin", blocks)
+    ckpt = tmp_path / "state.ckpt"
+    direct, resumed = tmp_path / "direct.ply", tmp_path / "resumed.ply"
+    subprocess.run([exe, str(tmp_path / "blocks.bin"), "0.2", str(direct)], check=True, capture_output=True)
+    subprocess.run([exe, str(tmp_path / "blocks.bin"), "0.2", str(resumed), "1", str(ckpt)], check=True, capture_output=True)
+    dv, dt, _ = plyfile.read_mesh_ply(direct)
+    rv, rt, _ = plyfile.read_mesh_ply(resumed)
+    check_isomorphic(dv, dt.ravel(), rv, rt)
+    assert len(dv) == 12 * 4 - 11                                     # the island is pruned
+    # the command line resumes from the same file; --fit-prune is the resuming run's
+    for prune, nv, kept in (("0.2", 12 * 4 - 11, 1), ("0", 12 * 4 - 11 + 4, 2)):
+        out = tmp_path / "cli.ply"
+        r = subprocess.run([cli, "-o", str(out), "--resume", str(ckpt), "--fit-prune", prune, "--statistics"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        stats = dict(line.split(": ", 1) for line in r.stdout.strip().splitlines() if ": " in line)
+        assert int(stats["components.total"]) == 2 and int(stats["components.kept"]) == kept
+        v, t, _ = plyfile.read_mesh_ply(out)
+        assert len(v) == nv == int(stats["output.vertices"]) and t.max() < len(v)
+    # a --split checkpoint resumes into chunk files
+    chunks = [(0, 0, 0)] * 6 + [(1, 0, 0)] * 6 + [(2, 2, 2)]
+    write_blocks(tmp_path / "blocks.bin", blocks, chunks)
+    subprocess.run([exe, str(tmp_path / "blocks.bin"), "0", str(tmp_path / "h"), "1", str(ckpt)], check=True, capture_output=True)
+    r = subprocess.run([cli, "-o", str(tmp_path / "r"), "--resume", str(ckpt), "--fit-prune", "0", "-q"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == ""
+    for name in ("_0000_0000_0000.ply", "_0001_0000_0000.ply", "_0002_0002_0002.ply"):
+        hv, ht, _ = plyfile.read_mesh_ply(str(tmp_path / "h") + name)
+        cv, ct, _ = plyfile.read_mesh_ply(str(tmp_path / "r") + name)
+        check_isomorphic(hv, ht.ravel(), cv, ct)
+    # garbage is refused
+    (tmp_path / "bad.ckpt").write_bytes(b"not a checkpoint at all")
+    r = subprocess.run([cli, "-o", str(tmp_path / "x.ply"), "--resume", str(tmp_path / "bad.ckpt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "checkpoint" in r.stderr
 
 
 @THREADS

@@ -63,6 +63,20 @@ def test_mesher_welds_by_key_and_prunes(tmp_path):
     assert len(verts) == nv and len(tris) == nt
 
 
+@pytest.mark.parametrize("args", [
+    (60000, 1, 0.01, 63, 1 << 20, 0),        # plain grid of blocks
+    (60000, 2, 0.01, 63, 1500, 0),           # small --mem-bucket-splats: overfull blocks are halved
+    (60000, 3, 0.01, 255, 1 << 20, 70),      # --split: chunk boundaries inside what would be one block
+    (60000, 4, 0.004, 255, 20000, 300),      # both
+    (50, 5, 0.05, 7, 3, 0),                  # a handful of fat splats, tiny bins
+])
+def test_binning_contract_by_brute_force(args):
+    r = subprocess.run([build("bucket_test")] + [str(a) for a in args], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+    bins, chunks = int(r.stdout.split()[1]), int(r.stdout.split()[3])
+    assert bins >= 8 and (chunks > 1) == (args[5] > 0)
+
+
 def test_cli_option_validation():
     exe = build("mlsgpu")
     def run(*args):

@@ -292,7 +292,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--splats", type=int, default=10_000_000)
     ap.add_argument("--threads", type=int, default=0,
-                    help="workers per GPU (--device-threads); 0 = 12, fewer when the ranks share few host cores (never below 4)")
+                    help="workers per GPU (--device-threads); 0 = 12 (fewer only on hosts with less than a core per 4 workers)")
     ap.add_argument("--order", default="largest-first", choices=["largest-first", "bucket"],
                     help="order in which the bins are handed to the worker group")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -304,8 +304,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.threads <= 0:
         # measured on one B200: 3 workers 250, 4: 266, 6: 273, 8: 281 Msplats/s (sort-based marching);
-        # with the lattice weld and stream priorities 8: 308, 12: 314
-        args.threads = max(4, min(12, (os.cpu_count() or 8) // world - 1))
+        # with the lattice weld and stream priorities 8: 308, 12: 314, 16: 311.  The workers mostly wait
+        # (on events, once there are more of them than cores: MLSB_SYNC=block below), so they may
+        # outnumber the cores: 2 GPUs pinned to 8 cores gave 642 Msplats/s with 12 workers each and 569
+        # with 4.  Only a host with less than a core per four workers gets fewer.
+        args.threads = max(4, min(12, 4 * (os.cpu_count() or 8) // world))
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -3,6 +3,7 @@
 // (extras/plymanifold.cpp:135-205), same output and exit codes (0 manifold, 1 not / unreadable,
 // 2 usage).
 #include <cmath>
+#include <cstdio>
 #include <iostream>
 
 #include "manifold.hpp"
@@ -29,16 +30,14 @@ int main(int argc, const char **argv)
         mlsb::manifold::Metadata metadata;
         const std::string reason =
             mlsb::manifold::isManifold(mesh.vertices.size(), mesh.triangles.data(), mesh.triangles.size(), &metadata);
-        if (reason != "")
+        if (!reason.empty())
         {
-            std::cout << "Mesh is not manifold: " << reason << "\n";
+            std::printf("Mesh is not manifold: %s\n", reason.c_str());
             return 1;
         }
-        std::cout << "Mesh is manifold."
-                  << "\nVertices: " << metadata.numVertices
-                  << "\nTriangles: " << metadata.numTriangles
-                  << "\nComponents: " << metadata.numComponents
-                  << "\nBoundaries: " << metadata.numBoundaries << std::endl;
+        // the report lines of extras/plymanifold.cpp:183-187
+        std::printf("Mesh is manifold.\nVertices: %zu\nTriangles: %zu\nComponents: %zu\nBoundaries: %zu\n",
+                    metadata.numVertices, metadata.numTriangles, metadata.numComponents, metadata.numBoundaries);
     }
     catch (mlsb::PlyFormatError &e)
     {

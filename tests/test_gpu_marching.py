@@ -90,3 +90,20 @@ def test_random_field(orc):
     with m.Worker(max_splats=16, max_cells=63) as w:
         blocks = w.marching_generate_host_field(vol, (1, 2, 3))
     assert_block_equal(blocks[0], ref)
+
+
+@pytest.mark.parametrize("width", [33, 65, 257, 34])
+def test_row_widths_around_the_lattice_word_size(orc, width):
+    """Cell rows of exactly 32, 64 and 256 cells (and 33): the vertex of the last corner column is carried
+    into the extra lattice word of the row, and random NaN holes cut the surface everywhere."""
+    import mlsgpu_b200 as m
+    rng = np.random.RandomState(width)
+    vol = rng.standard_normal((6, 11, width)).astype(np.float32)
+    vol[rng.rand(*vol.shape) < 0.1] = np.nan
+    vol[:, :, -1] = np.where(np.arange(11)[None, :] % 2 == 0, 1.0, -1.0)      # crossings in the last column
+    ref = oracle_mesh(orc, vol, (3, 5, 7))
+    with m.Worker(max_splats=16, max_cells=width - 1 if width > 32 else 32) as w:
+        blocks = w.marching_generate_host_field(vol, (3, 5, 7))
+    assert len(blocks) == 1 and len(ref["vertices"]) > ref["num_internal"] > 0
+    assert_block_equal(blocks[0], ref)
+    np.testing.assert_array_equal(blocks[0]["triangles"], ref["triangles"])

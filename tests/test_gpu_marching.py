@@ -92,10 +92,11 @@ def test_random_field(orc):
     assert_block_equal(blocks[0], ref)
 
 
-@pytest.mark.parametrize("width", [33, 65, 257, 34])
+@pytest.mark.parametrize("width", [33, 65, 257, 34, 300, 512])
 def test_row_widths_around_the_lattice_word_size(orc, width):
     """Cell rows of exactly 32, 64 and 256 cells (and 33): the vertex of the last corner column is carried
-    into the extra lattice word of the row, and random NaN holes cut the surface everywhere."""
+    into the extra lattice word of the row, and random NaN holes cut the surface everywhere.  300 and
+    512 corners need the two-chunk variant of the cell kernels (bins up to 511 cells per side)."""
     import mlsgpu_b200 as m
     rng = np.random.RandomState(width)
     vol = rng.standard_normal((6, 11, width)).astype(np.float32)

@@ -311,6 +311,31 @@ WELD_BLOCKS = [
         [0, 2, 1, 1, 2, 4, 4, 2, 3])]
 
 
+@pytest.mark.parametrize("order", [(0, 1, 2), (2, 1, 0)])
+def test_mesher_reference_simple_fixture(tmp_path, order):
+    """testSimple, test/test_mesher.cpp:462-544: three blocks without shared keys, in either order."""
+    expected_vertices = [(0, 0, 1), (0, 0, 2), (0, 0, 3), (0, 0, 4), (0, 0, 5), (1, 0, 1), (1, 0, 2), (1, 0, 3), (1, 0, 4),
+                         (0, 1, 0), (0, 2, 0), (0, 3, 0), (2, 0, 1), (2, 0, 2)]
+    expected_indices = [0, 1, 3, 1, 2, 3, 3, 4, 0, 5, 6, 8, 6, 7, 8, 7, 5, 8, 9, 10, 12, 10, 13, 12, 11, 12, 13, 9, 11, 13,
+                        9, 12, 11]
+    verts, tris = run_mesher(tmp_path, [WELD_BLOCKS[i] for i in order], 0.0)
+    check_isomorphic(expected_vertices, expected_indices, verts, tris)
+
+
+def test_mesher_reference_no_internal_and_no_external_fixtures(tmp_path):
+    """testNoInternal / testNoExternal, test/test_mesher.cpp:546-650 (degenerate triangles included)."""
+    b1 = WELD_BLOCKS[1]
+    b2 = blk([], [(2, 0, 1), (2, 0, 2)], [0x1234567812345678, 0x12345678], [0, 1, 1, 0, 0, 1])
+    verts, tris = run_mesher(tmp_path, [b1, b2], 0.0)
+    check_isomorphic([(1, 0, 1), (1, 0, 2), (1, 0, 3), (1, 0, 4), (2, 0, 1), (2, 0, 2)],
+                     [0, 1, 3, 1, 2, 3, 2, 0, 3, 4, 5, 5, 4, 4, 5], verts, tris)
+    b0 = WELD_BLOCKS[0]
+    b2 = blk([(0, 1, 0), (0, 2, 0), (0, 3, 0)], [], [], [0, 1, 2, 2, 1, 0])
+    verts, tris = run_mesher(tmp_path, [b0, b2], 0.0)
+    check_isomorphic([(0, 0, 1), (0, 0, 2), (0, 0, 3), (0, 0, 4), (0, 0, 5), (0, 1, 0), (0, 2, 0), (0, 3, 0)],
+                     [0, 1, 3, 1, 2, 3, 3, 4, 0, 5, 6, 7, 7, 6, 5], verts, tris)
+
+
 def run_split(tmp_path, blocks, chunks, prune, threads=1, base="chunk"):
     exe = build("mesher_test")
     write_blocks(tmp_path / "blocks.bin", blocks, chunks)

@@ -336,6 +336,30 @@ def test_mesher_reference_no_internal_and_no_external_fixtures(tmp_path):
                      [0, 1, 3, 1, 2, 3, 3, 4, 0, 5, 6, 7, 7, 6, 5], verts, tris)
 
 
+@THREADS
+def test_mesher_on_oracle_blocks(tmp_path, threads):
+    """A real surface shipped out in four blocks (the oracle's marching over four z ranges of the
+    reference's truncated-sphere volume): the mesher's weld equals the key weld of the test suite and
+    `plymanifold` accepts it — the role of testRandom, test/test_mesher.cpp:1010-1100."""
+    from oracle.oracle import Oracle
+    from test_oracle_marching import MARCHING_CASES, to_image, weld_by_key
+    orc = Oracle()
+    vol = MARCHING_CASES["truncated"]()
+    d, h, w = vol.shape
+    img, zs = to_image(vol)
+    cuts = [0, 13, 14, 40, d - 1]                        # one block is a single slab of cells
+    parts = [orc.marching_generate(img, w, h, zs, 0, z0, z1, (2, 3, 4)) for z0, z1 in zip(cuts[:-1], cuts[1:])]
+    blocks = [dict(vertices=p["vertices"], triangles=p["triangles"], num_internal=p["num_internal"],
+                   keys=p["keys"][p["num_internal"]:].copy()) for p in parts]
+    verts, tris = run_mesher(tmp_path, blocks, 0.0, threads)
+    pv, pt = weld_by_key(parts)
+    whole = orc.marching_generate(img, w, h, zs, 0, 0, d - 1, (2, 3, 4))
+    assert len(verts) == len(pv) == len(whole["vertices"]) and len(tris) == len(pt) == len(whole["triangles"])
+    np.testing.assert_array_equal(np.unique(verts, axis=0), np.unique(whole["vertices"], axis=0))
+    check = subprocess.run([build("plymanifold"), str(tmp_path / "out.ply")], capture_output=True, text=True)
+    assert check.returncode == 0 and "Components: 1\n" in check.stdout, check.stdout
+
+
 def run_split(tmp_path, blocks, chunks, prune, threads=1, base="chunk"):
     exe = build("mesher_test")
     write_blocks(tmp_path / "blocks.bin", blocks, chunks)

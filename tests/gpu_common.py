@@ -34,3 +34,72 @@ def assert_block_equal(gpu, orc, scale=1.0, bias=(0.0, 0.0, 0.0), exact=True):
     ni = orc["num_internal"]
     np.testing.assert_array_equal(gpu["external_keys"], orc["keys"][ni:])
     np.testing.assert_array_equal(gpu["triangles"], orc["triangles"])
+
+
+def same_field(a, b):
+    """NaN positions equal and finite values bit-identical."""
+    na, nb = np.isnan(a), np.isnan(b)
+    np.testing.assert_array_equal(na, nb)
+    np.testing.assert_array_equal(a[~na].view(np.uint32), b[~nb].view(np.uint32))
+
+
+def padded(size):
+    """(pitch, zStride, depth): the bin's corners per axis rounded up to the 8-wide MLS blocks."""
+    return tuple(-(-int(v) // 8) * 8 for v in size)
+
+
+def gpu_field(w, splats, size, offset):
+    """Octree build + processCorners of one bin on worker `w`, stage by stage through the C ABI.
+    Returns (field image, start, commands, splats as mutated by the build, (T, H))."""
+    from mlsgpu_b200.capi import DeviceBuffer
+    pitch, zs, depth = padded(size)
+    w.set_work_counting(True)
+    w.reset_statistics()
+    w.upload_splats(splats)
+    w.octree_build(0, len(splats), padded(size), offset)
+    w.mls_set(offset)
+    d_img = DeviceBuffer(4 * pitch * zs * depth)
+    d_img.fill(0)
+    w.mls_corners(d_img, pitch, int(size[0]), int(size[1]), zs, 0, 0, int(size[2]) - 1)
+    w.synchronize()
+    got = d_img.to_array(np.float32, (zs * depth, pitch))
+    d_img.free()
+    start, commands = w.octree_get()
+    out = w.download_splats(0, len(splats))
+    work = w.mls_work()
+    w.set_work_counting(False)
+    return got, start, commands, out, work
+
+
+def oracle_field(orc, splats, size, offset, limit=1.0, shape=0, max_levels=6, subsampling=3):
+    """The same two stages on the oracle.  Returns (field image, tree, mutated splats, (T, H))."""
+    s = splats.copy()
+    tree = orc.octree_build(s, 0, len(s), offset, subsampling, max_levels)
+    pitch, zs, depth = padded(size)
+    img = np.zeros((zs * depth, pitch), np.float32)
+    work = orc.mls_process_corners(img, s, tree["commands"], tree["start"], 3 * subsampling, offset, int(size[0]),
+                                   int(size[1]), zs, 0, 0, int(size[2]) - 1, orc.boundary_factor(limit), shape)
+    return img, tree, s, work
+
+
+def oracle_blocks(orc, img, size, offset, vertex_space, index_space, z0=0, z1=None):
+    """Marching on the oracle with the worker's overflow rule: a z range whose per-cell vertex or index
+    count exceeds the mesh memory is halved and shipped as two blocks (shipRange in csrc/marching.cu;
+    the reference splits by its per-slice histogram, src/marching.cpp:651-704)."""
+    zs = padded(size)[1]
+    z1 = int(size[2]) - 1 if z1 is None else z1
+    mesh = orc.marching_generate(img, int(size[0]), int(size[1]), zs, 0, z0, z1, [int(v) for v in offset],
+                                 vcap=8 << 20, icap=48 << 20)
+    _, nv, ni = mesh["stats"]
+    if nv > vertex_space or ni > index_space:
+        assert z1 - z0 > 1
+        mid = z0 + (z1 - z0) // 2
+        return (oracle_blocks(orc, img, size, offset, vertex_space, index_space, z0, mid)
+                + oracle_blocks(orc, img, size, offset, vertex_space, index_space, mid, z1))
+    return [mesh] if len(mesh["vertices"]) else []
+
+
+def mesh_space(mesh_bytes):
+    """(vertexSpace, indexSpace) of a worker: meshBytes / 872 cells x 13 / x 36 (src/marching.cpp:389-392)."""
+    cells = mesh_bytes // 872
+    return cells * 13, cells * 36

@@ -232,6 +232,11 @@ MLSB_API int mlsb_worker_reset_statistics(mlsb_worker *w);
  * pass).  Counters are cleared by mlsb_worker_reset_statistics. */
 MLSB_API int mlsb_worker_set_work_counting(mlsb_worker *w, int enabled);
 MLSB_API int mlsb_worker_get_mls_work(mlsb_worker *w, uint64_t *pairTests, uint64_t *hits);
+/* Marching's side of the same model, always counted (the per-block sizes are read back anyway):
+ * corners classified (C), occupied cells (K), per-cell i.e. unwelded vertices (V), indices (I) and
+ * welded vertices of all blocks shipped since the last mlsb_worker_reset_statistics. */
+MLSB_API int mlsb_worker_get_marching_work(mlsb_worker *w, uint64_t *corners, uint64_t *cells, uint64_t *unwelded,
+                                           uint64_t *indices, uint64_t *welded);
 /* FP32 pipe peak of a device in lane-instructions per second, measured with a dependent-free
  * FFMA stream (the roofline denominator of processCorners). */
 MLSB_API int mlsb_measure_fp32_peak(int device, double *laneInstPerSecond);

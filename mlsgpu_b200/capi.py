@@ -84,6 +84,7 @@ API = {
     "mlsb_worker_set_work_counting": (C.c_int, [_P, C.c_int]),
     "mlsb_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "mlsb_worker_get_mls_work": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "mlsb_worker_get_marching_work": (C.c_int, [_P] + [C.POINTER(C.c_uint64)] * 5),
     "mlsb_worker_launch_count": (C.c_uint64, [_P]),
     "mlsb_device_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "mlsb_device_free": (C.c_int, [_P]),
@@ -393,6 +394,12 @@ class Worker:
         t, h = C.c_uint64(), C.c_uint64()
         _check(lib().mlsb_worker_get_mls_work(self.h, C.byref(t), C.byref(h)))
         return t.value, h.value
+
+    def marching_work(self):
+        """(corners, occupied cells, unwelded vertices, indices, welded vertices) since the last reset."""
+        v = [C.c_uint64() for _ in range(5)]
+        _check(lib().mlsb_worker_get_marching_work(self.h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
 
     @property
     def launch_count(self):

@@ -205,9 +205,7 @@ int mlsb_worker_create(const mlsb_worker_config *config, mlsb_worker **out)
     if ((st = octreeAlloc(w)) != MLSB_OK) return fail(st);
     if ((st = mlsAlloc(w)) != MLSB_OK) return fail(st);
     if ((st = marchingAlloc(w)) != MLSB_OK) return fail(st);
-    // shared scan / sort scratch
-    size_t maxSort = 8ull * config->maxSplats;
-    if ((st = sortScratchAlloc(w->sort, maxSort, 4)) != MLSB_OK) return fail(st);
+    // shared scan scratch (the sort's lives with the octree's, see octreeAlloc)
     uint64_t cells = (uint64_t) config->maxCells * config->maxCells * config->maxCells;
     uint64_t words = std::max<uint64_t>({divUp<uint64_t>(cells, 256) + 2, divUp<uint64_t>(w->numStartMax, 2048) + 2,
                                          divUp<uint64_t>(config->maxSplats, 256) + 2,
@@ -236,7 +234,6 @@ void mlsb_worker_destroy(mlsb_worker *w)
     octreeFree(w);
     mlsFree(w);
     marchingFree(w);
-    sortScratchFree(w->sort);
     cudaFree(w->scanStatus);
     cudaFree(w->scanTicket);
     if (w->copyEvent) cudaEventDestroy(w->copyEvent);
@@ -327,7 +324,9 @@ int mlsb_octree_get(mlsb_worker *w, const int32_t **start, uint32_t *numStart, c
 int mlsb_mls_set(mlsb_worker *w, const int32_t offset[3], uint32_t subsamplingShift)
 {
     MLSB_REQUIRE(w != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null worker");
-    return mlsb_mls_set_buffers(w, offset, w->splats, w->commands, w->start, subsamplingShift);
+    MLSB_TRY(mlsb_mls_set_buffers(w, offset, w->splats, w->commands, w->start, subsamplingShift));
+    w->mlsThresholds = w->hitThresholds;   // written by the octree build for exactly these splats
+    return MLSB_OK;
 }
 
 int mlsb_mls_set_buffers(mlsb_worker *w, const int32_t offset[3], const mlsb_splat *splats, const int32_t *commands,
@@ -340,6 +339,7 @@ int mlsb_mls_set_buffers(mlsb_worker *w, const int32_t offset[3], const mlsb_spl
     w->mlsSplats = splats;
     w->mlsCommands = commands;
     w->mlsStart = start;
+    w->mlsThresholds = nullptr;
     memcpy(w->mlsOffset, offset, sizeof(w->mlsOffset));
     w->mlsStartShift = 3 * subsamplingShift;
     w->mlsBound = true;
@@ -450,6 +450,7 @@ int mlsb_worker_reset_statistics(mlsb_worker *w)
     MLSB_CUDA(cudaStreamSynchronize(w->stream));
     collectStats(w);
     for (StatAccum &a : w->stats) a = StatAccum();
+    for (uint64_t &v : w->marchWork) v = 0;
     MLSB_CUDA(cudaMemset(w->mlsWork, 0, 2 * sizeof(unsigned long long)));
     return MLSB_OK;
 }
@@ -469,6 +470,18 @@ int mlsb_worker_get_mls_work(mlsb_worker *w, uint64_t *pairTests, uint64_t *hits
     MLSB_CUDA(cudaMemcpy(h, w->mlsWork, sizeof(h), cudaMemcpyDeviceToHost));
     if (pairTests) *pairTests = h[0];
     if (hits) *hits = h[1];
+    return MLSB_OK;
+}
+
+int mlsb_worker_get_marching_work(mlsb_worker *w, uint64_t *corners, uint64_t *cells, uint64_t *unwelded, uint64_t *indices,
+                                  uint64_t *welded)
+{
+    MLSB_REQUIRE(w != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null worker");
+    if (corners) *corners = w->marchWork[0];
+    if (cells) *cells = w->marchWork[1];
+    if (unwelded) *unwelded = w->marchWork[2];
+    if (indices) *indices = w->marchWork[3];
+    if (welded) *welded = w->marchWork[4];
     return MLSB_OK;
 }
 

@@ -48,6 +48,31 @@ constexpr unsigned kMaxCellVertices = 13;  // src/marching.h:88
 constexpr unsigned kMaxCellIndices = 36;   // src/marching.h:92
 constexpr unsigned kMaxCellBytes = 872;    // src/marching.h:97-100
 
+// The hit test of kernels/mls.cl:373-374 is  d = pp * invr2;  d < 0.99f.  x -> RN(x * w) is
+// monotone for w > 0, so the set of pp >= 0 that pass is exactly { pp < T } for one float T per
+// splat: the smallest T with RN(T * w) >= 0.99f.  Comparing against T saves the multiply in the
+// pair test (d itself is only needed for a hit) without changing a single decision.
+// w = +0 (infinite radius) passes every finite pp: T = +inf.  w = +inf or NaN passes nothing: T = 0.
+// Computed once per splat by the octree build (a side array), or by the MLS kernel itself when it
+// is bound to buffers that did not come from our build.
+#ifdef __CUDACC__
+__device__ __forceinline__ float hitThreshold(float w)
+{
+    const float cutoff = 0.99f;   // RADIUS_CUTOFF, kernels/mls.cl:36
+    if (!(w > 0.0f)) return w == 0.0f ? __uint_as_float(0x7F800000u) : 0.0f;
+    if (__float_as_uint(w) == 0x7F800000u) return 0.0f;
+    float t = __fdiv_rn(cutoff, w);
+    if ((__float_as_uint(t) & 0x7F800000u) == 0x7F800000u) t = __uint_as_float(0x7F7FFFFFu);
+    for (int k = 0; k < 8 && t > 0.0f && __fmul_rn(t, w) >= cutoff; k++) t = __uint_as_float(__float_as_uint(t) - 1);
+    for (int k = 0; k < 8 && __fmul_rn(t, w) < cutoff; k++)
+    {
+        if (__float_as_uint(t) >= 0x7F7FFFFFu) return __uint_as_float(0x7F800000u);
+        t = __uint_as_float(__float_as_uint(t) + 1);
+    }
+    return t;
+}
+#endif
+
 // One timed interval recorded with a pair of CUDA events on the worker's stream.
 struct TimedSpan
 {
@@ -64,6 +89,7 @@ struct StatAccum
 // Device-side layout of the radix sort scratch (see sort.cu).
 struct SortScratch
 {
+    void *base = nullptr;          // the allocation: [caller's prefix | hist | tickets | status]
     uint32_t *hist = nullptr;      // [passes][256] global digit histograms
     uint32_t *status = nullptr;    // [passes][tiles][256] decoupled look-back words
     uint32_t *tickets = nullptr;   // [passes] dynamic tile counters
@@ -104,6 +130,13 @@ struct mlsb_worker
     uint32_t *entryValues[2] = {nullptr, nullptr};
     int32_t *runFirst = nullptr, *runLast = nullptr;
     uint32_t *runIndex = nullptr;
+    // scratch of the fused build, zeroed by ONE memset per bin together with the sort's (they share an
+    // allocation): look-back words of the entry tiles, {ticket, numValid}, per-key entry counts
+    uint64_t *entryStatus = nullptr;
+    uint32_t entryTilesMax = 0;
+    uint32_t *entryCounters = nullptr;   // [0] tile ticket, [1] number of accepted entries
+    uint32_t *keyCount = nullptr;        // only when the octree is small enough for the one-CTA plan kernel
+    float *hitThresholds = nullptr;      // per splat: the |p|^2 below which the splat counts (mls.cu), by the build
     uint64_t *scanStatus = nullptr;   // decoupled look-back words for device-wide scans
     uint32_t scanStatusWords = 0;
     uint32_t *scanTicket = nullptr;
@@ -113,6 +146,7 @@ struct mlsb_worker
     const mlsb_splat *mlsSplats = nullptr;
     const int32_t *mlsCommands = nullptr;
     const int32_t *mlsStart = nullptr;
+    const float *mlsThresholds = nullptr;   // per-splat hit thresholds when the octree came from our build
     int32_t mlsOffset[3] = {0, 0, 0};
     uint32_t mlsStartShift = 0;
     float boundaryFactor = 0.0f;
@@ -125,7 +159,9 @@ struct mlsb_worker
     uint8_t *blockActive = nullptr;   // [bz][by][bx] per 8x8x8 block of the field: written by the MLS kernel
     uint64_t vertexSpace = 0, indexSpace = 0;
     uint32_t *latMask = nullptr;      // lattice of edge midpoints: 1 bit per possible vertex of a block
-    uint2 *latPrefix = nullptr;       // per lattice word: welded vertices in front of it (unflagged, flagged)
+    uint4 *latRecord = nullptr;       // per non-empty lattice word: (mask, welded vertices in front of it: unflagged, flagged, -)
+    uint64_t *latStatus = nullptr;    // look-back words of the lattice scan; they follow marchCounters in one allocation
+    uint32_t latStatusWords = 0;
     size_t latticeWords = 0;
     uint32_t *indices = nullptr;
     float *welded = nullptr;          // packed float3
@@ -152,6 +188,7 @@ struct mlsb_worker
     std::vector<mlsb::TimedSpan> pendingSpans;
     std::vector<cudaEvent_t> eventPool;
     uint64_t launches = 0;
+    uint64_t marchWork[5] = {0, 0, 0, 0, 0};   // corners, cells, unwelded vertices, indices, welded vertices
     // host waits: spin (lowest latency) or block on an event (frees the core; MLSB_SYNC=block)
     bool blockingSync = false;
     bool yieldingSync = false;    // MLSB_SYNC=yield: poll cudaStreamQuery with sched_yield between polls
@@ -180,7 +217,9 @@ int waitStream(mlsb_worker *w);   // host wait for the worker's compute stream
 void collectStats(mlsb_worker *w);   // requires the stream to be idle
 
 // sort.cu
-int sortScratchAlloc(SortScratch &s, size_t maxItems, uint32_t maxPasses);
+// prefixBytes: room in front of the sort's own scratch, in the same allocation (*prefix), for state the
+// caller wants zeroed by the same memset
+int sortScratchAlloc(SortScratch &s, size_t maxItems, uint32_t maxPasses, size_t prefixBytes = 0, void **prefix = nullptr);
 void sortScratchFree(SortScratch &s);
 // Stable LSD radix sort of (key,value) u32 pairs on the low `bits` bits.  Input in keys[0] /
 // values[0]; returns in *result which of the two buffers holds the output.
@@ -191,6 +230,14 @@ int radixSortPairs(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint3
 int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n,
                               const uint32_t *nDev, uint32_t bits, int *result, const char *statName,
                               bool identityValues);
+
+// The last pass of a sort whose digit histograms were written by the caller (s.hist) into scratch the
+// caller has zeroed: instead of the sorted pairs it writes the octree's command list,
+// commands[1 + position + 2 * runIndex[key]] = value.  n = host-side bound, *nDev the real count.
+int radixSortToCommands(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n, const uint32_t *nDev,
+                        uint32_t bits, int32_t *commands, const uint32_t *runIndex, const char *statName);
+// bytes of sort scratch (from s.hist on) a sort of n items with `passes` passes touches
+size_t sortScratchBytesUsed(const SortScratch &s, uint32_t n, uint32_t passes);
 
 // octree.cu
 int octreeAlloc(mlsb_worker *w);

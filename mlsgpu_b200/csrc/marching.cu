@@ -10,7 +10,8 @@
 //   generateCells<classify>  genOccupied (:84-120) bit-parallel on ballot masks; every warp row
 //                   that holds surface also ORs the lattice bits of its valid cells' crossed edges
 //                   (19 edges = 9 lattice rows x {even, odd} columns, a handful of logic ops each)
-//   scanTiles       per-tile index bases (the role of clogs::Scan at src/marching.cpp:721)
+//   (tile scan)     per-tile index bases (the role of clogs::Scan at src/marching.cpp:721): one extra
+//                   CTA of the scanLattice launch, so it costs no launch and no time of its own
 //   scanLattice     countUniqueVertices + scan + compactVertices + scaleBiasVertices (:271-326,
 //                   kernels/scale_bias.cl:32-40) with generateElements' interpolation (:130-138):
 //                   one decoupled look-back scan over the lattice words in (z, y, x) order = key
@@ -35,6 +36,18 @@ namespace mlsb
 namespace
 {
 
+// Measured on the 70-bin C2 step (one worker, ms per step; profiles/r2_summary.md): the index pass is
+// bound by latency and by how many independent loads it has in flight, not by instruction count —
+// a thread per INDEX (binary search, table walk and record load for every index) takes 4.2 ms, a thread
+// per occupied CELL that ranks each vertex once (a third of the instructions) 4.9-5.5 ms; having all
+// corner rows of a warp in flight before the first ballot helps the index pass (4.5 -> 4.2 ms, its CTAs
+// start from a cold field) and not the classification (3.1 -> 3.2 ms).
+#ifndef MLSB_MC_PREFETCH
+#define MLSB_MC_PREFETCH EMIT
+#endif
+#ifndef MLSB_MC_EMIT
+#define MLSB_MC_EMIT 0
+#endif
 constexpr int kNumEdges = 19;
 constexpr int kGenThreads = 256;
 
@@ -176,7 +189,7 @@ struct GenParams
     // lattice of edge midpoints of this block: [2 * (zLast - zFirst) + 1][latRows][latStride] words,
     // bit x2 of row (y2, z2) = the edge with midpoint (x2, y2, z2) / 2 carries a vertex
     uint32_t *latMask;
-    const uint2 *latPrefix;        // per non-empty word: vertices before it (unflagged, flagged)
+    const uint4 *latRecord;        // per non-empty word: (mask, vertices before it: unflagged, flagged, -)
     uint32_t latStride, latRows;
     uint64_t *tileTotals;          // per tile: classify writes (v | i << 21 | cells << 42), scanTiles turns it
                                    // into the tile's exclusive base (v | i << 31)
@@ -206,13 +219,29 @@ struct RowMasks
     uint32_t f0, f1;   // finite bits at corner x / x+1
 };
 
-// Masks of one corner row of one slice for the 32 cells starting at cell x0 (needs 33 corners).
-__device__ __forceinline__ RowMasks loadRowMasks(const float *__restrict__ row, uint32_t x0, uint32_t lane, uint32_t numCorners)
+// The 33 corner values of one row of one slice that the 32 cells starting at x0 need: lane L holds
+// corner x0 + L, lane 0 also the 33rd.  Loading and ballot are separate so that a warp can have the
+// loads of ALL its rows in flight before it consumes the first one (nine dependent round trips to
+// memory otherwise).
+struct RowValues
+{
+    float v, e;
+};
+
+__device__ __forceinline__ RowValues loadRowValues(const float *__restrict__ row, uint32_t x0, uint32_t lane, uint32_t numCorners)
 {
     const uint32_t x = x0 + lane;
-    const float v = x < numCorners ? __ldg(row + x) : __uint_as_float(0x7FC00000u);
-    float e = __uint_as_float(0x7FC00000u);
-    if (lane == 0 && x0 + 32 < numCorners) e = __ldg(row + x0 + 32);
+    RowValues r;
+    r.v = x < numCorners ? __ldg(row + x) : __uint_as_float(0x7FC00000u);
+    r.e = __uint_as_float(0x7FC00000u);
+    if (lane == 0 && x0 + 32 < numCorners) r.e = __ldg(row + x0 + 32);
+    return r;
+}
+
+// Masks of one corner row of one slice for the 32 cells starting at cell x0.
+__device__ __forceinline__ RowMasks rowMasks(const RowValues rv)
+{
+    const float v = rv.v, e = rv.e;
     const uint32_t s = __ballot_sync(0xFFFFFFFFu, v >= 0.0f);
     const uint32_t f = __ballot_sync(0xFFFFFFFFu, finiteF(v));
     const uint32_t eb = __shfl_sync(0xFFFFFFFFu, (uint32_t) (e >= 0.0f) | ((uint32_t) finiteF(e) << 1), 0);
@@ -248,30 +277,28 @@ __device__ __forceinline__ uint32_t latticeFlagMask(uint32_t wcol, uint32_t y2, 
 }
 
 // Welded index of the vertex at lattice point (x2, y2, z2) of the block.
-__device__ __forceinline__ uint32_t latticeRank(const uint32_t *__restrict__ mask, const uint2 *__restrict__ prefix,
-                                                uint32_t stride, uint32_t rows, uint32_t x2, uint32_t y2, uint32_t z2,
-                                                uint32_t topX, uint32_t topY, uint32_t numUnflagged)
+__device__ __forceinline__ uint32_t latticeRank(const uint4 *__restrict__ record, uint32_t stride, uint32_t rows, uint32_t x2,
+                                                uint32_t y2, uint32_t z2, uint32_t topX, uint32_t topY, uint32_t numUnflagged)
 {
     const uint32_t wcol = x2 >> 5, bit = x2 & 31;
     const size_t word = ((size_t) z2 * rows + y2) * stride + wcol;
-    const uint32_t m = __ldg(mask + word);
-    const uint2 pre = __ldg(prefix + word);
+    const uint4 rec = __ldg(record + word);   // one 16-byte load: mask and both ranks
     const uint32_t fm = latticeFlagMask(wcol, y2, z2, topX, topY);
     const uint32_t below = (1u << bit) - 1;
-    return (fm >> bit) & 1 ? numUnflagged + pre.y + __popc(m & fm & below) : pre.x + __popc(m & ~fm & below);
+    return (fm >> bit) & 1 ? numUnflagged + rec.z + __popc(rec.x & fm & below) : rec.y + __popc(rec.x & ~fm & below);
 }
 
 // EMIT = false: classify the tile's cells and write its (vertices, indices, cells) totals; warp
 //               rows that hold surface also OR their crossed edges into the lattice mask.
 // EMIT = true:  re-classify a NON-EMPTY tile (blockIdx.x indexes tileList), list its occupied cells
-//               in shared memory and emit one index per thread at the base that scanTilesKernel
+//               in shared memory and emit one index per thread at the base that the tile scan
 //               computed, so that all stores are contiguous.
 // Splitting the pass keeps every CTA free of inter-CTA waits; only the few percent of tiles that
 // hold surface are classified twice.  CHUNKS = ceil(cellsX / 256).
 template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) generateCellsKernel(GenParams P)
 {
     constexpr int kVRows = kGenRows * CHUNKS;
-    extern __shared__ uint32_t sList[];   // EMIT: [2][kVRows * 256]: cell, index base
+    extern __shared__ uint32_t sList[];   // EMIT: [2][kVRows * 256]: cell, index base; then [13][256] vertex ranks
     __shared__ uint64_t sWarpTot[kVRows * kGenWarps];
     __shared__ uint64_t sScan[33];
 
@@ -308,11 +335,27 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
         if (active && P.blockActive != nullptr)
             active = *reinterpret_cast<const uint32_t *>(P.blockActive + ((size_t) (z >> 3) * P.activeDim + (y0 >> 3)) * P.activeDim + (x0 >> 3)) != 0;
         RowMasks p0 = {0, 0, 0, 0}, p1 = {0, 0, 0, 0};
+#if MLSB_MC_PREFETCH
+        RowValues rv0[kGenRows + 1], rv1[kGenRows + 1];
         if (active)
         {
-            p0 = loadRowMasks(slice0, x0, lane, numCorners);
-            p1 = loadRowMasks(slice1, x0, lane, numCorners);
+#pragma unroll
+            for (int r = 0; r <= kGenRows; r++)
+                if ((uint32_t) r <= nRows)
+                {
+                    rv0[r] = loadRowValues(slice0 + (size_t) r * P.pitch, x0, lane, numCorners);
+                    rv1[r] = loadRowValues(slice1 + (size_t) r * P.pitch, x0, lane, numCorners);
+                }
+            p0 = rowMasks(rv0[0]);
+            p1 = rowMasks(rv1[0]);
         }
+#else
+        if (active)
+        {
+            p0 = rowMasks(loadRowValues(slice0, x0, lane, numCorners));
+            p1 = rowMasks(loadRowValues(slice1, x0, lane, numCorners));
+        }
+#endif
         const uint32_t inRange = P.cellsX - x0 >= 32 ? 0xFFFFFFFFu : (active ? (1u << (P.cellsX - x0)) - 1 : 0u);
         // per corner row, combined over its four corners per cell column (x, x+1 of both slices):
         // all finite / all outside / any outside.  A cell row then needs five more operations.
@@ -324,8 +367,13 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
             uint32_t packed = 0, code = 0;
             if (active && (uint32_t) r < nRows)
             {
-                const RowMasks c0 = loadRowMasks(slice0 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners);
-                const RowMasks c1 = loadRowMasks(slice1 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners);
+#if MLSB_MC_PREFETCH
+                const RowMasks c0 = rowMasks(rv0[r + 1]);
+                const RowMasks c1 = rowMasks(rv1[r + 1]);
+#else
+                const RowMasks c0 = rowMasks(loadRowValues(slice0 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners));
+                const RowMasks c1 = rowMasks(loadRowValues(slice1 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners));
+#endif
                 const uint32_t cv = c0.f0 & c0.f1 & c1.f0 & c1.f1, ca = c0.s0 & c0.s1 & c1.s0 & c1.s1, co = c0.s0 | c0.s1 | c1.s0 | c1.s1;
                 const uint32_t occ = (pv & cv) & (po | co) & ~(pa & ca) & inRange;
                 if (occ)
@@ -442,10 +490,13 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
     const uint32_t iBase = (uint32_t) (P.tileTotals[tile] >> 31);
     if (P.counters[CTR_OVERFLOW]) return;   // the block did not fit: the host splits it and starts over
 
-    // ---- generateElements' index half + reindex (kernels/marching.cl:240-258, :334-340): one
-    // thread per index; the vertex it names is a lattice point, its welded index a rank ----
+    // ---- generateElements' index half + reindex (kernels/marching.cl:240-258, :334-340).  MLSB_MC_EMIT:
+    // 0 = one thread per index (binary search for its cell, table walk and record load for every index),
+    // 1 / 2 = one thread per occupied cell: it ranks the cell's <= 13 vertices once into its own column
+    // of shared memory (2: unrolled and predicated) and then writes the cell's indices from there ----
     const uint32_t numUnflagged = P.counters[CTR_UNFLAGGED];
     const uint32_t topX = 2 * P.cellsX, topY = 2 * P.cellsY;
+#if MLSB_MC_EMIT == 0
     for (uint32_t j = tid; j < numIdx; j += kGenThreads)
     {
         // last cell whose first index is <= j
@@ -459,23 +510,55 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
         const uint32_t x = cell & 0xFFFF, r = (cell >> 16) & 0xFF, code = cell >> 24;
         const uint32_t e = T.data[T.start[code][0] + T.data[T.start[code][1] + k]];
         const uint32_t a = T.edge[e][0], b = T.edge[e][1];
-        // computeKey(), :148-154: twice the cell plus the offsets of the edge's two corners
         const uint32_t x2 = 2 * x + (a & 1) + (b & 1);
         const uint32_t y2 = 2 * (y0 + r) + ((a >> 1) & 1) + ((b >> 1) & 1);
         const uint32_t z2 = 2 * (z - P.zFirst) + (a >> 2) + (b >> 2);
-        P.indices[iBase + j] = latticeRank(P.latMask, P.latPrefix, P.latStride, P.latRows, x2, y2, z2, topX, topY, numUnflagged);
+        P.indices[iBase + j] = latticeRank(P.latRecord, P.latStride, P.latRows, x2, y2, z2, topX, topY, numUnflagged);
     }
+#else
+    (void) numIdx;
+    uint32_t *const sRank = sList + 2 * kVRows * kGenThreads;   // [kMaxCellVertices][kGenThreads]
+    for (uint32_t ci = tid; ci < numCells; ci += kGenThreads)
+    {
+        const uint32_t cell = sCell[ci];
+        const uint32_t x = cell & 0xFFFF, r = (cell >> 16) & 0xFF, code = cell >> 24;
+        const uint32_t v0 = T.start[code][0], i0 = T.start[code][1];
+        const uint32_t nV = T.count[code][0], nI = T.count[code][1];
+#if MLSB_MC_EMIT == 2
+        // unrolled and predicated, so that the record loads of all vertices are in flight together
+#pragma unroll
+        for (uint32_t v = 0; v < kMaxCellVertices; v++)
+            if (v < nV)
+#else
+        for (uint32_t v = 0; v < nV; v++)
+#endif
+            {
+                const uint32_t e = T.data[v0 + v];
+                const uint32_t a = T.edge[e][0], b = T.edge[e][1];
+                // computeKey(), :148-154: twice the cell plus the offsets of the edge's two corners
+                const uint32_t x2 = 2 * x + (a & 1) + (b & 1);
+                const uint32_t y2 = 2 * (y0 + r) + ((a >> 1) & 1) + ((b >> 1) & 1);
+                const uint32_t z2 = 2 * (z - P.zFirst) + (a >> 2) + (b >> 2);
+                sRank[v * kGenThreads + tid] = latticeRank(P.latRecord, P.latStride, P.latRows, x2, y2, z2, topX, topY, numUnflagged);
+            }
+        uint32_t *const out = P.indices + iBase + sIloc[ci];
+        for (uint32_t k = 0; k < nI; k++) out[k] = sRank[(uint32_t) T.data[i0 + k] * kGenThreads + tid];
+    }
+#endif
 }
 
-// Exclusive scan of the tile totals (one CTA: at most ~33 k tiles), list of non-empty tiles,
-// grand totals -> counters.  The role of clogs::Scan(uint2) at src/marching.cpp:721.
-__global__ void __launch_bounds__(1024) scanTilesKernel(uint64_t *tileTotals, uint32_t *tileList, uint32_t numTiles,
-                                                        uint32_t *counters, uint32_t vertexSpace, uint32_t indexSpace)
+// Exclusive scan of the tile totals, list of non-empty tiles, grand totals -> counters: the role of
+// clogs::Scan(uint2) at src/marching.cpp:721.  Runs as ONE EXTRA CTA of the scanLattice launch (the lattice
+// scan does not need the tile bases, the index pass after it does), so it costs neither a launch
+// nor time of its own.
+__device__ void scanTiles(uint64_t *tileTotals, uint32_t *tileList, uint32_t numTiles, uint32_t *counters,
+                          uint32_t vertexSpace, uint32_t indexSpace)
 {
     __shared__ uint64_t sScan[33];
     __shared__ uint32_t sScan32[33];
-    const uint32_t per = (numTiles + 1023) / 1024;
-    const uint32_t first = threadIdx.x * per, last = min(first + per, numTiles);
+    const uint32_t threads = blockDim.x;
+    const uint32_t per = (numTiles + threads - 1) / threads;
+    const uint32_t first = min(threadIdx.x * per, numTiles), last = min(first + per, numTiles);
     uint64_t sum = 0, cells = 0;
     uint32_t nonEmpty = 0;
     for (uint32_t t = first; t < last; t++)
@@ -509,12 +592,12 @@ __global__ void __launch_bounds__(1024) scanTilesKernel(uint64_t *tileTotals, ui
 struct LatticeParams
 {
     const uint32_t *mask;
-    uint2 *prefix;
+    uint4 *record;                   // out, per non-empty word: (mask, unflagged before, flagged before, 0)
     uint32_t stride, rows, planes;   // words per row, rows (y2) per plane, planes (z2)
     uint32_t totalWords;
     uint32_t topX, topY;             // 2 * cellsX, 2 * cellsY
     uint32_t *counters;
-    volatile uint64_t *status;
+    volatile uint64_t *status;       // per 2048-word chunk: (unflagged | flagged << 32) vertex counts
     // emitVertices
     const float *field;
     uint32_t pitch, zStride, zFirst;
@@ -523,29 +606,88 @@ struct LatticeParams
     uint64_t *weldedKeys, *weldedKeysFlagged;
     uint64_t keyOffset;              // src/marching.cpp:594-599
     float scale, bx, by, bz;         // ScaleBiasFilter
+    uint32_t vertexSpace, indexSpace;
+    // the tile scan riding along (last CTA of the grid)
+    uint64_t *tileTotals;
+    uint32_t *tileList;
+    uint32_t numTiles;
 };
 
 constexpr int kLatThreads = 256;
 constexpr int kLatItems = 8;
 
-// countUniqueVertices + scan + compactVertices + scaleBiasVertices in one pass
-// (kernels/marching.cl:271-326, src/marching.cpp:721, kernels/scale_bias.cl:32-40): the exclusive
-// (unflagged, flagged) vertex counts in front of every non-empty lattice word, in key order, and
-// the vertices themselves.  A vertex is interpolated from the lower corner A = lattice >> 1 of its
-// edge along d = lattice & 1 — the corner order of the edge table — as interp() does (:130-138).
-// Flagged vertices follow ALL unflagged ones in the output; their count is only known at the end
-// of the scan, so they go to a buffer of their own and the readback concatenates the two.
-__global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P)
+// countUniqueVertices + scan + compactVertices + scaleBiasVertices (kernels/marching.cl:271-326,
+// src/marching.cpp:721, kernels/scale_bias.cl:32-40) in two launches without any waiting between
+// CTAs: latticeCountKernel leaves the (unflagged, flagged) vertex count of every 2048-word chunk of
+// the lattice, and every CTA of latticeEmitKernel adds up the counts of the chunks in front of its own
+// (at most ~2200 values from L2, 9 per thread) before it ranks and writes its vertices.  A decoupled
+// look-back in one launch measured slower: its chain is ~2000 tiles of a few microseconds each, and a
+// third of all warp stalls were spins on predecessors' status words.
+// A vertex is interpolated from the lower corner A = lattice >> 1 of its edge along d = lattice & 1 —
+// the corner order of the edge table — as interp() does (:130-138).  Flagged vertices follow ALL
+// unflagged ones in the output, so they go to a buffer of their own and the readback concatenates.
+__global__ void __launch_bounds__(kLatThreads) latticeCountKernel(LatticeParams P)
 {
     __shared__ uint64_t sScan[33];
-    __shared__ uint32_t sTile;
-    __shared__ uint64_t sPrefix;
-    if (P.counters[CTR_OVERFLOW]) return;   // the block did not fit: the host splits it and starts over
-    if (threadIdx.x == 0) sTile = atomicAdd(&P.counters[CTR_WELD_TICKET], 1u);
-    __syncthreads();
-    const uint32_t tile = sTile;
+    if (blockIdx.x == gridDim.x - 1)
+    {
+        scanTiles(P.tileTotals, P.tileList, P.numTiles, P.counters, P.vertexSpace, P.indexSpace);
+        return;
+    }
+    const uint32_t tile = blockIdx.x;
     const uint32_t base = tile * (kLatThreads * kLatItems) + threadIdx.x * kLatItems;
+    uint32_t wcol = base % P.stride, row = base / P.stride;
+    uint32_t y2 = row % P.rows, z2 = row / P.rows;
+    uint32_t nU = 0, nF = 0;
+    uint32_t m[kLatItems];
+#pragma unroll
+    for (int i = 0; i < kLatItems; i++) m[i] = base + i < P.totalWords ? P.mask[base + i] : 0u;
+#pragma unroll
+    for (int i = 0; i < kLatItems; i++)
+    {
+        if (m[i])
+        {
+            const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
+            nU += __popc(m[i] & ~fm);
+            nF += __popc(m[i] & fm);
+        }
+        if (++wcol == P.stride)
+        {
+            wcol = 0;
+            if (++y2 == P.rows)
+            {
+                y2 = 0;
+                z2++;
+            }
+        }
+    }
+    uint64_t total;
+    blockExclusiveScan((uint64_t) nU | ((uint64_t) nF << 32), sScan, &total);
+    if (threadIdx.x == 0) const_cast<uint64_t *>(P.status)[tile] = total;
+}
 
+__global__ void __launch_bounds__(kLatThreads) latticeEmitKernel(LatticeParams P, uint32_t numChunks)
+{
+    __shared__ uint64_t sScan[33];
+    __shared__ uint64_t sBefore;
+    const uint32_t tile = blockIdx.x;
+    const uint64_t *chunkCounts = const_cast<const uint64_t *>(P.status);
+    const uint64_t own = chunkCounts[tile];
+    const uint32_t lastPlane = (P.planes - 1) * P.rows * P.stride;   // its vertices are external, the ones before it are not
+    const uint32_t tileBase = tile * (kLatThreads * kLatItems);
+    const bool holdsLastPlane = tileBase <= lastPlane && lastPlane < tileBase + kLatThreads * kLatItems;
+    const bool holdsLastWord = tileBase < P.totalWords && P.totalWords <= tileBase + kLatThreads * kLatItems;
+    if (own == 0 && !holdsLastPlane && !holdsLastWord) return;   // nothing to rank, nothing to report: most chunks
+    // ---- vertices in front of this chunk: everyone adds up the counts of the chunks before it ----
+    {
+        uint64_t part = 0;
+        for (uint32_t t = threadIdx.x; t < tile; t += kLatThreads) part += chunkCounts[t];
+        uint64_t all;
+        blockExclusiveScan(part, sScan, &all);
+        if (threadIdx.x == 0) sBefore = all;
+        __syncthreads();
+    }
+    const uint32_t base = tileBase + threadIdx.x * kLatItems;
     const uint32_t row0 = base / P.stride, wcol0 = base % P.stride;
     const uint32_t y20 = row0 % P.rows, z20 = row0 / P.rows;
     uint32_t wcol = wcol0, y2 = y20, z2 = z20;
@@ -562,11 +704,11 @@ __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P
     };
     uint32_t m[kLatItems];
     uint32_t nU = 0, nF = 0, beforeLastPlane = 0;
-    const uint32_t lastPlane = (P.planes - 1) * P.rows * P.stride;   // its vertices are external, the ones before it are not
+#pragma unroll
+    for (int i = 0; i < kLatItems; i++) m[i] = base + i < P.totalWords ? P.mask[base + i] : 0u;
 #pragma unroll
     for (int i = 0; i < kLatItems; i++)
     {
-        m[i] = base + i < P.totalWords ? P.mask[base + i] : 0u;
         if (base + i == lastPlane) beforeLastPlane = nU;
         const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
         nU += __popc(m[i] & ~fm);
@@ -574,15 +716,9 @@ __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P
         advance();
     }
     uint64_t total;
-    const uint64_t excl = blockExclusiveScan((uint64_t) nU | ((uint64_t) nF << 31), sScan, &total);
-    if (threadIdx.x < 32)
-    {
-        const uint64_t p = lookbackExclusive(P.status, tile, total);
-        if (threadIdx.x == 0) sPrefix = p;
-    }
-    __syncthreads();
-    const uint64_t mine = sPrefix + excl;
-    uint32_t rankU = (uint32_t) (mine & 0x7FFFFFFFu), rankF = (uint32_t) (mine >> 31);
+    const uint64_t excl = blockExclusiveScan((uint64_t) nU | ((uint64_t) nF << 32), sScan, &total);
+    const uint64_t mine = sBefore + excl;
+    uint32_t rankU = (uint32_t) mine, rankF = (uint32_t) (mine >> 32);
     // internal vertices = unflagged ones in front of the last plane
     if (base <= lastPlane && lastPlane < base + kLatItems) P.counters[CTR_FIRST_EXTERNAL] = rankU + beforeLastPlane;
     if (base + kLatItems >= P.totalWords && base < P.totalWords)
@@ -597,10 +733,10 @@ __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P
     // work — two dependent field loads per vertex — to a handful of threads.) ----
     __shared__ uint32_t sMask[kLatThreads * kLatItems], sCount[kLatThreads * kLatItems];
     __shared__ uint32_t sRankU[kLatThreads * kLatItems], sRankF[kLatThreads * kLatItems];
-    const uint32_t tileVerts = (uint32_t) (total & 0x7FFFFFFFu) + (uint32_t) (total >> 31);
+    const uint32_t tileVerts = (uint32_t) total + (uint32_t) (total >> 32);
     if (tileVerts == 0) return;   // uniform over the CTA
     {
-        uint32_t c = (uint32_t) (excl & 0x7FFFFFFFu) + (uint32_t) (excl >> 31);
+        uint32_t c = (uint32_t) excl + (uint32_t) (excl >> 32);
         wcol = wcol0, y2 = y20, z2 = z20;
 #pragma unroll
         for (int i = 0; i < kLatItems; i++, advance())
@@ -612,7 +748,7 @@ __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P
             sRankF[l] = rankF;
             if (m[i])
             {
-                P.prefix[base + i] = make_uint2(rankU, rankF);
+                P.record[base + i] = make_uint4(m[i], rankU, rankF, 0u);
                 const uint32_t fm = latticeFlagMask(wcol, y2, z2, P.topX, P.topY);
                 const uint32_t f = __popc(m[i] & fm), u = __popc(m[i]) - f;
                 c += u + f;
@@ -622,7 +758,6 @@ __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P
         }
     }
     __syncthreads();
-    const uint32_t tileBase = tile * (kLatThreads * kLatItems);
     for (uint32_t j = threadIdx.x; j < tileVerts; j += kLatThreads)
     {
         // last word whose exclusive count is <= j (empty words share the count of their successor)
@@ -653,6 +788,7 @@ __global__ void __launch_bounds__(kLatThreads) scanLatticeKernel(LatticeParams P
         const float px = __fmaf_rn(t, (float) dx, (float) (ax + P.gridOffset.x));
         const float py = __fmaf_rn(t, (float) dy, (float) (ay + P.gridOffset.y));
         const float pz = __fmaf_rn(t, (float) dz, (float) (az + P.gridOffset.z));
+        if (rank >= P.vertexSpace) continue;   // the block does not fit: the host splits it and starts over
         float *const out = (flagged ? P.weldedFlagged : P.welded) + 3 * (size_t) rank;
         out[0] = __fmaf_rn(px, P.scale, P.bx);
         out[1] = __fmaf_rn(py, P.scale, P.by);
@@ -700,13 +836,16 @@ int marchingAlloc(mlsb_worker *w)
     w->latticeWords = (size_t) (2 * c.maxCells + 1) * (2 * c.maxCells + 1) * (2 * divUp(c.maxCells, 32u) + 1);
     MLSB_REQUIRE(w->latticeWords < (1ull << 32) - kLatThreads * kLatItems, MLSB_ERR_LENGTH, "lattice too large");
     MLSB_CUDA(cudaMalloc(&w->latMask, w->latticeWords * sizeof(uint32_t)));
-    MLSB_CUDA(cudaMalloc(&w->latPrefix, w->latticeWords * sizeof(uint2)));
+    MLSB_CUDA(cudaMalloc(&w->latRecord, w->latticeWords * sizeof(uint4)));
     MLSB_CUDA(cudaMalloc(&w->indices, (w->indexSpace + 1) * sizeof(uint32_t)));
     MLSB_CUDA(cudaMalloc(&w->welded, (w->vertexSpace + 1) * 3 * sizeof(float)));
     MLSB_CUDA(cudaMalloc(&w->weldedKeys, (w->vertexSpace + 1) * sizeof(uint64_t)));
     MLSB_CUDA(cudaMalloc(&w->weldedFlagged, (w->vertexSpace + 1) * 3 * sizeof(float)));
     MLSB_CUDA(cudaMalloc(&w->weldedKeysFlagged, (w->vertexSpace + 1) * sizeof(uint64_t)));
-    MLSB_CUDA(cudaMalloc(&w->marchCounters, CTR_COUNT * sizeof(uint32_t)));
+    // [counters | look-back words of the lattice scan]: one memset per block
+    w->latStatusWords = (uint32_t) divUp(w->latticeWords, (size_t) (kLatThreads * kLatItems)) + 2;
+    MLSB_CUDA(cudaMalloc(&w->marchCounters, CTR_COUNT * sizeof(uint32_t) + (size_t) w->latStatusWords * sizeof(uint64_t)));
+    w->latStatus = reinterpret_cast<uint64_t *>(w->marchCounters + CTR_COUNT);
     w->maxTiles = c.maxCells * divUp(c.maxCells, (uint32_t) kGenRows);
     MLSB_CUDA(cudaMalloc(&w->tileTotals, (size_t) w->maxTiles * sizeof(uint64_t)));
     MLSB_CUDA(cudaMalloc(&w->tileList, (size_t) w->maxTiles * sizeof(uint32_t)));
@@ -717,7 +856,7 @@ int marchingAlloc(mlsb_worker *w)
     MLSB_CUDA(cudaMallocHost(&w->hostBlob, w->hostBlobBytes));
     MLSB_CUDA(cudaMallocHost(&w->hostCounters, CTR_COUNT * sizeof(uint32_t)));
     MLSB_CUDA(cudaFuncSetAttribute(generateCellsKernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   2 * kGenRows * 2 * kGenThreads * (int) sizeof(uint32_t)));
+                                   (2 * kGenRows * 2 + (int) kMaxCellVertices) * kGenThreads * (int) sizeof(uint32_t)));
     return MLSB_OK;
 }
 
@@ -726,7 +865,7 @@ void marchingFree(mlsb_worker *w)
     cudaFree(w->field);
     cudaFree(w->blockActive);
     cudaFree(w->latMask);
-    cudaFree(w->latPrefix);
+    cudaFree(w->latRecord);
     cudaFree(w->indices);
     cudaFree(w->welded);
     cudaFree(w->weldedKeys);
@@ -758,11 +897,11 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     const uint32_t tiles = (zLast - zFirst) * divUp(cellsY, (uint32_t) kGenRows);
     const uint32_t chunks = divUp(cellsX, (uint32_t) kGenThreads);
     MLSB_REQUIRE(chunks <= 2, MLSB_ERR_LENGTH, "bin too wide");
-    const size_t genSmem = 2 * (size_t) kGenRows * chunks * kGenThreads * sizeof(uint32_t);
+    const size_t genSmem = (2 * (size_t) kGenRows * chunks + kMaxCellVertices) * kGenThreads * sizeof(uint32_t);
     const uint32_t latStride = 2 * divUp(cellsX, 32u) + 1, latRows = 2 * cellsY + 1, latPlanes = 2 * (zLast - zFirst) + 1;
     const size_t latWords = (size_t) latPlanes * latRows * latStride;
     const uint32_t latTiles = (uint32_t) divUp(latWords, (size_t) (kLatThreads * kLatItems));
-    MLSB_REQUIRE(latWords <= w->latticeWords && latTiles <= w->scanStatusWords && tiles <= w->maxTiles, MLSB_ERR_LENGTH,
+    MLSB_REQUIRE(latWords <= w->latticeWords && latTiles <= w->latStatusWords && tiles <= w->maxTiles, MLSB_ERR_LENGTH,
                  "scan scratch too small");
 
     GenParams G;
@@ -775,7 +914,7 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     G.indices = w->indices;
     G.counters = w->marchCounters;
     G.latMask = w->latMask;
-    G.latPrefix = w->latPrefix;
+    G.latRecord = w->latRecord;
     G.latStride = latStride;
     G.latRows = latRows;
     G.tileTotals = w->tileTotals;
@@ -786,7 +925,7 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
 
     LatticeParams L;
     L.mask = w->latMask;
-    L.prefix = w->latPrefix;
+    L.record = w->latRecord;
     L.stride = latStride;
     L.rows = latRows;
     L.planes = latPlanes;
@@ -794,7 +933,7 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     L.topX = 2 * cellsX;
     L.topY = 2 * cellsY;
     L.counters = w->marchCounters;
-    L.status = w->scanStatus;
+    L.status = w->latStatus;
     L.field = w->field;
     L.pitch = pitch;
     L.zStride = zStride;
@@ -810,12 +949,18 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     L.bx = w->bias[0];
     L.by = w->bias[1];
     L.bz = w->bias[2];
+    L.vertexSpace = (uint32_t) w->vertexSpace;
+    L.indexSpace = (uint32_t) w->indexSpace;
+    L.tileTotals = w->tileTotals;
+    L.tileList = w->tileList;
+    L.numTiles = tiles;
 
     {
         ScopedStat st(w, "kernel.marching.zero.time", 0);
+        // (writing the mask also leaves it in L2, where the classification's red.or find it: against a mask
+        // that cleans itself and is never memset the classify kernel ran 50 % longer on DRAM-resident lines)
         MLSB_CUDA(cudaMemsetAsync(w->marchCounters, 0, CTR_COUNT * sizeof(uint32_t), s));
         MLSB_CUDA(cudaMemsetAsync(w->latMask, 0, latWords * sizeof(uint32_t), s));
-        MLSB_CUDA(cudaMemsetAsync(w->scanStatus, 0, (size_t) latTiles * sizeof(uint64_t), s));
     }
     {
         ScopedStat st(w, "kernel.marching.genOccupied.time");
@@ -824,14 +969,14 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
         w->launches++;
     }
     {
-        ScopedStat st(w, "kernel.marching.scanElements.time");
-        scanTilesKernel<<<1, 1024, 0, s>>>(w->tileTotals, w->tileList, tiles, w->marchCounters, (uint32_t) w->vertexSpace,
-                                           (uint32_t) w->indexSpace);
+        // + 1: the CTA that scans the tile totals (kernel.marching.scanElements in the reference's vocabulary)
+        ScopedStat st(w, "kernel.marching.countUniqueVertices.time");
+        latticeCountKernel<<<latTiles + 1, kLatThreads, 0, s>>>(L);
         w->launches++;
     }
     {
         ScopedStat st(w, "kernel.marching.compactVertices.time");
-        scanLatticeKernel<<<latTiles, kLatThreads, 0, s>>>(L);
+        latticeEmitKernel<<<latTiles, kLatThreads, 0, s>>>(L, latTiles);
         w->launches++;
     }
     {
@@ -849,9 +994,14 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     }
     MLSB_TRY(waitStream(w));
     const uint32_t *hc = w->hostCounters;
+    w->marchWork[0] += (uint64_t) size[0] * size[1] * (zLast - zFirst + 1);
     if (hc[CTR_OVERFLOW] || hc[CTR_VERTS] > w->vertexSpace || hc[CTR_INDICES] > w->indexSpace) return MLSB_ERR_OVERFLOW;
     if (hc[CTR_VERTS] == 0) return MLSB_OK;
 
+    w->marchWork[1] += hc[CTR_CELLS];
+    w->marchWork[2] += hc[CTR_VERTS];
+    w->marchWork[3] += hc[CTR_INDICES];
+    w->marchWork[4] += hc[CTR_WELDED];
     mlsb_mesh_sizes sizes{hc[CTR_WELDED], hc[CTR_INDICES] / 3, hc[CTR_FIRST_EXTERNAL]};
     const uint64_t numExternal = sizes.numVertices - sizes.numInternalVertices;
     // unflagged vertices (internal, then the top plane) and flagged ones live in two buffers

@@ -1,14 +1,12 @@
 // Per-corner MLS field: MlsFunctor::enqueue (src/mls.cpp:101-135) and processCorners
 // (kernels/mls.cl:299-433), sphere and plane fits.
 //
-// One CTA per 8x8x8 block of corners, as in the reference, but 128 threads that each own FOUR
-// corners sharing (y, z):  dot3(p,p) = fma(px,px, fma(py,py, pz*pz)) (kernels/mls.cl:105-108),
-// so the inner fma(py,py,pz*pz) — and py, pz themselves — are computed once per splat per
-// thread and reused by the four corners.  A pair test therefore costs 3 FP32 instructions
-// (+4 shared by four corners) instead of the 7 of one-thread-per-corner, with bit-identical
-// results.  For each of a thread's four slots the 32 lanes of a warp cover a compact 2x4x4
-// brick of corners, which keeps the warp-level "any lane hit" rate — what the accumulation
-// cost is proportional to — low.
+// One CTA per 8x8x8 block of corners, as in the reference, but 256 threads that each own TWO
+// corners sharing (y, z) (MLSB_MLS_SLOTS = 2):  dot3(p,p) = fma(px,px, fma(py,py, pz*pz))
+// (kernels/mls.cl:105-108), so the inner fma(py,py,pz*pz) — and py, pz themselves — are computed
+// once per splat per thread and reused by both corners, with bit-identical results.  Each warp owns
+// a 4x4x4 brick of the block, walks the block's command chain on its own, and pair-tests only the
+// splats whose ball can reach its brick.
 //
 // Rounding contract (shared with oracle/orc_mls.c): every operation is written with an
 // explicit round-to-nearest intrinsic, fused only where the oracle fuses; the translation
@@ -47,6 +45,7 @@ struct MlsParams
     const mlsb_splat *splats;
     const int32_t *commands;
     const int32_t *start;
+    const float *thresholds;    // per splat hit threshold on |p|^2 (hitThreshold(), common.cuh) or nullptr
     float *field;
     uint32_t pitch;
     uint32_t startShift;
@@ -143,27 +142,9 @@ template <int SHAPE> __device__ __forceinline__ float finish(const Accum &f, flo
     return result;
 }
 
-// The hit test of kernels/mls.cl:373-374 is  d = pp * invr2;  d < 0.99f.  x -> RN(x * w) is
-// monotone for w > 0, so the set of pp >= 0 that pass is exactly { pp < T } for one float T per
-// splat: the smallest T with RN(T * w) >= 0.99f.  Comparing against T saves the multiply in the
-// pair test (d itself is only needed for a hit) without changing a single decision.
-// w = +0 (infinite radius) passes every finite pp: T = +inf.  w = +inf or NaN passes nothing: T = 0.
-__device__ __forceinline__ float hitThreshold(float w)
-{
-    if (!(w > 0.0f)) return w == 0.0f ? __uint_as_float(0x7F800000u) : 0.0f;
-    if (__float_as_uint(w) == 0x7F800000u) return 0.0f;
-    float t = __fdiv_rn(kRadiusCutoff, w);
-    if (!finite(t)) t = __uint_as_float(0x7F7FFFFFu);
-    for (int k = 0; k < 8 && t > 0.0f && __fmul_rn(t, w) >= kRadiusCutoff; k++) t = __uint_as_float(__float_as_uint(t) - 1);
-    for (int k = 0; k < 8 && __fmul_rn(t, w) < kRadiusCutoff; k++)
-    {
-        if (__float_as_uint(t) >= 0x7F7FFFFFu) return __uint_as_float(0x7F800000u);
-        t = __uint_as_float(__float_as_uint(t) + 1);
-    }
-    return t;
-}
-
-template <int SHAPE, bool COUNT>
+// PRE: the octree build left every splat's hit threshold in P.thresholds; otherwise (buffers bound by
+// mlsb_mls_set_buffers) the kernel derives it from 1/r^2 for every splat it keeps.
+template <int SHAPE, bool COUNT, bool PRE>
 __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKernel(MlsParams P)
 {
     // per-warp staging buffers for the splats that survive the cull
@@ -223,6 +204,7 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
         // batch may span several ranges; the per-corner visit order is still the chain order. ----
         int32_t end = P.commands[pos++];
         float4 rPos = make_float4(0.f, 0.f, 0.f, 0.f), rNq = rPos;
+        float rThr = 0.0f;
         bool rHave = false;
         int nextCount = 0;
         // one-deep software pipeline: batch k+1 is in flight while batch k is processed (a two-deep
@@ -251,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
                 const float4 *sp = reinterpret_cast<const float4 *>(P.splats + id);
                 rPos = __ldg(sp);
                 rNq = __ldg(sp + 1);
+                if (PRE) rThr = __ldg(P.thresholds + id);
             }
         };
 
@@ -274,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
             if (keep)
             {
                 const int p = __popc(m & ((1u << lane) - 1));
-                wPosT[p] = make_float4(rPos.x, rPos.y, rPos.z, hitThreshold(rPos.w));
+                wPosT[p] = make_float4(rPos.x, rPos.y, rPos.z, PRE ? rThr : hitThreshold(rPos.w));
                 wNormQ[p] = rNq;
                 wInvR[p] = rPos.w;
             }
@@ -495,6 +478,7 @@ int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &
     P.splats = w->mlsSplats;
     P.commands = w->mlsCommands;
     P.start = w->mlsStart;
+    P.thresholds = w->mlsThresholds;
     P.field = field;
     P.pitch = pitch;
     P.startShift = w->mlsStartShift;
@@ -516,16 +500,17 @@ int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &
         MLSB_CUDA(cudaStreamWaitEvent(w->mlsStream, w->mlsBefore, 0));
         s = w->mlsStream;
     }
-    if (w->cfg.shape == MLSB_SHAPE_SPHERE)
-    {
-        if (count) processCornersKernel<MLSB_SHAPE_SPHERE, true><<<grid, kThreads, 0, s>>>(P);
-        else processCornersKernel<MLSB_SHAPE_SPHERE, false><<<grid, kThreads, 0, s>>>(P);
-    }
-    else
-    {
-        if (count) processCornersKernel<MLSB_SHAPE_PLANE, true><<<grid, kThreads, 0, s>>>(P);
-        else processCornersKernel<MLSB_SHAPE_PLANE, false><<<grid, kThreads, 0, s>>>(P);
-    }
+    const bool pre = P.thresholds != nullptr;
+#define MLSB_LAUNCH(SHAPE)                                                                                  \
+    do {                                                                                                    \
+        if (count && pre) processCornersKernel<SHAPE, true, true><<<grid, kThreads, 0, s>>>(P);             \
+        else if (count) processCornersKernel<SHAPE, true, false><<<grid, kThreads, 0, s>>>(P);              \
+        else if (pre) processCornersKernel<SHAPE, false, true><<<grid, kThreads, 0, s>>>(P);                \
+        else processCornersKernel<SHAPE, false, false><<<grid, kThreads, 0, s>>>(P);                        \
+    } while (0)
+    if (w->cfg.shape == MLSB_SHAPE_SPHERE) MLSB_LAUNCH(MLSB_SHAPE_SPHERE);
+    else MLSB_LAUNCH(MLSB_SHAPE_PLANE);
+#undef MLSB_LAUNCH
     w->launches++;
     MLSB_CUDA(cudaGetLastError());
     if (w->mlsStream)

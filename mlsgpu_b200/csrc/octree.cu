@@ -12,9 +12,22 @@
 //                 (each cell finds its nearest non-empty ancestor directly, so the six
 //                 level-serial launches of src/splat_tree_cl.cpp:320-331 collapse into one)
 //
+// With the default six levels the key space (37 449 cells) fits the shared memory of one cluster and the build is
+// four launches and one memset ("planned" path below):
+//
+//   writeEntriesFused   splats read ONCE: candidates, tile base by decoupled look-back, packed
+//                       (key, id) pairs, 1/r^2 and the MLS hit threshold per splat, and the number of
+//                       entries of every key (warp-aggregated atomics)
+//   planKernel          one thread-block cluster (8 CTAs, distributed shared memory) over the key counts: run starts, run indices, start[], the
+//                       end/jump slots of every range AND the ancestor links, plus the sort's digit
+//                       histograms — none of it needs the sorted entries
+//   sort pass(es)       the last one writes the command list directly (no sorted pairs, no emit pass)
+//
+// Deeper octrees (levels > 6: the reference's tests use 8 and 9) take the general path further down.
 // The resulting start[] and commands[] arrays are bit-identical to the reference's.
 #include "common.cuh"
 #include "scan.cuh"
+#include <cooperative_groups.h>
 
 namespace mlsb
 {
@@ -111,36 +124,54 @@ __device__ __forceinline__ uint32_t splatEntries(const float4 pr, const int3 bia
 
 // The reference writes exactly 8 (key, id) slots per splat, UINT_MAX in the rejected ones, and sorts
 // all 8N.  Here only the accepted entries are written, packed in (splat, slot) order, and their
-// number goes to *numValid: the sort, the run detection and the command emission then touch 2-4x
-// fewer elements, with identical results (rejected slots sort to the end and are skipped by
-// writeSplatIds, kernels/octree.cl:266).  Three launches, none of which waits on another CTA:
-// EMIT = false counts per 256-splat tile, scanCountsKernel turns the counts into bases, EMIT = true
-// recomputes the (cheap) candidates and writes them.
-template <bool EMIT>
-__global__ void __launch_bounds__(256) writeEntriesKernel(uint32_t *__restrict__ keys, uint32_t *__restrict__ values,
-                                                          mlsb_splat *__restrict__ splats, int3 bias, LevelInfo lv,
-                                                          uint32_t firstSplat, uint32_t numSplats,
-                                                          uint32_t *__restrict__ tileCounts)
+// number goes to counters[1]: the sort and the command emission then touch 2-4x fewer elements, with
+// identical results (rejected slots sort to the end and are skipped by writeSplatIds,
+// kernels/octree.cl:266).  One launch: a tile of 256 splats computes its candidates, obtains its base
+// with a decoupled look-back over the tiles in front of it (tiles are numbered by an atomic ticket,
+// so every predecessor is running) and writes.  keyCount != nullptr: entries per key as well, one
+// atomic per distinct key and warp.
+__global__ void __launch_bounds__(256) writeEntriesFusedKernel(uint32_t *__restrict__ keys, uint32_t *__restrict__ values,
+                                                               mlsb_splat *__restrict__ splats, float *__restrict__ thresholds,
+                                                               int3 bias, LevelInfo lv, uint32_t firstSplat, uint32_t numSplats,
+                                                               volatile uint64_t *status, uint32_t *counters,
+                                                               uint32_t *__restrict__ keyCount)
 {
     __shared__ uint32_t sScan[33];
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint64_t sRed[33];
+    __shared__ uint32_t sFirst[33];
+    __shared__ uint32_t sTile;
+    if (threadIdx.x == 0) sTile = atomicAdd(&counters[0], 1u);
+    __syncthreads();
+    const uint32_t tile = sTile;
+    const uint32_t g = tile * blockDim.x + threadIdx.x;
     uint32_t k[8];
     uint32_t cnt = 0;
     const uint32_t gid = g + firstSplat;
+#pragma unroll
+    for (int o = 0; o < 8; o++) k[o] = 0xFFFFFFFFu;
     if (g < numSplats)
     {
         const float4 pr = *reinterpret_cast<const float4 *>(&splats[gid]);
-        cnt = splatEntries<EMIT>(pr, bias, lv, k);
-        if (EMIT) splats[gid].radius = __fdiv_rn(1.0f, __fmul_rn(pr.w, pr.w));   // kernels/octree.cl:193
+        cnt = splatEntries<true>(pr, bias, lv, k);
+        const float invR2 = __fdiv_rn(1.0f, __fmul_rn(pr.w, pr.w));
+        splats[gid].radius = invR2;   // kernels/octree.cl:193
+        thresholds[gid] = hitThreshold(invR2);
+    }
+    if (keyCount != nullptr)
+    {
+        const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+        for (int o = 0; o < 8; o++)
+        {
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, k[o]);
+            if (k[o] != 0xFFFFFFFFu && lane == (uint32_t) __ffs(peers) - 1) atomicAdd(&keyCount[k[o]], (uint32_t) __popc(peers));
+        }
     }
     uint32_t total;
     const uint32_t excl = blockExclusiveScan(cnt, sScan, &total);
-    if (!EMIT)
-    {
-        if (threadIdx.x == 0) tileCounts[blockIdx.x] = total;
-        return;
-    }
-    uint32_t dst = tileCounts[blockIdx.x] + excl;
+    const uint32_t base = (uint32_t) lookbackExclusiveBlock(status, tile, total, sRed, sFirst);
+    if ((tile + 1) * blockDim.x >= numSplats && tile * blockDim.x < numSplats && threadIdx.x == 0) counters[1] = base + total;
+    uint32_t dst = base + excl;
     if (cnt)
     {
 #pragma unroll
@@ -154,23 +185,132 @@ __global__ void __launch_bounds__(256) writeEntriesKernel(uint32_t *__restrict__
     }
 }
 
-// In-place exclusive scan of n per-tile counts by one CTA; the grand total goes to *total.
-__global__ void __launch_bounds__(1024) scanCountsKernel(uint32_t *counts, uint32_t n, uint32_t *total)
+// Everything the command list needs except the splat ids, from the per-key entry counts alone, by one
+// cluster that holds the key space in (distributed) shared memory (numStart <= kPlanMaxKeys):
+//   runStart[key] = (entries of smaller keys) + 2 * (non-empty smaller keys)     slot of the range's `end` pointer
+//   jump slot     = runStart + count + 1                                        kernels/octree.cl:256-279
+//   start[], commands[runStart] = jump slot, commands[jump slot] = nearest non-empty ancestor's
+//   runStart or -1                                                              kernels/octree.cl:292-341
+//   runIndex[key] (the sort's last pass places id i of the sorted order at 1 + i + 2 * runIndex[key])
+//   digit histograms of the radix passes, hist[p][256]
+// One SM cannot do it fast enough (160 k warp instructions: 20 us of issue slots on one SM), so the
+// key space is spread over a thread-block CLUSTER of eight CTAs: every CTA keeps the run starts of
+// its 1/8 of the keys in its own shared memory, the exclusive totals of the CTAs in front and the
+// run starts of ancestors in other CTAs' ranges are read through distributed shared memory, and
+// the three phases are separated by the cluster's hardware barrier — no global scratch, no
+// second launch.
+constexpr int kPlanCluster = 8;
+constexpr int kPlanThreads = 1024;
+constexpr int kPlanPer = 5;                                                     // keys per thread
+constexpr uint32_t kPlanChunkMax = kPlanThreads * kPlanPer;                     // keys per CTA
+constexpr uint32_t kPlanMaxKeys = kPlanCluster * kPlanChunkMax;                 // 40 960 >= 37 449 (six levels)
+__global__ void __cluster_dims__(kPlanCluster, 1, 1) __launch_bounds__(kPlanThreads)
+planKernel(uint32_t *__restrict__ keyCount, uint32_t numStart, LevelInfo lv, uint32_t bits, uint32_t *__restrict__ runIndex,
+           int32_t *__restrict__ start, int32_t *__restrict__ commands, uint32_t *__restrict__ hist, uint32_t *numValid)
 {
-    __shared__ uint32_t sScan[33];
-    const uint32_t per = (n + 1023) / 1024;
-    const uint32_t first = threadIdx.x * per, last = min(first + per, n);
-    uint32_t sum = 0;
-    for (uint32_t i = first; i < last; i++) sum += counts[i];
-    uint32_t all;
-    uint32_t base = blockExclusiveScan(sum, sScan, &all);
-    for (uint32_t i = first; i < last; i++)
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ uint32_t sRun[kPlanChunkMax];   // entry counts, then the run start of every key of this CTA (0xFFFFFFFF = empty)
+    __shared__ uint32_t sHist[2 * 256];
+    __shared__ uint64_t sScan[33];
+    __shared__ uint64_t sTotal;                // this CTA's (entries | runs << 32), read by the CTAs behind it
+    const uint32_t tid = threadIdx.x, rank = cluster.block_rank();
+    const uint32_t chunk = (numStart + kPlanCluster - 1) / kPlanCluster;   // keys per CTA
+    const uint32_t base = min(rank * chunk, numStart), count = min(base + chunk, numStart) - base;
+    if (tid < 512) sHist[tid] = 0;
+    // counts: key base + i * 1024 + tid in register c[i] — coalesced, all loads in flight at once
+    uint32_t c[kPlanPer];
+#pragma unroll
+    for (int i = 0; i < kPlanPer; i++)
     {
-        const uint32_t c = counts[i];
-        counts[i] = base;
-        base += c;
+        const uint32_t k = i * kPlanThreads + tid;
+        c[i] = k < count ? keyCount[base + k] : 0u;
     }
-    if (threadIdx.x == 0) *total = all;
+#pragma unroll
+    for (int i = 0; i < kPlanPer; i++)
+    {
+        const uint32_t k = i * kPlanThreads + tid;
+        if (k < count) sRun[k] = c[i];
+    }
+    __syncthreads();
+    // the scan runs over consecutive keys per thread, out of shared memory
+    const uint32_t per = (count + kPlanThreads - 1) / kPlanThreads;
+    const uint32_t first = min(tid * per, count), last = min(first + per, count);
+    const uint32_t mask0 = bits >= 8 ? 0xFFu : (1u << bits) - 1;
+    const uint32_t mask1 = bits > 8 ? (1u << min(bits - 8, 8u)) - 1 : 0u;
+    uint32_t entries = 0, runs = 0;
+    for (uint32_t k = first; k < last; k++)
+    {
+        const uint32_t n = sRun[k], key = base + k;
+        if (n)
+        {
+            entries += n;
+            runs++;
+            atomicAdd(&sHist[key & mask0], n);
+            if (bits > 8) atomicAdd(&sHist[256 + ((key >> 8) & mask1)], n);
+        }
+    }
+    uint64_t total;
+    const uint64_t excl = blockExclusiveScan((uint64_t) entries | ((uint64_t) runs << 32), sScan, &total);
+    if (tid == 0) sTotal = total;
+    cluster.sync();
+    uint64_t before = 0, all = 0;
+    for (uint32_t r = 0; r < kPlanCluster; r++)
+    {
+        const uint64_t t = *cluster.map_shared_rank(&sTotal, r);
+        all += t;
+        if (r < rank) before += t;
+    }
+    uint32_t e = (uint32_t) (excl + before), r = (uint32_t) ((excl + before) >> 32);
+    for (uint32_t k = first; k < last; k++)
+    {
+        const uint32_t n = sRun[k];
+        if (n)
+        {
+            runIndex[base + k] = r;   // only read for keys that have entries: a few thousand scattered stores
+            sRun[k] = e + 2 * r;
+            e += n;
+            r++;
+        }
+        else
+            sRun[k] = 0xFFFFFFFFu;
+    }
+    cluster.sync();
+#pragma unroll
+    for (int i = 0; i < kPlanPer; i++)
+    {
+        const uint32_t k = i * kPlanThreads + tid;
+        if (k >= count) continue;
+        const uint32_t pos = base + k;
+        // which level does this key belong to?  offsets grow from the finest level (minShift)
+        uint32_t level = lv.minShift;
+        while (level < lv.maxShift && pos >= lv.offsets[level + 1]) level++;
+        // nearest non-empty strict ancestor; the coarser levels live in the last CTAs of the cluster
+        int32_t prev = -1;
+        uint32_t l = level, code = pos - lv.offsets[level];
+        while (l < lv.maxShift)
+        {
+            l++;
+            code >>= 3;
+            const uint32_t idx = lv.offsets[l] + code, owner = idx / chunk;
+            const uint32_t a = cluster.map_shared_rank(sRun, owner)[idx - owner * chunk];
+            if (a != 0xFFFFFFFFu) { prev = (int32_t) a; break; }
+        }
+        if (c[i])
+        {
+            const uint32_t s = sRun[k];
+            const int32_t jp = (int32_t) (s + c[i] + 1);
+            commands[jp] = prev;
+            commands[s] = jp;
+            start[pos] = (int32_t) s;
+            keyCount[pos] = 0;   // clean for the next build: no memset of the counts
+        }
+        else
+            start[pos] = prev;
+    }
+    if (tid < 512 && sHist[tid]) atomicAdd(&hist[tid], sHist[tid]);   // hist was zeroed with the sort's scratch
+    if (rank == 0 && tid == 0) *numValid = (uint32_t) all;
+    cluster.sync();   // no CTA may leave while its shared memory can still be read
 }
 
 // First and last sorted position of each key (boundaries of equal-key runs).
@@ -307,17 +447,36 @@ int octreeAlloc(mlsb_worker *w)
                  "octree too large");
     w->numStartMax = (uint32_t) maxStart;
     w->numCommandsMax = (uint32_t) (maxEntries + 2 * maxRanges);
+    const bool planned = maxStart <= kPlanMaxKeys;
     MLSB_CUDA(cudaMalloc(&w->start, maxStart * sizeof(int32_t)));
-    MLSB_CUDA(cudaMalloc(&w->runStart, maxStart * sizeof(int32_t)));
-    MLSB_CUDA(cudaMalloc(&w->jumpPos, maxStart * sizeof(int32_t)));
-    MLSB_CUDA(cudaMalloc(&w->runFirst, maxStart * sizeof(int32_t)));
-    MLSB_CUDA(cudaMalloc(&w->runLast, maxStart * sizeof(int32_t)));
     MLSB_CUDA(cudaMalloc(&w->runIndex, maxStart * sizeof(uint32_t)));
+    if (!planned)
+    {
+        MLSB_CUDA(cudaMalloc(&w->runStart, maxStart * sizeof(int32_t)));
+        MLSB_CUDA(cudaMalloc(&w->jumpPos, maxStart * sizeof(int32_t)));
+        MLSB_CUDA(cudaMalloc(&w->runFirst, maxStart * sizeof(int32_t)));
+        MLSB_CUDA(cudaMalloc(&w->runLast, maxStart * sizeof(int32_t)));
+    }
     MLSB_CUDA(cudaMalloc(&w->commands, (size_t) w->numCommandsMax * sizeof(int32_t)));
+    MLSB_CUDA(cudaMalloc(&w->hitThresholds, (size_t) c.maxSplats * sizeof(float)));
     for (int i = 0; i < 2; i++)
     {
         MLSB_CUDA(cudaMalloc(&w->entryKeys[i], (maxEntries + 8) * sizeof(uint32_t)));
         MLSB_CUDA(cudaMalloc(&w->entryValues[i], (maxEntries + 8) * sizeof(uint32_t)));
+    }
+    // [key counts | entry tile status | {ticket, numValid}] sit in front of the sort's scratch, in its allocation;
+    // everything from the entry status on is zeroed by one memset per build, the key counts once, here
+    w->entryTilesMax = divUp(c.maxSplats, 256u) + 1;
+    const size_t statusBytes = roundUp((size_t) w->entryTilesMax * sizeof(uint64_t), (size_t) 256);
+    const size_t countBytes = planned ? roundUp((size_t) maxStart * sizeof(uint32_t), (size_t) 256) : 0;
+    void *prefix = nullptr;
+    MLSB_TRY(sortScratchAlloc(w->sort, maxEntries, 4, countBytes + statusBytes + 256, &prefix));
+    w->keyCount = planned ? static_cast<uint32_t *>(prefix) : nullptr;
+    w->entryStatus = reinterpret_cast<uint64_t *>(static_cast<char *>(prefix) + countBytes);
+    w->entryCounters = reinterpret_cast<uint32_t *>(static_cast<char *>(prefix) + countBytes + statusBytes);
+    if (planned)
+    {
+        MLSB_CUDA(cudaMemset(w->keyCount, 0, countBytes));
     }
     return MLSB_OK;
 }
@@ -331,11 +490,13 @@ void octreeFree(mlsb_worker *w)
     cudaFree(w->runLast);
     cudaFree(w->runIndex);
     cudaFree(w->commands);
+    cudaFree(w->hitThresholds);
     for (int i = 0; i < 2; i++)
     {
         cudaFree(w->entryKeys[i]);
         cudaFree(w->entryValues[i]);
     }
+    sortScratchFree(w->sort);
 }
 
 int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const int32_t offset[3],
@@ -359,26 +520,55 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
     w->numStart = numStart;
     cudaStream_t s = w->stream;
     const uint32_t numEntries = numSplats * 8;
+    const uint32_t bits = 3 * (maxShift - minShift) + 1;
+    const uint32_t passes = divUp(bits, 8u);
+    const bool planned = w->keyCount != nullptr && numStart <= kPlanMaxKeys && passes <= 2;
+    const uint32_t tiles = divUp(numSplats, 256u);
+    MLSB_REQUIRE(tiles <= w->entryTilesMax, MLSB_ERR_LENGTH, "entry scratch too small");
+    const int3 bias = make_int3(offset[0], offset[1], offset[2]);
+    uint32_t *numValid = w->entryCounters + 1;   // device-side count of accepted entries
 
-    if (numSplats > 0)
+    if (planned)
     {
         {
-            ScopedStat st(w, "kernel.octree.writeEntries.time");
-            const uint32_t tiles = divUp(numSplats, 256u);
-            MLSB_REQUIRE(tiles <= 2 * w->scanStatusWords, MLSB_ERR_LENGTH, "scan scratch too small");
-            uint32_t *tileCounts = reinterpret_cast<uint32_t *>(w->scanStatus);
-            const int3 bias = make_int3(offset[0], offset[1], offset[2]);
-            writeEntriesKernel<false><<<tiles, 256, 0, s>>>(nullptr, nullptr, w->splats, bias, lv, firstSplat, numSplats, tileCounts);
-            scanCountsKernel<<<1, 1024, 0, s>>>(tileCounts, tiles, w->scanTicket + 2);
-            writeEntriesKernel<true><<<tiles, 256, 0, s>>>(w->entryKeys[0], w->entryValues[0], w->splats, bias, lv, firstSplat,
-                                                          numSplats, tileCounts);
+            // one memset: the entry tiles' look-back words and counters and, behind them in the allocation,
+            // the sort's histograms, tickets and status.  The key counts are cleaned by planKernel itself.
+            ScopedStat st(w, "kernel.octree.fill.time", 0);
+            const size_t prefixBytes = reinterpret_cast<char *>(w->sort.hist) - reinterpret_cast<char *>(w->entryStatus);
+            const size_t sortBytes = numEntries ? sortScratchBytesUsed(w->sort, numEntries, passes) : 0;
+            MLSB_CUDA(cudaMemsetAsync(w->entryStatus, 0, prefixBytes + sortBytes, s));
         }
+        if (numSplats > 0)
+        {
+            ScopedStat st(w, "kernel.octree.writeEntries.time");
+            writeEntriesFusedKernel<<<tiles, 256, 0, s>>>(w->entryKeys[0], w->entryValues[0], w->splats, w->hitThresholds, bias, lv,
+                                                          firstSplat, numSplats, w->entryStatus, w->entryCounters, w->keyCount);
+        }
+        {
+            ScopedStat st(w, "kernel.octree.scan.time");
+            planKernel<<<kPlanCluster, kPlanThreads, 0, s>>>(w->keyCount, numStart, lv, bits, w->runIndex, w->start, w->commands,
+                                                              w->sort.hist, numValid);
+        }
+        if (numSplats > 0)
+            MLSB_TRY(radixSortToCommands(w, w->entryKeys, w->entryValues, numEntries, numValid, bits, w->commands, w->runIndex,
+                                         "kernel.octree.sort.time"));
+        w->launches += (numSplats > 0 ? 1 : 0) + 1;
+        MLSB_CUDA(cudaGetLastError());
+        return MLSB_OK;
+    }
+
+    // ---- general path: any number of levels ----
+    {
+        ScopedStat st(w, "kernel.octree.writeEntries.time");
+        const size_t prefixBytes = reinterpret_cast<char *>(w->entryCounters + 64) - reinterpret_cast<char *>(w->entryStatus);
+        MLSB_CUDA(cudaMemsetAsync(w->entryStatus, 0, prefixBytes, s));
+        if (numSplats > 0)
+            writeEntriesFusedKernel<<<tiles, 256, 0, s>>>(w->entryKeys[0], w->entryValues[0], w->splats, w->hitThresholds, bias, lv,
+                                                          firstSplat, numSplats, w->entryStatus, w->entryCounters, nullptr);
     }
     int cur = 0;
-    if (numSplats == 0) MLSB_CUDA(cudaMemsetAsync(w->scanTicket, 0, 4 * sizeof(uint32_t), s));
-    const uint32_t *numValid = w->scanTicket + 2;   // device-side count of accepted entries
     MLSB_TRY(radixSortPairsDeviceCount(w, w->entryKeys, w->entryValues, numEntries, numValid,
-                                       3 * (maxShift - minShift) + 1, &cur, "kernel.octree.sort.time", false));
+                                       bits, &cur, "kernel.octree.sort.time", false));
     {
         ScopedStat st(w, "kernel.octree.fill.time", 0);
         MLSB_CUDA(cudaMemsetAsync(w->runFirst, 0xFF, (size_t) numStart * sizeof(int32_t), s));
@@ -390,12 +580,12 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
     }
     {
         ScopedStat st(w, "kernel.octree.scan.time");
-        uint32_t tiles = divUp(numStart, (uint32_t) (kScanThreads * kScanItems));
-        MLSB_REQUIRE(tiles <= w->scanStatusWords, MLSB_ERR_LENGTH, "scan status too small");
-        MLSB_CUDA(cudaMemsetAsync(w->scanStatus, 0, (size_t) tiles * sizeof(uint64_t), s));
-        MLSB_CUDA(cudaMemsetAsync(w->scanTicket, 0, sizeof(uint32_t), s));   // ticket 0 only: [2] holds numValid
-        scanRunsKernel<<<tiles, kScanThreads, 0, s>>>(w->runFirst, w->runLast, numStart, w->runIndex, w->runStart,
-                                                      w->jumpPos, w->scanStatus, w->scanTicket);
+        uint32_t scanTiles = divUp(numStart, (uint32_t) (kScanThreads * kScanItems));
+        MLSB_REQUIRE(scanTiles <= w->scanStatusWords, MLSB_ERR_LENGTH, "scan status too small");
+        MLSB_CUDA(cudaMemsetAsync(w->scanStatus, 0, (size_t) scanTiles * sizeof(uint64_t), s));
+        MLSB_CUDA(cudaMemsetAsync(w->scanTicket, 0, sizeof(uint32_t), s));
+        scanRunsKernel<<<scanTiles, kScanThreads, 0, s>>>(w->runFirst, w->runLast, numStart, w->runIndex, w->runStart,
+                                                          w->jumpPos, w->scanStatus, w->scanTicket);
     }
     if (numEntries > 0)
     {
@@ -407,7 +597,7 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
         ScopedStat st(w, "kernel.octree.writeStart.time");
         linkLevelsKernel<<<divUp(numStart, 256u), 256, 0, s>>>(w->start, w->commands, w->runStart, w->jumpPos, lv, numStart);
     }
-    w->launches += (numSplats > 0 ? 5 : 0) + 2;
+    w->launches += (numSplats > 0 ? 3 : 0) + 2;
     MLSB_CUDA(cudaGetLastError());
     return MLSB_OK;
 }

@@ -91,4 +91,46 @@ __device__ __forceinline__ uint64_t lookbackExclusive(volatile uint64_t *status,
     return exclusive;
 }
 
+// The same for a whole thread block (blockDim.x a multiple of 32, at most 1024): every hop inspects
+// blockDim.x predecessors instead of 32, so a tile in a chain of thousands of short tiles needs a
+// handful of round trips to global memory instead of a hundred (with all tiles resident at once the
+// aggregates are there almost immediately, and what a tile waits for is its own walk back).
+// Must be called by ALL threads of the block; sRed needs 33 elements, sFirst 33.
+__device__ __forceinline__ uint64_t lookbackExclusiveBlock(volatile uint64_t *status, uint32_t tile, uint64_t aggregate,
+                                                           uint64_t *sRed, uint32_t *sFirst)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (tile == 0)
+    {
+        if (tid == 0) status[0] = kFlagPrefix | aggregate;
+        return 0;
+    }
+    if (tid == 0) status[tile] = kFlagAggregate | aggregate;
+    uint64_t exclusive = 0;
+    int base = (int) tile - 1;
+    while (true)
+    {
+        const int t = base - (int) tid;
+        uint64_t v = kFlagPrefix;   // virtual tiles before 0: empty prefix
+        if (t >= 0)
+        {
+            do { v = loadStatus(status + t); } while ((v & kFlagMask) == 0);
+        }
+        const unsigned pm = __ballot_sync(0xFFFFFFFFu, (v & kFlagMask) == kFlagPrefix);
+        __syncthreads();   // sFirst / sRed free again
+        if (lane == 0) sFirst[warp] = pm ? warp * 32 + __ffs(pm) - 1 : 0xFFFFFFFFu;
+        __syncthreads();
+        uint32_t first = 0xFFFFFFFFu;
+        for (uint32_t w = 0; w < nwarps; w++) first = min(first, sFirst[w]);
+        const uint64_t part = warpSum(tid <= first ? (v & ~kFlagMask) : 0ull);
+        if (lane == 0) sRed[warp] = part;
+        __syncthreads();
+        for (uint32_t w = 0; w < nwarps; w++) exclusive += sRed[w];
+        if (first != 0xFFFFFFFFu) break;
+        base -= (int) blockDim.x;
+    }
+    if (tid == 0) status[tile] = kFlagPrefix | (exclusive + aggregate);
+    return exclusive;
+}
+
 }  // namespace mlsb

@@ -49,7 +49,10 @@ __global__ void __launch_bounds__(256) sortHistogramKernel(const uint32_t *__res
 // THREADS = 256 (4096-key tiles: plenty of CTAs for the ~1 M-element sorts of a typical bin) or
 // 1024 (16384-key tiles, one CTA per SM: with hundreds of small tiles in flight the look-back chain
 // — one status word per tile and digit — becomes the bottleneck of multi-million-element sorts).
-template <int THREADS> __global__ void __launch_bounds__(THREADS)
+// EMIT: the last pass of the octree's entry sort writes the command list instead of the sorted pairs
+// (writeSplatIds, kernels/octree.cl:256-279): commands[1 + position + 2 * runIndex[key]] = value, with
+// keysOut = the int32 command buffer and valsOut = runIndex.
+template <int THREADS, bool EMIT> __global__ void __launch_bounds__(THREADS)
 sortOnesweepKernel(const uint32_t *__restrict__ keysIn, const uint32_t *__restrict__ valsIn,
                    uint32_t *__restrict__ keysOut, uint32_t *__restrict__ valsOut, uint32_t nHost,
                    const uint32_t *__restrict__ nDev, uint32_t shift, uint32_t mask, const uint32_t *__restrict__ hist,
@@ -136,23 +139,26 @@ sortOnesweepKernel(const uint32_t *__restrict__ keysIn, const uint32_t *__restri
     else
     {
         *st = kStFlagAggregate | tileCount;
-        // walk back over the predecessors, four status words in flight at a time
+        // walk back over the predecessors, kLookBack status words in flight at a time: with every
+        // tile of a small sort resident at once the aggregates are there within microseconds, and what
+        // the last tile waits for is its own walk (132 tiles: 33 dependent round trips at 4 in flight)
+        constexpr int kLookBack = 16;
         int t = (int) tile - 1;
         bool done = false;
         while (!done)
         {
-            uint32_t v[4];
+            uint32_t v[kLookBack];
 #pragma unroll
-            for (int k = 0; k < 4; k++) v[k] = t - k >= 0 ? status[(size_t) (t - k) * kRadix + d] : (2u << 30) /* empty prefix */;
+            for (int k = 0; k < kLookBack; k++) v[k] = t - k >= 0 ? status[(size_t) (t - k) * kRadix + d] : (2u << 30) /* empty prefix */;
 #pragma unroll
-            for (int k = 0; k < 4; k++)
+            for (int k = 0; k < kLookBack; k++)
             {
                 if (done) break;
                 while ((v[k] & kStFlagMask) == 0) v[k] = status[(size_t) (t - k) * kRadix + d];
                 exclusive += v[k] & ~kStFlagMask;
                 done = (v[k] & kStFlagMask) == kStFlagPrefix;
             }
-            t -= 4;
+            t -= kLookBack;
         }
         *st = kStFlagPrefix | (exclusive + tileCount);
     }
@@ -185,24 +191,35 @@ sortOnesweepKernel(const uint32_t *__restrict__ keysIn, const uint32_t *__restri
     {
         uint32_t k = sKeys[i];
         uint32_t dst = sGlobalBase[(k >> shift) & mask] + i;
-        keysOut[dst] = k;
-        valsOut[dst] = sVals[i];
+        if (EMIT)
+        {
+            if (k != 0xFFFFFFFFu) reinterpret_cast<int32_t *>(keysOut)[1 + dst + 2 * __ldg(valsOut + k)] = (int32_t) sVals[i];
+        }
+        else
+        {
+            keysOut[dst] = k;
+            valsOut[dst] = sVals[i];
+        }
     }
 }
 
 }  // namespace
 
-int sortScratchAlloc(SortScratch &s, size_t maxItems, uint32_t maxPasses)
+int sortScratchAlloc(SortScratch &s, size_t maxItems, uint32_t maxPasses, size_t prefixBytes, void **prefix)
 {
     s.maxItems = maxItems;
     s.maxPasses = maxPasses;
     size_t tiles = divUp(maxItems, (size_t) (kSortThreadsSmall * kSortItems)) + 1;
     s.statusWordsPerPass = tiles * kRadix;
-    MLSB_CUDA(cudaFuncSetAttribute(sortOnesweepKernel<kSortThreadsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int) (((kSortThreadsLarge / 32) * kRadix + 2 * kSortThreadsLarge * kSortItems + 2 * kRadix) * sizeof(uint32_t))));
-    // one allocation [hist | tickets | status] so that a sort needs a single memset
+    const int largeSmem = (int) (((kSortThreadsLarge / 32) * kRadix + 2 * kSortThreadsLarge * kSortItems + 2 * kRadix) * sizeof(uint32_t));
+    MLSB_CUDA(cudaFuncSetAttribute(sortOnesweepKernel<kSortThreadsLarge, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, largeSmem));
+    MLSB_CUDA(cudaFuncSetAttribute(sortOnesweepKernel<kSortThreadsLarge, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, largeSmem));
+    // one allocation [prefix | hist | tickets | status] so that a sort (and its caller) needs a single memset
+    prefixBytes = roundUp(prefixBytes, (size_t) 256);
     const size_t words = (size_t) maxPasses * kRadix + 64 + (size_t) maxPasses * s.statusWordsPerPass;
-    MLSB_CUDA(cudaMalloc(&s.hist, words * sizeof(uint32_t)));
+    MLSB_CUDA(cudaMalloc(&s.base, prefixBytes + words * sizeof(uint32_t)));
+    if (prefix) *prefix = s.base;
+    s.hist = reinterpret_cast<uint32_t *>(static_cast<char *>(s.base) + prefixBytes);
     s.tickets = s.hist + (size_t) maxPasses * kRadix;
     s.status = s.tickets + 64;
     return MLSB_OK;
@@ -210,8 +227,75 @@ int sortScratchAlloc(SortScratch &s, size_t maxItems, uint32_t maxPasses)
 
 void sortScratchFree(SortScratch &s)
 {
-    cudaFree(s.hist);
+    cudaFree(s.base);
     s = SortScratch();
+}
+
+namespace
+{
+
+struct SortPlan
+{
+    bool large;
+    int threads;
+    uint32_t tiles;
+    size_t smem, statusStride;
+};
+
+SortPlan planSort(uint32_t n)
+{
+    SortPlan p;
+    p.large = n >= kSortLargeThreshold;
+    p.threads = p.large ? kSortThreadsLarge : kSortThreadsSmall;
+    p.tiles = divUp(n, (uint32_t) (p.threads * kSortItems));
+    p.smem = ((size_t) (p.threads / 32) * kRadix + 2 * (size_t) p.threads * kSortItems + 2 * kRadix) * sizeof(uint32_t);
+    p.statusStride = (size_t) p.tiles * kRadix;   // status of pass q lives at s.status + q * tiles * 256: compact
+    return p;
+}
+
+template <bool EMIT>
+void launchPass(mlsb_worker *w, const SortPlan &pl, const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout,
+                uint32_t n, const uint32_t *nDev, uint32_t p, uint32_t wbits)
+{
+    SortScratch &s = w->sort;
+    if (pl.large)
+        sortOnesweepKernel<kSortThreadsLarge, EMIT><<<pl.tiles, kSortThreadsLarge, pl.smem, w->stream>>>(
+            kin, vin, kout, vout, n, nDev, 8 * p, (1u << wbits) - 1, s.hist + p * kRadix, s.status + p * pl.statusStride, s.tickets + p);
+    else
+        sortOnesweepKernel<kSortThreadsSmall, EMIT><<<pl.tiles, kSortThreadsSmall, pl.smem, w->stream>>>(
+            kin, vin, kout, vout, n, nDev, 8 * p, (1u << wbits) - 1, s.hist + p * kRadix, s.status + p * pl.statusStride, s.tickets + p);
+}
+
+}  // namespace
+
+size_t sortScratchBytesUsed(const SortScratch &s, uint32_t n, uint32_t passes)
+{
+    return ((size_t) s.maxPasses * kRadix + 64 + passes * planSort(n).statusStride) * sizeof(uint32_t);
+}
+
+int radixSortToCommands(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n, const uint32_t *nDev,
+                        uint32_t bits, int32_t *commands, const uint32_t *runIndex, const char *statName)
+{
+    SortScratch &s = w->sort;
+    const uint32_t passes = divUp(bits, 8u);
+    MLSB_REQUIRE(n > 0 && passes >= 1 && n <= s.maxItems && passes <= s.maxPasses && passes <= 4, MLSB_ERR_LENGTH,
+                 "sort scratch too small");
+    ScopedStat stat(w, statName, passes);
+    const SortPlan pl = planSort(n);
+    int cur = 0;
+    for (uint32_t p = 0; p < passes; p++)
+    {
+        const uint32_t wbits = bits - 8 * p < 8 ? bits - 8 * p : 8;
+        if (p + 1 == passes)
+            launchPass<true>(w, pl, keys[cur], values[cur], reinterpret_cast<uint32_t *>(commands), const_cast<uint32_t *>(runIndex),
+                             n, nDev, p, wbits);
+        else
+            launchPass<false>(w, pl, keys[cur], values[cur], keys[cur ^ 1], values[cur ^ 1], n, nDev, p, wbits);
+        cur ^= 1;
+    }
+    w->launches += passes;
+    MLSB_CUDA(cudaGetLastError());
+    return MLSB_OK;
 }
 
 int radixSortPairs(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n, uint32_t bits,
@@ -230,13 +314,8 @@ int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *value
     uint32_t passes = divUp(bits, 8u);
     MLSB_REQUIRE(n <= s.maxItems && passes <= s.maxPasses && passes <= 4, MLSB_ERR_LENGTH, "sort scratch too small");
     ScopedStat stat(w, statName, 1 + passes);
-    const bool large = n >= kSortLargeThreshold;
-    const int threads = large ? kSortThreadsLarge : kSortThreadsSmall;
-    uint32_t tiles = divUp(n, (uint32_t) (threads * kSortItems));
-    const size_t smem = ((size_t) (threads / 32) * kRadix + 2 * (size_t) threads * kSortItems + 2 * kRadix) * sizeof(uint32_t);
-    // status of pass p lives at s.status + p * tiles * 256: compact, so one memset covers everything
-    const size_t statusStride = (size_t) tiles * kRadix;
-    MLSB_CUDA(cudaMemsetAsync(s.hist, 0, ((size_t) s.maxPasses * kRadix + 64 + passes * statusStride) * sizeof(uint32_t), w->stream));
+    const SortPlan pl = planSort(n);
+    MLSB_CUDA(cudaMemsetAsync(s.hist, 0, sortScratchBytesUsed(s, n, passes), w->stream));
     uint32_t histBlocks = min(divUp(n, 256u * 8u), 148u * 8u);
     sortHistogramKernel<<<histBlocks, 256, 0, w->stream>>>(keys[0], n, nDev, s.hist, passes, bits);
     int cur = 0;
@@ -244,14 +323,7 @@ int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *value
     {
         uint32_t wbits = bits - 8 * p < 8 ? bits - 8 * p : 8;
         const uint32_t *vin = (p == 0 && identityValues) ? nullptr : values[cur];
-        if (large)
-            sortOnesweepKernel<kSortThreadsLarge><<<tiles, kSortThreadsLarge, smem, w->stream>>>(
-                keys[cur], vin, keys[cur ^ 1], values[cur ^ 1], n, nDev, 8 * p, (1u << wbits) - 1, s.hist + p * kRadix,
-                s.status + p * statusStride, s.tickets + p);
-        else
-            sortOnesweepKernel<kSortThreadsSmall><<<tiles, kSortThreadsSmall, smem, w->stream>>>(
-                keys[cur], vin, keys[cur ^ 1], values[cur ^ 1], n, nDev, 8 * p, (1u << wbits) - 1, s.hist + p * kRadix,
-                s.status + p * statusStride, s.tickets + p);
+        launchPass<false>(w, pl, keys[cur], vin, keys[cur ^ 1], values[cur ^ 1], n, nDev, p, wbits);
         cur ^= 1;
     }
     w->launches += 1 + passes;

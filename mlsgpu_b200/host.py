@@ -168,6 +168,143 @@ def torus_splats(n, seed=2, R=1.0, r=0.4, bump=0.02, freq=20.0):
     return np.ascontiguousarray(out)
 
 
+def _torus_points(rng, n, u_lo, u_hi, R, r, bump, freq, spacing):
+    """n area-uniform samples of the bumpy torus with u in [u_lo, u_hi): positions, unit normals, radii."""
+    u = rng.uniform(u_lo, u_hi, n)
+    v = rng.uniform(0.0, 2 * np.pi, int(n * 1.6) + 16)
+    keep = rng.uniform(0.0, 1.0, len(v)) < (R + r * np.cos(v)) / (R + r)
+    v = v[keep][:n]
+    if len(v) < n:
+        v = np.concatenate([v, rng.uniform(0.0, 2 * np.pi, n - len(v))])
+    rr = r + bump * np.sin(freq * u) * np.sin(freq * v)
+    cu, su, cv, sv = np.cos(u), np.sin(u), np.cos(v), np.sin(v)
+    p = np.stack([(R + rr * cv) * cu, (R + rr * cv) * su, rr * sv], axis=1)
+    drr_du = bump * freq * np.cos(freq * u) * np.sin(freq * v)
+    drr_dv = bump * freq * np.sin(freq * u) * np.cos(freq * v)
+    dpu = np.stack([-(R + rr * cv) * su + drr_du * cv * cu, (R + rr * cv) * cu + drr_du * cv * su, drr_du * sv], axis=1)
+    dpv = np.stack([(drr_dv * cv - rr * sv) * cu, (drr_dv * cv - rr * sv) * su, drr_dv * sv + rr * cv], axis=1)
+    nrm = np.cross(dpu, dpv)
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    out = np.zeros(n, SPLAT_DTYPE)
+    out["position"] = p.astype(np.float32)
+    out["normal"] = nrm.astype(np.float32)
+    out["radius"] = (spacing * rng.uniform(1.0, 2.0, n)).astype(np.float32)
+    return out
+
+
+class ShardedTorus:
+    """ONE bumpy-torus scan of `n` splats (the C2 surface) laid out so that each of `world`
+    GPUs can build exactly its share without generating the rest: the scan consists of `chunks`
+    angular sectors of n / chunks samples each (sector c = u in [2 pi c / chunks, 2 pi (c+1) / chunks), its own
+    Philox stream, Morton-ordered inside), the full grid is cut into the same blocks of <= max_cells
+    cells on every rank (make_bins' first cut), the blocks are dealt to the ranks in contiguous angular
+    runs of equal estimated load (owners()), and a rank generates only the sectors its blocks can reach.  The bins a rank ends up
+    with are identical to the bins of those blocks had the whole scan been binned in one place
+    (tests/test_multi_gpu_host.py checks that), so N ranks mesh ONE surface with no collective and
+    no replicated work — the static spatial partition SURVEY 8e allows for reproducible runs."""
+
+    def __init__(self, n, world, fit_grid, seed=2, chunks=None, R=1.0, r=0.4, bump=0.02, freq=20.0, smooth=4.0,
+                 max_cells=255, max_splats=1 << 21, bucket_size=63):
+        self.n, self.world, self.seed = int(n), int(world), seed
+        self.R, self.r, self.bump, self.freq, self.smooth = R, r, bump, freq, smooth
+        self.chunks = int(chunks or max(8 * world, 16))
+        self.per_chunk = self.n // self.chunks
+        self.n = self.per_chunk * self.chunks
+        self.spacing = np.float32(fit_grid)
+        self.max_cells, self.max_splats = max_cells, max_splats
+        self.sample_spacing = np.sqrt(4 * np.pi * np.pi * R * r / self.n)
+        # the full grid, from the surface's analytic bounds (every rank must agree without seeing all splats)
+        rmax = float(np.float32(2.0 * self.sample_spacing) * np.float32(smooth))
+        bound = np.array([R + r + bump + rmax, R + r + bump + rmax, r + bump + rmax])
+        lo = np.floor(-bound / fit_grid).astype(np.int64)
+        self.lo = (lo // bucket_size) * bucket_size
+        self.hi = np.ceil(bound / fit_grid).astype(np.int64)
+        self.num_cells = self.hi - self.lo
+        self.rmax_cells = rmax / fit_grid
+        counts = -(-self.num_cells // max_cells)
+        self.block_counts = counts
+        self.edges = [np.arange(counts[a] + 1) * self.num_cells[a] // counts[a] for a in range(3)]
+        self._owners = None
+
+    def chunk(self, c):
+        """Sector c of the scan, world coordinates (unconditioned)."""
+        rng = np.random.Generator(np.random.Philox(key=self.seed, counter=[c, 0, 0, 0]))
+        s = _torus_points(rng, self.per_chunk, 2 * np.pi * c / self.chunks, 2 * np.pi * (c + 1) / self.chunks,
+                          self.R, self.r, self.bump, self.freq, self.sample_spacing)
+        return np.ascontiguousarray(s[morton_order(s["position"])])
+
+    def block_of(self, offset):
+        return tuple(int(np.searchsorted(self.edges[a], offset[a], side="right") - 1) for a in range(3))
+
+    def owners(self):
+        """{block (bx, by, bz): rank}.  Every rank computes the same map from a coarse sample of the
+        whole scan (its own Philox stream, ~300 k points, a fraction of a second): the blocks are
+        ordered by the angle of their centre around the torus' axis and the ordered list is cut into
+        `world` contiguous runs of equal estimated load — contiguous, so that a rank needs only the
+        sectors around its run; equal, because the step time of a sharded run is its slowest rank's."""
+        if self._owners is not None:
+            return self._owners
+        rng = np.random.Generator(np.random.Philox(key=self.seed, counter=[1 << 40, 0, 0, 0]))
+        m = min(self.n, 40_000 * max(self.world, 8))
+        s = _torus_points(rng, m, 0.0, 2 * np.pi, self.R, self.r, self.bump, self.freq, self.sample_spacing)
+        g = world_to_grid(condition_splats(s, self.smooth), self.spacing, self.lo)
+        load = {}
+        for b in make_bins(g, self.num_cells, self.max_cells, 1 << 30):
+            k = self.block_of(b["offset"])
+            load[k] = load.get(k, 0) + len(b["ids"])
+
+        def angle(k):
+            c = [0.5 * (self.edges[a][k[a]] + self.edges[a][k[a] + 1]) + self.lo[a] for a in range(2)]
+            return float(np.arctan2(c[1], c[0]) % (2 * np.pi))
+
+        # every block gets an owner (a block the sample missed may still hold a few real splats)
+        blocks = [(bx, by, bz) for bz in range(int(self.block_counts[2])) for by in range(int(self.block_counts[1]))
+                  for bx in range(int(self.block_counts[0]))]
+        blocks.sort(key=lambda k: (angle(k), k))
+        total = float(sum(load.values()))
+        self._owners, acc = {}, 0.0
+        for k in blocks:
+            w = load.get(k, 0)
+            self._owners[k] = min(int((acc + 0.5 * w) / total * self.world), self.world - 1)
+            acc += w
+        self._loads = load
+        return self._owners
+
+    def block_chunks(self, bx, by):
+        """Sectors that can hold a splat reaching block column (bx, by)."""
+        m = self.rmax_cells + 1.0
+        x0, x1 = self.edges[0][bx] + self.lo[0] - m, self.edges[0][bx + 1] + self.lo[0] + m
+        y0, y1 = self.edges[1][by] + self.lo[1] - m, self.edges[1][by + 1] + self.lo[1] + m
+        # no splat closer to the axis than R - r - bump, nor further than R + r + bump (grid units)
+        near = np.hypot(max(x0, -x1, 0.0), max(y0, -y1, 0.0))
+        far = np.hypot(max(abs(x0), abs(x1)), max(abs(y0), abs(y1)))
+        if far < (self.R - self.r - self.bump) / float(self.spacing) or near > (self.R + self.r + self.bump) / float(self.spacing):
+            return set()
+        if x0 <= 0.0 <= x1 and y0 <= 0.0 <= y1:
+            return set(range(self.chunks))            # the column holds the axis: every angle
+        # the angular extent of a rectangle that misses the origin is spanned by its corners, all within
+        # less than pi of the centre direction
+        pts = [(x0, y0), (x0, y1), (x1, y0), (x1, y1)]
+        mid = np.arctan2(0.5 * (y0 + y1), 0.5 * (x0 + x1))
+        d = [((np.arctan2(y, x) - mid + np.pi) % (2 * np.pi)) - np.pi for x, y in pts]
+        w = 2 * np.pi / self.chunks
+        c0, c1 = int(np.floor((mid + min(d)) / w)), int(np.floor((mid + max(d)) / w))
+        return {c % self.chunks for c in range(c0, c1 + 1)}
+
+    def rank_share(self, rank):
+        """(grid splats, bins, lo, spacing) of `rank`: only its blocks' bins, complete."""
+        mine = {k for k, r in self.owners().items() if r == rank}
+        need = set()
+        for bx, by in {(k[0], k[1]) for k in mine}:
+            need |= self.block_chunks(bx, by)
+        parts = [self.chunk(c) for c in sorted(need)]
+        s = np.concatenate(parts) if parts else np.zeros(0, SPLAT_DTYPE)
+        s = condition_splats(s, self.smooth)
+        g = world_to_grid(s, self.spacing, self.lo)
+        bins = make_bins(g, self.num_cells, self.max_cells, self.max_splats)
+        return g, [b for b in bins if self.block_of(b["offset"]) in mine], self.lo, self.spacing
+
+
 def prepare(splats, fit_grid, smooth=4.0, max_cells=255, max_splats=1 << 21, bucket_size=63):
     """World-space splats -> (grid_splats, bins, lo, spacing): everything the reference does on
     the host before DeviceWorkerGroup sees a bin."""

@@ -43,7 +43,7 @@ namespace
 // corner rows of a warp in flight before the first ballot helps the index pass (4.5 -> 4.2 ms, its CTAs
 // start from a cold field) and not the classification (3.1 -> 3.2 ms).
 #ifndef MLSB_MC_PREFETCH
-#define MLSB_MC_PREFETCH EMIT
+#define MLSB_MC_PREFETCH EMIT      /* a C++ expression in the kernel's scope, not a preprocessor value */
 #endif
 #ifndef MLSB_MC_EMIT
 #define MLSB_MC_EMIT 0
@@ -335,9 +335,9 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
         if (active && P.blockActive != nullptr)
             active = *reinterpret_cast<const uint32_t *>(P.blockActive + ((size_t) (z >> 3) * P.activeDim + (y0 >> 3)) * P.activeDim + (x0 >> 3)) != 0;
         RowMasks p0 = {0, 0, 0, 0}, p1 = {0, 0, 0, 0};
-#if MLSB_MC_PREFETCH
+        constexpr bool kPrefetch = MLSB_MC_PREFETCH;
         RowValues rv0[kGenRows + 1], rv1[kGenRows + 1];
-        if (active)
+        if (kPrefetch && active)
         {
 #pragma unroll
             for (int r = 0; r <= kGenRows; r++)
@@ -349,13 +349,11 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
             p0 = rowMasks(rv0[0]);
             p1 = rowMasks(rv1[0]);
         }
-#else
-        if (active)
+        if (!kPrefetch && active)
         {
             p0 = rowMasks(loadRowValues(slice0, x0, lane, numCorners));
             p1 = rowMasks(loadRowValues(slice1, x0, lane, numCorners));
         }
-#endif
         const uint32_t inRange = P.cellsX - x0 >= 32 ? 0xFFFFFFFFu : (active ? (1u << (P.cellsX - x0)) - 1 : 0u);
         // per corner row, combined over its four corners per cell column (x, x+1 of both slices):
         // all finite / all outside / any outside.  A cell row then needs five more operations.
@@ -367,13 +365,8 @@ template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) 
             uint32_t packed = 0, code = 0;
             if (active && (uint32_t) r < nRows)
             {
-#if MLSB_MC_PREFETCH
-                const RowMasks c0 = rowMasks(rv0[r + 1]);
-                const RowMasks c1 = rowMasks(rv1[r + 1]);
-#else
-                const RowMasks c0 = rowMasks(loadRowValues(slice0 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners));
-                const RowMasks c1 = rowMasks(loadRowValues(slice1 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners));
-#endif
+                const RowMasks c0 = rowMasks(kPrefetch ? rv0[r + 1] : loadRowValues(slice0 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners));
+                const RowMasks c1 = rowMasks(kPrefetch ? rv1[r + 1] : loadRowValues(slice1 + (size_t) (r + 1) * P.pitch, x0, lane, numCorners));
                 const uint32_t cv = c0.f0 & c0.f1 & c1.f0 & c1.f1, ca = c0.s0 & c0.s1 & c1.s0 & c1.s1, co = c0.s0 | c0.s1 | c1.s0 | c1.s1;
                 const uint32_t occ = (pv & cv) & (po | co) & ~(pa & ca) & inRange;
                 if (occ)

@@ -50,7 +50,7 @@ struct Options
     int deviceThreads = 4;           // the reference defaults to 1 and recommends more (src/marching.h:573-576)
     std::uint64_t memBucketSplats = 64ull << 20;   // bytes
     std::uint64_t memMesh = 512ull << 20;
-    int device = 0;
+    std::vector<int> devices;        // CUDA ordinals; empty = every device found (the reference's default, src/clh.cpp:180-240)
     bool quiet = false, statistics = false, statisticsCL = false, split = false;
     std::uint64_t splitSize = 100ull << 20;   // src/mlsgpu_core.cpp:162
     std::string checkpoint, resume;           // src/mlsgpu_core.cpp:121-122
@@ -78,7 +78,8 @@ void usage()
         "  --device-threads N          worker threads per device (4)\n"
         "  --mem-bucket-splats SIZE    device memory for splats of one bin, K/M/G suffix (64M)\n"
         "  --mem-mesh SIZE             device memory for raw mesh data (512M)\n"
-        "  --device N                  CUDA device ordinal (replaces --cl-device)\n"
+        "  --device N[,N...]|all       CUDA devices to use, one worker group each (replaces --cl-device; default: all)\n"
+        "  --cl-gpu                    use every GPU (the default)\n"
         "  --split                     split the output into a grid of files BASE_XXXX_YYYY_ZZZZ.ply (-o gives BASE)\n"
         "  --split-size SIZE           approximate size of the output chunks (100M)\n"
         "  --checkpoint FILE           save the mesher's state to FILE instead of writing the output\n"
@@ -142,7 +143,20 @@ Options parse(int argc, char **argv)
         else if (a == "--device-threads") o.deviceThreads = std::stoi(value());
         else if (a == "--mem-bucket-splats") o.memBucketSplats = parseCapacity(value());
         else if (a == "--mem-mesh") o.memMesh = parseCapacity(value());
-        else if (a == "--device") o.device = std::stoi(value());
+        else if (a == "--device" || a == "--devices")
+        {
+            // --cl-device name[:n] selects among OpenCL devices (src/clh.cpp:170-178); CUDA has ordinals
+            const std::string list = value();
+            o.devices.clear();
+            if (list != "all")
+            {
+                std::stringstream ss(list);
+                std::string item;
+                while (std::getline(ss, item, ','))
+                    if (!item.empty()) o.devices.push_back(std::stoi(item));
+                if (o.devices.empty()) throw std::invalid_argument("bad device list " + list);
+            }
+        }
         else if (a == "--statistics") o.statistics = true;
         else if (a == "--statistics-file") { o.statisticsFile = value(); o.statistics = true; }
         else if (a == "--statistics-cl") o.statisticsCL = true;
@@ -312,21 +326,40 @@ int main(int argc, char **argv)
             return 0;
         }
 
-        // ---- device workers: created in the background while the input is read and bucketed.
+        // ---- device workers: one group per device (the reference: one DeviceWorkerGroup per device,
+        // src/mlsgpu_core.cpp:704-741), created in the background while the input is read and bucketed.
         // The buffers are sized from the options alone (--mem-bucket-splats, --levels,
         // --subsampling), as DeviceWorkerGroup's are (src/mlsgpu_core.cpp:722-735). ----
         const std::int64_t maxCells = (std::int64_t(1) << (o.levels + o.subsampling - 1)) - 1;   // src/mlsgpu_core.cpp:722
         const std::size_t maxBucketSplats = (std::size_t) (o.memBucketSplats / sizeof(mlsb_splat));
-        mlsb_worker_config cfg;
-        cfg.device = o.device;
-        cfg.maxLevels = (std::uint32_t) o.levels;
-        cfg.subsampling = (std::uint32_t) o.subsampling;
-        cfg.maxSplats = (std::uint32_t) std::max<std::size_t>(maxBucketSplats, 1);
-        cfg.maxCells = (std::uint32_t) maxCells;
-        cfg.meshBytes = std::max<std::uint64_t>(o.memMesh / (o.deviceThreads + 1), (std::uint64_t) maxCells * maxCells * 872);
-        cfg.shape = o.fitShape == "plane" ? MLSB_SHAPE_PLANE : MLSB_SHAPE_SPHERE;
-        cfg.boundaryLimit = (float) o.fitBoundaryLimit;
+        std::vector<int> devices = o.devices;
+        if (devices.empty())
+        {
+            int n = 0;
+            mlsb::check(mlsb_device_count(&n));
+            if (n == 0) throw std::runtime_error("No suitable CUDA device found");   // "No suitable OpenCL device found", mlsgpu.cpp:221
+            for (int d = 0; d < n; d++) devices.push_back(d);
+        }
+        const std::size_t numGroups = devices.size();
+        std::vector<mlsb_worker_config> cfgs(numGroups);
+        for (std::size_t g = 0; g < numGroups; g++)
+        {
+            mlsb_worker_config &cfg = cfgs[g];
+            cfg.device = devices[g];
+            cfg.maxLevels = (std::uint32_t) o.levels;
+            cfg.subsampling = (std::uint32_t) o.subsampling;
+            cfg.maxSplats = (std::uint32_t) std::max<std::size_t>(maxBucketSplats, 1);
+            cfg.maxCells = (std::uint32_t) maxCells;
+            cfg.meshBytes = std::max<std::uint64_t>(o.memMesh / (o.deviceThreads + 1), (std::uint64_t) maxCells * maxCells * 872);
+            cfg.shape = o.fitShape == "plane" ? MLSB_SHAPE_PLANE : MLSB_SHAPE_SPHERE;
+            cfg.boundaryLimit = (float) o.fitBoundaryLimit;
+        }
+        // Everything the worker threads and the sink read is declared BEFORE the guard that joins them,
+        // so that on any exit path (an exception included) it outlives the workers.
         SinkState state(o.split);
+        std::vector<mlsb_splat> splats;
+        std::vector<mlsb::Bin> bins;
+        std::vector<std::unique_ptr<mlsb_splat[]>> ring;
         struct Created
         {
             mlsb_group *group = nullptr;
@@ -334,31 +367,33 @@ int main(int argc, char **argv)
             std::string message;
             double seconds = 0.0;
         };
-        std::future<Created> creating = std::async(std::launch::async, [&cfg, &o, &state] {
-            Created c;
-            const double t = now();
-            c.status = mlsb_group_create(&cfg, (std::uint32_t) o.deviceThreads, 0, 1, meshSink, &state, &c.group);
-            if (c.status != MLSB_OK) c.message = mlsb_last_error_string();   // the error string is per thread
-            c.seconds = now() - t;
-            return c;
-        });
-        // whatever happens below, the group is joined and destroyed before state and cfg go away
+        std::vector<std::future<Created>> creating;
+        for (std::size_t g = 0; g < numGroups; g++)
+            creating.push_back(std::async(std::launch::async, [&cfgs, &o, &state, g] {
+                Created c;
+                const double t = now();
+                c.status = mlsb_group_create(&cfgs[g], (std::uint32_t) o.deviceThreads, 0, 1, meshSink, &state, &c.group);
+                if (c.status != MLSB_OK) c.message = mlsb_last_error_string();   // the error string is per thread
+                c.seconds = now() - t;
+                return c;
+            }));
+        // whatever happens below, the groups are joined and destroyed before anything above goes away
         struct GroupGuard
         {
-            std::future<Created> &creating;
-            mlsb_group *group;
-            explicit GroupGuard(std::future<Created> &c) : creating(c), group(nullptr) {}
+            std::vector<std::future<Created>> &creating;
+            std::vector<mlsb_group *> groups;
+            explicit GroupGuard(std::vector<std::future<Created>> &c) : creating(c) {}
             ~GroupGuard()
             {
-                if (creating.valid()) group = creating.get().group;
-                mlsb_group_destroy(group);
+                for (std::future<Created> &f : creating)
+                    if (f.valid()) groups.push_back(f.get().group);
+                for (mlsb_group *g : groups) mlsb_group_destroy(g);
             }
         } guard(creating);
 
         // ---- read and condition (FastPly::Reader) ----
         std::vector<std::string> files;
         collectInputs(o.inputs, files);
-        std::vector<mlsb_splat> splats;
         for (const std::string &f : files)
         {
             mlsb::PlyReader reader(f, (float) o.fitSmooth, (float) o.maxRadius);
@@ -380,54 +415,94 @@ int main(int argc, char **argv)
         // side in ~20 x^2 vertices of 38 bytes each (src/mlsgpu_core.cpp:635-652)
         std::int64_t chunkCells = 0;
         if (o.split) chunkCells = std::max<std::int64_t>(1, (std::int64_t) std::ceil(std::sqrt(o.splitSize / 760.0)));
-        const std::vector<mlsb::Bin> bins = mlsb::makeBins(splats, grid, maxCells, maxBucketSplats, chunkCells);
+        bins = mlsb::makeBins(splats, grid, maxCells, maxBucketSplats, chunkCells);
         state.bins = &bins;
         const double tBucket = now();
 
         // ---- device pipeline ----
         const double tCreate0 = now();
-        const Created created = creating.get();
-        mlsb_group *group = guard.group = created.group;
-        if (created.status != MLSB_OK) throw std::runtime_error(created.message);
-        mlsb::check(mlsb_group_set_concurrent_sink(group, 1));
+        std::vector<mlsb_group *> groups;
+        double createSeconds = 0.0;
+        {
+            std::string failure;
+            for (std::future<Created> &f : creating)
+            {
+                const Created c = f.get();
+                guard.groups.push_back(c.group);
+                groups.push_back(c.group);
+                createSeconds = std::max(createSeconds, c.seconds);
+                if (c.status != MLSB_OK && failure.empty()) failure = c.message;
+            }
+            if (!failure.empty()) throw std::runtime_error(failure);
+        }
         float origin[3];
         grid.getVertex0(origin);
-        for (int i = 0; i < o.deviceThreads; i++)
+        for (mlsb_group *group : groups)
         {
-            mlsb_worker *w = nullptr;
-            mlsb::check(mlsb_group_worker(group, (std::uint32_t) i, &w));
-            mlsb::check(mlsb_set_scale_bias(w, grid.spacing, origin));   // ScaleBiasFilter::setScaleBias(grid)
-            if (o.statisticsCL) mlsb::check(mlsb_worker_set_profiling(w, 2));   // src/mlsgpu_core.cpp:225-228
+            mlsb::check(mlsb_group_set_concurrent_sink(group, 1));
+            for (int i = 0; i < o.deviceThreads; i++)
+            {
+                mlsb_worker *w = nullptr;
+                mlsb::check(mlsb_group_worker(group, (std::uint32_t) i, &w));
+                mlsb::check(mlsb_set_scale_bias(w, grid.spacing, origin));   // ScaleBiasFilter::setScaleBias(grid)
+                if (o.statisticsCL) mlsb::check(mlsb_worker_set_profiling(w, 2));   // src/mlsgpu_core.cpp:225-228
+            }
         }
         const double tCreateWait = now() - tCreate0;   // the part of the creation that was not hidden
         double tGather = 0.0;
         // Gather buffers are recycled (BucketLoader's circular buffer): a slot is reused once the
-        // group has released the bin that used it, which keeps the gather out of the page-fault path.
+        // group it went to has released the bin that used it, which keeps the gather out of the
+        // page-fault path.
         std::size_t largest = 1;
         for (const mlsb::Bin &bin : bins) largest = std::max(largest, bin.ids.size());
         const std::size_t queueDepth = 2 * (std::size_t) o.deviceThreads;   // mlsb_group_create's default
-        std::vector<std::unique_ptr<mlsb_splat[]>> ring(queueDepth + (std::size_t) o.deviceThreads + 1);
+        ring.resize(numGroups * (queueDepth + (std::size_t) o.deviceThreads) + 1);
+        struct SlotUse { std::size_t group = 0; std::uint64_t sequence = 0; bool used = false; };
+        std::vector<SlotUse> slotUse(ring.size());
+        std::vector<std::uint64_t> submittedBins(numGroups, 0), submittedSplats(numGroups, 0);
         for (std::size_t b = 0; b < bins.size(); b++)
         {
             // BucketLoader::operator(): gather the bin's splats (src/bucket_loader.cpp:104-126)
             const double tg = now();
             const std::vector<std::uint32_t> &ids = bins[b].ids;
-            std::unique_ptr<mlsb_splat[]> &slot = ring[b % ring.size()];
+            const std::size_t slotIndex = b % ring.size();
+            std::unique_ptr<mlsb_splat[]> &slot = ring[slotIndex];
             if (!slot) slot.reset(new mlsb_splat[largest]);
-            for (std::uint64_t released = 0; b >= ring.size();)
-            {
-                mlsb::check(mlsb_group_released(group, &released));
-                if (released > b - ring.size()) break;
-                std::this_thread::yield();
-            }
+            if (slotUse[slotIndex].used)
+                for (std::uint64_t released = 0;;)
+                {
+                    mlsb::check(mlsb_group_released(groups[slotUse[slotIndex].group], &released));
+                    if (released > slotUse[slotIndex].sequence) break;
+                    std::this_thread::yield();
+                }
             mlsb_splat *dst = slot.get();
             // a few threads are enough and leave the cores to the device workers
 #pragma omp parallel for schedule(static) num_threads(4)
             for (std::int64_t i = 0; i < (std::int64_t) ids.size(); i++) dst[i] = splats[ids[(std::size_t) i]];
             tGather += now() - tg;
-            mlsb::check(mlsb_group_submit(group, dst, (std::uint32_t) ids.size(), bins[b].size, bins[b].offset, b));
+            // CopyGroupBase::Worker::flush (src/workers.cpp:329-343) hands a bin to the device with the most
+            // unallocated splat capacity: here, the group with the fewest splats submitted and not yet processed
+            std::size_t target = 0;
+            std::uint64_t least = ~0ull;
+            for (std::size_t g = 0; g < numGroups; g++)
+            {
+                std::uint64_t doneSplats = 0;
+                mlsb::check(mlsb_group_counters(groups[g], nullptr, &doneSplats, nullptr));
+                const std::uint64_t pending = submittedSplats[g] - doneSplats;
+                if (pending < least) { least = pending; target = g; }
+            }
+            slotUse[slotIndex].group = target;
+            slotUse[slotIndex].sequence = submittedBins[target]++;
+            slotUse[slotIndex].used = true;
+            submittedSplats[target] += ids.size();
+            mlsb::check(mlsb_group_submit(groups[target], dst, (std::uint32_t) ids.size(), bins[b].size, bins[b].offset, b));
         }
-        mlsb::check(mlsb_group_wait(group));
+        {
+            std::string failure;
+            for (mlsb_group *group : groups)
+                if (mlsb_group_wait(group) != MLSB_OK && failure.empty()) failure = mlsb_last_error_string();
+            if (!failure.empty()) throw std::runtime_error(failure);
+        }
         const double tDevice = now();
 
         // ---- mesher: prune, write (OOCMesher::write) ----
@@ -460,6 +535,7 @@ int main(int argc, char **argv)
             out << "mlsgpu version: " << mlsb_version() << "\n"
                 << "files.splats: " << numSplats << "\n"
                 << "bins: " << bins.size() << "\n"
+                << "devices: " << numGroups << "\n"
                 << "components.total: " << mesh.totalComponents << "\ncomponents.kept: " << mesh.keptComponents << "\n"
                 << "output.vertices: " << mesh.numVertices << "\noutput.triangles: " << mesh.numTriangles << "\n"
                 << "output.files: " << outputFiles << "\n";
@@ -469,8 +545,14 @@ int main(int argc, char **argv)
             out << buf;
             std::snprintf(buf, sizeof(buf), "device.create.time: %.3f\ndevice.create.wait: %.3f\ndevice.gather.time: %.3f\n"
                           "mesher.prepare.time: %.3f\nmesher.commit.time: %.3f\n",
-                          created.seconds, tCreateWait, tGather, state.prepareSeconds, state.commitSeconds);
+                          createSeconds, tCreateWait, tGather, state.prepareSeconds, state.commitSeconds);
             out << buf;
+            for (std::size_t g = 0; g < numGroups; g++)
+            {
+                std::snprintf(buf, sizeof(buf), "device.%d.bins: %llu\ndevice.%d.splats: %llu\n", devices[g], (unsigned long long) submittedBins[g],
+                              devices[g], (unsigned long long) submittedSplats[g]);
+                out << buf;
+            }
             if (o.statisticsCL)
             {
                 // Statistics::Variable::write (src/statistics.cpp:175-182): "sum : mean [n]", summed over the workers
@@ -478,23 +560,24 @@ int main(int argc, char **argv)
                     "kernel.octree.writeEntries.time", "kernel.octree.sort.time", "kernel.octree.fill.time",
                     "kernel.octree.countCommands.time", "kernel.octree.scan.time", "kernel.octree.writeSplatIds.time",
                     "kernel.octree.writeStart.time", "kernel.mls.processCorners.time", "kernel.marching.zero.time",
-                    "kernel.marching.genOccupied.time", "kernel.marching.scanElements.time",
+                    "kernel.marching.genOccupied.time", "kernel.marching.countUniqueVertices.time",
                     "kernel.marching.compactVertices.time", "kernel.marching.generateElements.time",
                     "kernel.marching.readback.time"};
                 for (const char *name : names)
                 {
                     double sum = 0.0;
                     std::uint64_t count = 0;
-                    for (int i = 0; i < o.deviceThreads; i++)
-                    {
-                        mlsb_worker *w = nullptr;
-                        double s1 = 0.0;
-                        std::uint64_t c1 = 0;
-                        mlsb::check(mlsb_group_worker(group, (std::uint32_t) i, &w));
-                        mlsb::check(mlsb_worker_get_statistic(w, name, &s1, &c1));
-                        sum += s1;
-                        count += c1;
-                    }
+                    for (mlsb_group *group : groups)
+                        for (int i = 0; i < o.deviceThreads; i++)
+                        {
+                            mlsb_worker *w = nullptr;
+                            double s1 = 0.0;
+                            std::uint64_t c1 = 0;
+                            mlsb::check(mlsb_group_worker(group, (std::uint32_t) i, &w));
+                            mlsb::check(mlsb_worker_get_statistic(w, name, &s1, &c1));
+                            sum += s1;
+                            count += c1;
+                        }
                     if (count == 0) continue;
                     std::snprintf(buf, sizeof(buf), "%s: %.9g : %.9g [%llu]\n", name, sum, sum / (double) count, (unsigned long long) count);
                     out << buf;

@@ -86,6 +86,49 @@ typedef struct
 
 typedef struct mlsb_worker mlsb_worker;
 
+/* SplatTreeCL::MAX_LEVELS and MAX_SPLATS (src/splat_tree_cl.h:76,88), Marching::MAX_DIMENSION as built here
+ * (the reference's is 8192, src/marching.h:103; bins above 512 corners per side are not supported) and
+ * MAX_GLOBAL_DIMENSION (src/marching.h:120). */
+#define MLSB_MAX_LEVELS 10u
+#define MLSB_MAX_SPLATS ((1u << 31) / 16u)
+#define MLSB_MAX_DIMENSION 512u
+#define MLSB_MAX_GLOBAL_DIMENSION ((1u << 20) - 1u)
+
+/* CLH::ResourceUsage (src/clh.h) for one worker: what DeviceWorkerGroup::resourceUsage adds up
+ * (src/workers.cpp:176-205) plus the pinned host memory the reference accounts for separately. */
+typedef struct
+{
+    uint64_t deviceBytes;          /* total device memory a worker allocates */
+    uint64_t maxAllocationBytes;   /* its largest single allocation (CL_DEVICE_MAX_MEM_ALLOC_SIZE check) */
+    uint64_t pinnedHostBytes;      /* page-locked host memory: mesh read-back blob and counters */
+} mlsb_resource_usage;
+
+/* Marching::Generator (src/marching.h:204-253) as a callback: must ENQUEUE, on `stream` (a
+ * cudaStream_t), work that fills deviceField — corner (x, y, z) at
+ * deviceField[(y + z*zStride + zBias) * pitch + x] — for the corner slices zFirst..zLast of the swathe,
+ * with NaN wherever the function is undefined, and return 0 (anything else aborts the generate with
+ * MLSB_ERR_STATE).  Rows and columns beyond width/height up to the next multiple of 8 may be
+ * written; nothing else may be (the post-conditions of :233-246). */
+typedef int (*mlsb_field_generator)(void *user, float *deviceField, uint32_t pitch, const mlsb_swathe *swathe, void *stream);
+
+/* DeviceKeyMesh (src/mesh.h:101-123): one shipped-out block still on the device.  vertices holds
+ * numVertices packed float[3] (internal first, then external), vertexKeys numVertices uint64 of which
+ * only [numInternalVertices, numVertices) are defined, triangles numTriangles x uint32[3] indexing
+ * vertices.  The buffers are the worker's own and stay valid until the callback returns. */
+typedef struct
+{
+    mlsb_mesh_sizes sizes;
+    float *vertices;
+    uint64_t *vertexKeys;
+    uint32_t *triangles;
+} mlsb_device_mesh;
+
+/* Marching::OutputFunctor (src/marching.h:516-546) on the device side: called once per block before
+ * any read-back.  It may modify the mesh in place with work enqueued on `stream` (a MeshFilter,
+ * src/mesh_filter.h:55-116) and/or read it back itself with mlsb_device_mesh_read; whatever it
+ * enqueues must have been waited for, or be on `stream`, when it returns.  A non-zero return aborts. */
+typedef int (*mlsb_device_mesh_sink)(const mlsb_device_mesh *mesh, void *stream, void *user);
+
 /* Receives one shipped-out block, the equivalent of Marching::OutputFunctor after
  * enqueueReadMesh (src/marching.h:516-546, src/mesh.cpp:62-102).  hostBlob has the HostKeyMesh
  * layout (src/mesh.cpp:51-60): [uint64 keys of external vertices][float[3] vertices]
@@ -108,6 +151,13 @@ MLSB_API int mlsb_worker_create(const mlsb_worker_config *config, mlsb_worker **
 MLSB_API void mlsb_worker_destroy(mlsb_worker *w);
 /* DeviceWorkerGroup::resourceUsage (src/workers.cpp:176-205): device bytes a worker allocates. */
 MLSB_API int mlsb_worker_resource_usage(const mlsb_worker_config *config, uint64_t *deviceBytes);
+MLSB_API int mlsb_worker_resource_usage_ex(const mlsb_worker_config *config, mlsb_resource_usage *usage);
+/* SplatTreeCL::validateDevice / Marching::validateDevice / MlsFunctor's requirements
+ * (src/splat_tree_cl.cpp:55-66, src/marching.cpp:296-309, src/clh.cpp:180-240) for a CUDA device:
+ * MLSB_OK if the library can run on it, otherwise MLSB_ERR_CUDA with the reason in
+ * mlsb_last_error_string() (compute capability other than 10.x — the kernels are built for sm_100a
+ * only —, too little shared memory, no thread-block clusters). */
+MLSB_API int mlsb_validate_device(int device);
 /* The worker's own stream (the cl::CommandQueue of workers.cpp:215). */
 MLSB_API void *mlsb_worker_stream(mlsb_worker *w);
 MLSB_API int mlsb_worker_synchronize(mlsb_worker *w);
@@ -163,6 +213,19 @@ MLSB_API int mlsb_marching_generate(mlsb_worker *w, const uint32_t size[3], cons
 MLSB_API int mlsb_marching_generate_host_field(mlsb_worker *w, const float *hostField,
                                                const uint32_t size[3], const uint32_t keyOffset[3],
                                                mlsb_mesh_sink sink, void *user);
+/* Marching::generate with ANY generator (src/marching.h:603-608): `generate` fills the worker's
+ * field, once for the whole bin (the field is resident; there are no swathes to loop over). */
+MLSB_API int mlsb_marching_generate_cb(mlsb_worker *w, mlsb_field_generator generate, void *generatorUser,
+                                       const uint32_t size[3], const uint32_t keyOffset[3],
+                                       mlsb_mesh_sink sink, void *user);
+/* Marching::generate handing out DeviceKeyMesh blocks (the reference's OutputFunctor contract)
+ * instead of host blobs; generate == NULL uses the MlsFunctor bound by mlsb_mls_set. */
+MLSB_API int mlsb_marching_generate_device(mlsb_worker *w, mlsb_field_generator generate, void *generatorUser,
+                                           const uint32_t size[3], const uint32_t keyOffset[3],
+                                           mlsb_device_mesh_sink sink, void *user);
+/* enqueueReadMesh (src/mesh.cpp:62-102): reads a device mesh into a HostKeyMesh blob of
+ * mlsb_mesh_host_bytes(&mesh->sizes) bytes (pinned memory for speed) and waits for it. */
+MLSB_API int mlsb_device_mesh_read(mlsb_worker *w, const mlsb_device_mesh *mesh, void *hostBlob);
 /* Bytes of the HostKeyMesh blob, MeshSizes::getHostBytes (src/mesh.h:76-81). */
 MLSB_API uint64_t mlsb_mesh_host_bytes(const mlsb_mesh_sizes *sizes);
 /* The four lookup tables of Marching::makeTables (src/marching.cpp:109-252), host copies:

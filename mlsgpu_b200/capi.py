@@ -39,7 +39,19 @@ class MeshSizes(C.Structure):
     _fields_ = [("numVertices", C.c_uint64), ("numTriangles", C.c_uint64), ("numInternalVertices", C.c_uint64)]
 
 
+class ResourceUsage(C.Structure):
+    _fields_ = [("deviceBytes", C.c_uint64), ("maxAllocationBytes", C.c_uint64), ("pinnedHostBytes", C.c_uint64)]
+
+
+class DeviceMesh(C.Structure):
+    _fields_ = [("sizes", MeshSizes), ("vertices", C.c_void_p), ("vertexKeys", C.c_void_p), ("triangles", C.c_void_p)]
+
+
+MAX_LEVELS, MAX_SPLATS, MAX_DIMENSION, MAX_GLOBAL_DIMENSION = 10, (1 << 31) // 16, 512, (1 << 20) - 1
+
 MESH_SINK = C.CFUNCTYPE(None, C.POINTER(MeshSizes), C.c_void_p, C.c_void_p)
+FIELD_GENERATOR = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Swathe), C.c_void_p)
+DEVICE_MESH_SINK = C.CFUNCTYPE(C.c_int, C.POINTER(DeviceMesh), C.c_void_p, C.c_void_p)
 GROUP_SINK = C.CFUNCTYPE(None, C.c_uint64, C.POINTER(MeshSizes), C.c_void_p, C.c_void_p)
 
 # every symbol include/mlsb200.h declares: name -> (restype, argtypes)
@@ -51,6 +63,8 @@ API = {
     "mlsb_worker_create": (C.c_int, [C.POINTER(WorkerConfig), C.POINTER(_P)]),
     "mlsb_worker_destroy": (None, [_P]),
     "mlsb_worker_resource_usage": (C.c_int, [C.POINTER(WorkerConfig), C.POINTER(C.c_uint64)]),
+    "mlsb_worker_resource_usage_ex": (C.c_int, [C.POINTER(WorkerConfig), C.POINTER(ResourceUsage)]),
+    "mlsb_validate_device": (C.c_int, [C.c_int]),
     "mlsb_worker_stream": (_P, [_P]),
     "mlsb_worker_synchronize": (C.c_int, [_P]),
     "mlsb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
@@ -67,6 +81,9 @@ API = {
     "mlsb_set_scale_bias": (C.c_int, [_P, C.c_float, _P]),
     "mlsb_marching_generate": (C.c_int, [_P, _P, _P, MESH_SINK, _P]),
     "mlsb_marching_generate_host_field": (C.c_int, [_P, _P, _P, _P, MESH_SINK, _P]),
+    "mlsb_marching_generate_cb": (C.c_int, [_P, FIELD_GENERATOR, _P, _P, _P, MESH_SINK, _P]),
+    "mlsb_marching_generate_device": (C.c_int, [_P, FIELD_GENERATOR, _P, _P, _P, DEVICE_MESH_SINK, _P]),
+    "mlsb_device_mesh_read": (C.c_int, [_P, C.POINTER(DeviceMesh), _P]),
     "mlsb_mesh_host_bytes": (C.c_uint64, [C.POINTER(MeshSizes)]),
     "mlsb_marching_tables": (C.c_int, [_P, _P, _P, _P]),
     "mlsb_worker_process_bin": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, MESH_SINK, _P]),
@@ -130,6 +147,19 @@ def device_count():
     n = C.c_int(0)
     _check(lib().mlsb_device_count(C.byref(n)))
     return n.value
+
+
+def validate_device(device=0):
+    """Raises MlsbError with the reason if the library cannot run on `device`."""
+    _check(lib().mlsb_validate_device(device))
+
+
+def resource_usage(**kw):
+    """mlsb_worker_resource_usage_ex for a Worker(**kw) configuration: dict of device / largest allocation / pinned bytes."""
+    cfg = Worker.config(**kw)
+    u = ResourceUsage()
+    _check(lib().mlsb_worker_resource_usage_ex(C.byref(cfg), C.byref(u)))
+    return dict(device_bytes=u.deviceBytes, max_allocation_bytes=u.maxAllocationBytes, pinned_host_bytes=u.pinnedHostBytes)
 
 
 def measure_fp32_peak(device=0):
@@ -223,12 +253,15 @@ class Worker:
         self._borrowed = True
         return self
 
-    def __init__(self, device=0, max_levels=6, subsampling=3, max_splats=1 << 20, max_cells=255,
-                 mesh_bytes=None, shape=0, boundary_limit=1.0):
+    @staticmethod
+    def config(device=0, max_levels=6, subsampling=3, max_splats=1 << 20, max_cells=255,
+               mesh_bytes=None, shape=0, boundary_limit=1.0):
         if mesh_bytes is None:
             mesh_bytes = max(64 << 20, max_cells * max_cells * 872)
-        self.cfg = WorkerConfig(device, max_levels, subsampling, max_splats, max_cells, mesh_bytes, shape,
-                                boundary_limit)
+        return WorkerConfig(device, max_levels, subsampling, max_splats, max_cells, mesh_bytes, shape, boundary_limit)
+
+    def __init__(self, **kw):
+        self.cfg = Worker.config(**kw)
         self.h = _P()
         _check(lib().mlsb_worker_create(C.byref(self.cfg), C.byref(self.h)))
         self._keep = []
@@ -362,6 +395,45 @@ class Worker:
         ko = _arr3(key_offset, np.uint32)
         _check(lib().mlsb_marching_generate_host_field(self.h, field.ctypes.data, size.ctypes.data, ko.ctypes.data,
                                                        cb, None))
+        return blocks
+
+    def marching_generate_cb(self, fill, size, key_offset):
+        """Marching::generate with a generator callback: fill(device_field_ptr, pitch, swathe, stream) -> 0."""
+        blocks = []
+        cb = self._collector(blocks)
+        gen = FIELD_GENERATOR(lambda _u, field, pitch, sw, stream: int(fill(field, pitch, sw.contents, stream) or 0))
+        size = _arr3(size, np.uint32)
+        ko = _arr3(key_offset, np.uint32)
+        _check(lib().mlsb_marching_generate_cb(self.h, gen, None, size.ctypes.data, ko.ctypes.data, cb, None))
+        return blocks
+
+    def marching_generate_device(self, size, key_offset, visit=None, fill=None):
+        """Marching::generate handing out DeviceKeyMesh blocks.  visit(mesh: DeviceMesh, stream) may change the
+        device buffers (a MeshFilter); every block is then read back with mlsb_device_mesh_read."""
+        blocks = []
+
+        def sink(mesh_p, stream, _user):
+            mesh = mesh_p.contents
+            if visit is not None:
+                visit(mesh, stream)
+            s = mesh.sizes
+            nv, nt, ni = int(s.numVertices), int(s.numTriangles), int(s.numInternalVertices)
+            ne = nv - ni
+            raw = np.empty(max(8 * ne + 12 * nv + 12 * nt, 1), np.uint8)
+            st = lib().mlsb_device_mesh_read(self.h, mesh_p, raw.ctypes.data)
+            if st != 0:
+                return st
+            blocks.append(dict(vertices=raw[8 * ne:8 * ne + 12 * nv].view(np.float32).reshape(nv, 3).copy(),
+                               external_keys=raw[:8 * ne].view(np.uint64).copy(),
+                               triangles=raw[8 * ne + 12 * nv:8 * ne + 12 * nv + 12 * nt].view(np.uint32).reshape(nt, 3).copy(),
+                               num_internal=ni))
+            return 0
+        cb = DEVICE_MESH_SINK(sink)
+        gen = FIELD_GENERATOR(lambda _u, field, pitch, sw, stream: int(fill(field, pitch, sw.contents, stream) or 0)) \
+            if fill is not None else FIELD_GENERATOR()
+        size = _arr3(size, np.uint32)
+        ko = _arr3(key_offset, np.uint32)
+        _check(lib().mlsb_marching_generate_device(self.h, gen, None, size.ctypes.data, ko.ctypes.data, cb, None))
         return blocks
 
     def process_bin(self, first, n, size, offset, collect=True):

@@ -114,6 +114,12 @@ static int validateConfig(const mlsb_worker_config *c)
     MLSB_REQUIRE(c->subsampling + c->maxLevels - 1 < 32, MLSB_ERR_INVALID_ARGUMENT, "levels + subsampling too large");
     MLSB_REQUIRE(c->shape == MLSB_SHAPE_SPHERE || c->shape == MLSB_SHAPE_PLANE, MLSB_ERR_INVALID_ARGUMENT, "unknown shape");
     MLSB_REQUIRE(c->maxCells >= 1, MLSB_ERR_INVALID_ARGUMENT, "maxCells must be positive");
+    // src/marching.cpp:311-315 (the reference's MAX_DIMENSION is 8192; the lattice words and tile layout here
+    // carry 512 corners per axis), :316-318 (mesh memory for at least one slice of worst-case cells)
+    MLSB_REQUIRE(c->maxCells + 1 <= MLSB_MAX_DIMENSION, MLSB_ERR_INVALID_ARGUMENT, "maxCells + 1 must be in [2, 512]");
+    MLSB_REQUIRE(c->meshBytes >= (uint64_t) c->maxCells * c->maxCells * kMaxCellBytes, MLSB_ERR_INVALID_ARGUMENT,
+                 "meshBytes smaller than one slice of worst-case cells");
+    MLSB_REQUIRE(c->meshBytes / kMaxCellBytes * kMaxCellIndices < (1ull << 31), MLSB_ERR_LENGTH, "meshBytes too large");
     return MLSB_OK;
 }
 
@@ -135,23 +141,62 @@ const char *mlsb_last_error_string(void) { return gError; }
 
 const char *mlsb_version(void) { return "mlsb200 0.1 (sm_100a)"; }
 
-int mlsb_worker_resource_usage(const mlsb_worker_config *c, uint64_t *deviceBytes)
+// words of the scan scratch shared by the general octree path (computed in one place for create and usage)
+static uint64_t scanStatusWordsFor(const mlsb_worker_config *c)
+{
+    const uint64_t maxStart = (1ull << (3 * c->maxLevels)) / 7;
+    return std::max<uint64_t>(divUp<uint64_t>(maxStart, 2048) + 2, divUp<uint64_t>(c->maxSplats, 256) + 2);
+}
+
+int mlsb_worker_resource_usage_ex(const mlsb_worker_config *c, mlsb_resource_usage *usage)
 {
     MLSB_TRY(validateConfig(c));
+    MLSB_REQUIRE(usage != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
+    uint64_t maxOct = 0, maxMarch = 0, pinned = 0;
+    uint64_t total = (uint64_t) c->maxSplats * sizeof(mlsb_splat);                  // DeviceWorkerGroup::WorkItem::splats
+    total += octreeDeviceBytes(*c, &maxOct);
+    total += marchingDeviceBytes(*c, &maxMarch, &pinned);
+    total += 2 * sizeof(unsigned long long);                                         // MLS work counters
+    total += scanStatusWordsFor(c) * sizeof(uint64_t) + 4 * sizeof(uint32_t);        // scan status + tickets
+    usage->deviceBytes = total;
+    usage->maxAllocationBytes = std::max<uint64_t>({maxOct, maxMarch, (uint64_t) c->maxSplats * sizeof(mlsb_splat)});
+    usage->pinnedHostBytes = pinned;
+    return MLSB_OK;
+}
+
+int mlsb_worker_resource_usage(const mlsb_worker_config *c, uint64_t *deviceBytes)
+{
     MLSB_REQUIRE(deviceBytes != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
-    uint64_t maxStart = (1ull << (3 * c->maxLevels)) / 7;
-    uint64_t entries = 8ull * c->maxSplats;
-    uint64_t ranges = maxStart < entries ? maxStart : entries;
-    uint64_t dim = roundUp<uint64_t>(c->maxCells + 1, kMlsWgs);
-    uint64_t meshCells = c->meshBytes / kMaxCellBytes;
-    uint64_t vs = meshCells * kMaxCellVertices, is = meshCells * kMaxCellIndices;
-    uint64_t total = 0;
-    total += (uint64_t) c->maxSplats * sizeof(mlsb_splat);
-    total += maxStart * 4 * 6 + (entries + 2 * ranges) * 4 + entries * 4 * 4;   // octree
-    total += dim * dim * dim * 4;                                               // field
-    uint64_t lattice = (2ull * c->maxCells + 1) * (2ull * c->maxCells + 1) * (2 * divUp<uint64_t>(c->maxCells, 32) + 1);
-    total += vs * 2 * (12 + 8) + is * 4 + lattice * 12;                         // marching
-    *deviceBytes = total;
+    mlsb_resource_usage u;
+    MLSB_TRY(mlsb_worker_resource_usage_ex(c, &u));
+    *deviceBytes = u.deviceBytes;
+    return MLSB_OK;
+}
+
+int mlsb_validate_device(int device)
+{
+    int ndev = 0;
+    MLSB_CUDA(cudaGetDeviceCount(&ndev));
+    MLSB_REQUIRE(device >= 0 && device < ndev, MLSB_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    cudaDeviceProp p;
+    MLSB_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10)
+    {
+        setError("device %d (%s) has compute capability %d.%d: this library is built for sm_100a only", device, p.name, p.major, p.minor);
+        return MLSB_ERR_CUDA;
+    }
+    if (p.sharedMemPerBlockOptin < 96 * 1024)
+    {
+        setError("device %d offers %zu bytes of shared memory per block, the large sort tiles need 96 KiB", device, p.sharedMemPerBlockOptin);
+        return MLSB_ERR_CUDA;
+    }
+    int clusters = 0;
+    MLSB_CUDA(cudaDeviceGetAttribute(&clusters, cudaDevAttrClusterLaunch, device));
+    if (!clusters)
+    {
+        setError("device %d cannot launch thread-block clusters (the octree's plan kernel is one)", device);
+        return MLSB_ERR_CUDA;
+    }
     return MLSB_OK;
 }
 
@@ -164,6 +209,7 @@ int mlsb_worker_create(const mlsb_worker_config *config, mlsb_worker **out)
     MLSB_CUDA(cudaGetDeviceCount(&ndev));
     MLSB_REQUIRE(ndev > 0, MLSB_ERR_CUDA, "no CUDA device: mlsb200 has no CPU fallback");
     MLSB_REQUIRE(config->device >= 0 && config->device < ndev, MLSB_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    MLSB_TRY(mlsb_validate_device(config->device));
     MLSB_CUDA(cudaSetDevice(config->device));
 
     mlsb_worker *w = new (std::nothrow) mlsb_worker();
@@ -206,10 +252,7 @@ int mlsb_worker_create(const mlsb_worker_config *config, mlsb_worker **out)
     if ((st = mlsAlloc(w)) != MLSB_OK) return fail(st);
     if ((st = marchingAlloc(w)) != MLSB_OK) return fail(st);
     // shared scan scratch (the sort's lives with the octree's, see octreeAlloc)
-    uint64_t cells = (uint64_t) config->maxCells * config->maxCells * config->maxCells;
-    uint64_t words = std::max<uint64_t>({divUp<uint64_t>(cells, 256) + 2, divUp<uint64_t>(w->numStartMax, 2048) + 2,
-                                         divUp<uint64_t>(config->maxSplats, 256) + 2,
-                                         divUp<uint64_t>(w->latticeWords, 2048) + 2});
+    const uint64_t words = scanStatusWordsFor(config);
     w->scanStatusWords = (uint32_t) words;
     if (cudaMalloc(&w->scanStatus, words * sizeof(uint64_t)) != cudaSuccess
         || cudaMalloc(&w->scanTicket, 4 * sizeof(uint32_t)) != cudaSuccess)
@@ -253,6 +296,7 @@ int mlsb_worker_synchronize(mlsb_worker *w)
     MLSB_REQUIRE(w != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null worker");
     MLSB_CUDA(cudaStreamSynchronize(w->copyStream));
     MLSB_CUDA(cudaStreamSynchronize(w->stream));
+    w->copyPending = false;
     collectStats(w);
     return MLSB_OK;
 }
@@ -373,7 +417,11 @@ int mlsb_marching_generate(mlsb_worker *w, const uint32_t size[3], const uint32_
 {
     MLSB_REQUIRE(w != nullptr && size != nullptr && keyOffset != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
     MLSB_CUDA(cudaSetDevice(w->device));
-    int st = marchingGenerate(w, true, nullptr, size, keyOffset, sink, user);
+    MarchIo io;
+    io.useMls = true;
+    io.sink = sink;
+    io.user = user;
+    int st = marchingGenerate(w, io, size, keyOffset);
     collectStats(w);
     return st;
 }
@@ -383,9 +431,51 @@ int mlsb_marching_generate_host_field(mlsb_worker *w, const float *hostField, co
 {
     MLSB_REQUIRE(w != nullptr && size != nullptr && keyOffset != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
     MLSB_CUDA(cudaSetDevice(w->device));
-    int st = marchingGenerate(w, false, hostField, size, keyOffset, sink, user);
+    MarchIo io;
+    io.hostField = hostField;
+    io.sink = sink;
+    io.user = user;
+    int st = marchingGenerate(w, io, size, keyOffset);
     collectStats(w);
     return st;
+}
+
+int mlsb_marching_generate_cb(mlsb_worker *w, mlsb_field_generator generate, void *generatorUser, const uint32_t size[3],
+                              const uint32_t keyOffset[3], mlsb_mesh_sink sink, void *user)
+{
+    MLSB_REQUIRE(w != nullptr && generate != nullptr && size != nullptr && keyOffset != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
+    MLSB_CUDA(cudaSetDevice(w->device));
+    MarchIo io;
+    io.generate = generate;
+    io.generateUser = generatorUser;
+    io.sink = sink;
+    io.user = user;
+    int st = marchingGenerate(w, io, size, keyOffset);
+    collectStats(w);
+    return st;
+}
+
+int mlsb_marching_generate_device(mlsb_worker *w, mlsb_field_generator generate, void *generatorUser, const uint32_t size[3],
+                                  const uint32_t keyOffset[3], mlsb_device_mesh_sink sink, void *user)
+{
+    MLSB_REQUIRE(w != nullptr && sink != nullptr && size != nullptr && keyOffset != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
+    MLSB_CUDA(cudaSetDevice(w->device));
+    MarchIo io;
+    io.useMls = generate == nullptr;
+    io.generate = generate;
+    io.generateUser = generatorUser;
+    io.deviceSink = sink;
+    io.deviceUser = user;
+    int st = marchingGenerate(w, io, size, keyOffset);
+    collectStats(w);
+    return st;
+}
+
+int mlsb_device_mesh_read(mlsb_worker *w, const mlsb_device_mesh *mesh, void *hostBlob)
+{
+    MLSB_REQUIRE(w != nullptr && mesh != nullptr && hostBlob != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
+    MLSB_CUDA(cudaSetDevice(w->device));
+    return marchingReadDeviceMesh(w, mesh, hostBlob);
 }
 
 uint64_t mlsb_mesh_host_bytes(const mlsb_mesh_sizes *s)

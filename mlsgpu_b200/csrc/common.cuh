@@ -236,6 +236,7 @@ int radixSortPairsDeviceCount(mlsb_worker *w, uint32_t *keys[2], uint32_t *value
 // commands[1 + position + 2 * runIndex[key]] = value.  n = host-side bound, *nDev the real count.
 int radixSortToCommands(mlsb_worker *w, uint32_t *keys[2], uint32_t *values[2], uint32_t n, const uint32_t *nDev,
                         uint32_t bits, int32_t *commands, const uint32_t *runIndex, const char *statName);
+size_t sortScratchBytes(size_t maxItems, uint32_t maxPasses);   // what sortScratchAlloc allocates behind the prefix
 // bytes of sort scratch (from s.hist on) a sort of n items with `passes` passes touches
 size_t sortScratchBytesUsed(const SortScratch &s, uint32_t n, uint32_t passes);
 
@@ -254,8 +255,23 @@ int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &
 // marching.cu
 int marchingAlloc(mlsb_worker *w);
 void marchingFree(mlsb_worker *w);
-int marchingGenerate(mlsb_worker *w, bool useMls, const float *hostField, const uint32_t size[3],
-                     const uint32_t keyOffset[3], mlsb_mesh_sink sink, void *user);
+// where the field comes from (MlsFunctor bound to the worker / a host array / any generator) and where
+// the blocks go (host blobs / device meshes)
+struct MarchIo
+{
+    bool useMls = false;
+    const float *hostField = nullptr;
+    mlsb_field_generator generate = nullptr;
+    void *generateUser = nullptr;
+    mlsb_mesh_sink sink = nullptr;
+    void *user = nullptr;
+    mlsb_device_mesh_sink deviceSink = nullptr;
+    void *deviceUser = nullptr;
+};
+int marchingGenerate(mlsb_worker *w, const MarchIo &io, const uint32_t size[3], const uint32_t keyOffset[3]);
+int marchingReadDeviceMesh(mlsb_worker *w, const mlsb_device_mesh *mesh, void *hostBlob);
+uint64_t marchingDeviceBytes(const mlsb_worker_config &c, uint64_t *maxAllocation, uint64_t *pinnedHost);
+uint64_t octreeDeviceBytes(const mlsb_worker_config &c, uint64_t *maxAllocation);
 int marchingTablesHost(uint8_t *count, uint16_t *start, uint8_t *data, uint32_t *key);
 
 }  // namespace mlsb

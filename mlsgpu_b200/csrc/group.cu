@@ -67,7 +67,10 @@ void groupTrampoline(const mlsb_mesh_sizes *sizes, const void *blob, void *user)
     SinkContext *ctx = static_cast<SinkContext *>(user);
     mlsb_group *g = ctx->group;
     g->meshBytes += mlsb_mesh_host_bytes(sizes);
-    if (g->sink)
+    if (!g->sink) return;
+    // A C++ consumer may throw (bad_alloc in a mesher, say): nothing may unwind through the C ABI and the
+    // worker thread, so the failure is recorded and reported by mlsb_group_wait like any other.
+    try
     {
         if (g->concurrentSink)
             g->sink(ctx->tag, sizes, blob, g->user);
@@ -75,6 +78,24 @@ void groupTrampoline(const mlsb_mesh_sizes *sizes, const void *blob, void *user)
         {
             std::lock_guard<std::mutex> lock(g->sinkMutex);
             g->sink(ctx->tag, sizes, blob, g->user);
+        }
+    }
+    catch (const std::exception &e)
+    {
+        std::lock_guard<std::mutex> lock(g->errorMutex);
+        if (g->status == MLSB_OK)
+        {
+            g->status = MLSB_ERR_STATE;
+            g->message = std::string("mesh sink failed: ") + e.what();
+        }
+    }
+    catch (...)
+    {
+        std::lock_guard<std::mutex> lock(g->errorMutex);
+        if (g->status == MLSB_OK)
+        {
+            g->status = MLSB_ERR_STATE;
+            g->message = "mesh sink failed with an unknown exception";
         }
     }
 }
@@ -113,7 +134,7 @@ void workerLoop(mlsb_group *g, size_t index)
         {
             std::unique_lock<std::mutex> lock(g->mutex);
             g->canPop.wait(lock, [g] { return g->stopping || !g->queue.empty(); });
-            if (g->queue.empty()) return;   // stopping
+            if (g->stopping || g->queue.empty()) return;   // on destroy, bins still queued are dropped, not processed
             item = g->queue.front();
             g->queue.pop_front();
             g->inFlight++;
@@ -134,6 +155,9 @@ void workerLoop(mlsb_group *g, size_t index)
         if (st == MLSB_OK) st = mlsb_worker_process_bin(w, 0, item.numSplats, item.size, item.offset, groupTrampoline, &ctx);
         if (st != MLSB_OK)
         {
+            // the bin may have failed before the compute stream waited for the upload (argument checks):
+            // the staging buffer must not be overwritten while that copy is still in flight
+            mlsb_worker_synchronize(w);
             std::lock_guard<std::mutex> lock(g->errorMutex);
             if (g->status == MLSB_OK)
             {
@@ -202,6 +226,7 @@ void mlsb_group_destroy(mlsb_group *g)
     }
     g->canPop.notify_all();
     for (std::thread &t : g->threads) t.join();
+    g->queue.clear();
     for (mlsb_worker *w : g->workers) mlsb_worker_destroy(w);
     for (mlsb_splat *p : g->staging)
         if (p) cudaFreeHost(p);

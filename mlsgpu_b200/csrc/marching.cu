@@ -804,49 +804,110 @@ int marchingTablesHost(uint8_t *count, uint16_t *start, uint8_t *data, uint32_t 
     return MLSB_OK;
 }
 
+namespace
+{
+
+// Every buffer marchingAlloc makes, in bytes: the ONE place sizes are computed, so that
+// mlsb_worker_resource_usage reports what a worker really takes.
+struct MarchSizes
+{
+    uint32_t fieldDim, maxTiles, latStatusWords;
+    uint64_t vertexSpace, indexSpace;
+    size_t latticeWords;
+    size_t field, blockActive, latMask, latRecord, indices, welded, weldedKeys, counters, tileTotals, tileList, tables;
+    size_t hostBlobWorst;
+};
+
+MarchSizes marchSizes(const mlsb_worker_config &c)
+{
+    MarchSizes z{};
+    z.fieldDim = roundUp(c.maxCells + 1, (uint32_t) kMlsWgs);
+    const uint64_t meshCells = c.meshBytes / kMaxCellBytes;
+    z.vertexSpace = meshCells * kMaxCellVertices;    // src/marching.cpp:389-392
+    z.indexSpace = meshCells * kMaxCellIndices;
+    z.field = (size_t) z.fieldDim * z.fieldDim * z.fieldDim * sizeof(float);
+    const size_t nb = roundUp(z.fieldDim / kMlsWgs, 4u);
+    z.blockActive = nb * nb * nb + 16;
+    // lattice of edge midpoints for the largest block: (2 cells + 1)^2 rows of 2 words per 32 cells (+1 carry word)
+    z.latticeWords = (size_t) (2 * c.maxCells + 1) * (2 * c.maxCells + 1) * (2 * divUp(c.maxCells, 32u) + 1);
+    z.latMask = z.latticeWords * sizeof(uint32_t);
+    z.latRecord = z.latticeWords * sizeof(uint4);
+    z.indices = (z.indexSpace + 1) * sizeof(uint32_t);
+    z.welded = (z.vertexSpace + 1) * 3 * sizeof(float);        // twice: unflagged and flagged vertices
+    z.weldedKeys = (z.vertexSpace + 1) * sizeof(uint64_t);     // twice
+    z.latStatusWords = (uint32_t) divUp(z.latticeWords, (size_t) (kLatThreads * kLatItems)) + 2;
+    z.counters = CTR_COUNT * sizeof(uint32_t) + (size_t) z.latStatusWords * sizeof(uint64_t);
+    z.maxTiles = c.maxCells * divUp(c.maxCells, (uint32_t) kGenRows);
+    z.tileTotals = (size_t) z.maxTiles * sizeof(uint64_t);
+    z.tileList = (size_t) z.maxTiles * sizeof(uint32_t);
+    z.tables = sizeof(Tables);
+    mlsb_mesh_sizes worst{z.vertexSpace, z.indexSpace / 3, 0};
+    z.hostBlobWorst = mlsb_mesh_host_bytes(&worst) + 64;
+    return z;
+}
+
+// The read-back blob grows on demand: the reference's sizing rule gives 124 MB of pinned memory per
+// worker at 256 MB of mesh memory, the largest C2 block needs 12.
+int ensureHostBlob(mlsb_worker *w, size_t bytes)
+{
+    if (bytes <= w->hostBlobBytes) return MLSB_OK;
+    size_t want = std::max(bytes + bytes / 2, (size_t) 4 << 20);
+    if (w->hostBlob) MLSB_CUDA(cudaFreeHost(w->hostBlob));
+    w->hostBlob = nullptr;
+    w->hostBlobBytes = 0;
+    MLSB_CUDA(cudaMallocHost(&w->hostBlob, want));
+    w->hostBlobBytes = want;
+    return MLSB_OK;
+}
+
+}  // namespace
+
+uint64_t marchingDeviceBytes(const mlsb_worker_config &c, uint64_t *maxAllocation, uint64_t *pinnedHost)
+{
+    const MarchSizes z = marchSizes(c);
+    const size_t all[] = {z.field, z.blockActive, z.latMask, z.latRecord, z.indices, z.welded, z.welded, z.weldedKeys, z.weldedKeys,
+                          z.counters, z.tileTotals, z.tileList, z.tables};
+    uint64_t total = 0, largest = 0;
+    for (size_t b : all)
+    {
+        total += b;
+        largest = std::max<uint64_t>(largest, b);
+    }
+    if (maxAllocation) *maxAllocation = largest;
+    if (pinnedHost) *pinnedHost = z.hostBlobWorst + CTR_COUNT * sizeof(uint32_t);   // the blob's upper bound: it grows on demand
+    return total;
+}
+
 int marchingAlloc(mlsb_worker *w)
 {
     const mlsb_worker_config &c = w->cfg;
-    const uint32_t corners = c.maxCells + 1;
-    // src/marching.cpp:311-315 (the reference's MAX_DIMENSION is 8192; the compact sort key
-    // used here carries 10 bits per axis)
-    MLSB_REQUIRE(corners >= 2 && corners <= 512, MLSB_ERR_INVALID_ARGUMENT, "maxCells + 1 must be in [2, 512]");
-    MLSB_REQUIRE(c.meshBytes >= (uint64_t) c.maxCells * c.maxCells * kMaxCellBytes, MLSB_ERR_INVALID_ARGUMENT,
-                 "meshBytes smaller than one slice of worst-case cells");
     buildTables();
-    w->fieldDim = roundUp(corners, (uint32_t) kMlsWgs);
-    const uint64_t meshCells = c.meshBytes / kMaxCellBytes;
-    w->vertexSpace = meshCells * kMaxCellVertices;
-    w->indexSpace = meshCells * kMaxCellIndices;
-    MLSB_REQUIRE(w->vertexSpace < (1ull << 31) && w->indexSpace < (1ull << 31), MLSB_ERR_LENGTH, "meshBytes too large");
-    MLSB_CUDA(cudaMalloc(&w->field, (size_t) w->fieldDim * w->fieldDim * w->fieldDim * sizeof(float)));
-    {
-        const size_t nb = roundUp(w->fieldDim / kMlsWgs, 4u);
-        MLSB_CUDA(cudaMalloc(&w->blockActive, nb * nb * nb + 16));
-        MLSB_CUDA(cudaMemset(w->blockActive, 0, nb * nb * nb + 16));
-    }
-    // lattice of edge midpoints for the largest block: (2 cells + 1)^2 rows of 2 words per 32 cells (+1 carry word)
-    w->latticeWords = (size_t) (2 * c.maxCells + 1) * (2 * c.maxCells + 1) * (2 * divUp(c.maxCells, 32u) + 1);
+    const MarchSizes z = marchSizes(c);
+    w->fieldDim = z.fieldDim;
+    w->vertexSpace = z.vertexSpace;
+    w->indexSpace = z.indexSpace;
+    w->latticeWords = z.latticeWords;
+    w->latStatusWords = z.latStatusWords;
+    w->maxTiles = z.maxTiles;
     MLSB_REQUIRE(w->latticeWords < (1ull << 32) - kLatThreads * kLatItems, MLSB_ERR_LENGTH, "lattice too large");
-    MLSB_CUDA(cudaMalloc(&w->latMask, w->latticeWords * sizeof(uint32_t)));
-    MLSB_CUDA(cudaMalloc(&w->latRecord, w->latticeWords * sizeof(uint4)));
-    MLSB_CUDA(cudaMalloc(&w->indices, (w->indexSpace + 1) * sizeof(uint32_t)));
-    MLSB_CUDA(cudaMalloc(&w->welded, (w->vertexSpace + 1) * 3 * sizeof(float)));
-    MLSB_CUDA(cudaMalloc(&w->weldedKeys, (w->vertexSpace + 1) * sizeof(uint64_t)));
-    MLSB_CUDA(cudaMalloc(&w->weldedFlagged, (w->vertexSpace + 1) * 3 * sizeof(float)));
-    MLSB_CUDA(cudaMalloc(&w->weldedKeysFlagged, (w->vertexSpace + 1) * sizeof(uint64_t)));
-    // [counters | look-back words of the lattice scan]: one memset per block
-    w->latStatusWords = (uint32_t) divUp(w->latticeWords, (size_t) (kLatThreads * kLatItems)) + 2;
-    MLSB_CUDA(cudaMalloc(&w->marchCounters, CTR_COUNT * sizeof(uint32_t) + (size_t) w->latStatusWords * sizeof(uint64_t)));
+    MLSB_CUDA(cudaMalloc(&w->field, z.field));
+    MLSB_CUDA(cudaMalloc(&w->blockActive, z.blockActive));
+    MLSB_CUDA(cudaMemset(w->blockActive, 0, z.blockActive));
+    MLSB_CUDA(cudaMalloc(&w->latMask, z.latMask));
+    MLSB_CUDA(cudaMalloc(&w->latRecord, z.latRecord));
+    MLSB_CUDA(cudaMalloc(&w->indices, z.indices));
+    MLSB_CUDA(cudaMalloc(&w->welded, z.welded));
+    MLSB_CUDA(cudaMalloc(&w->weldedKeys, z.weldedKeys));
+    MLSB_CUDA(cudaMalloc(&w->weldedFlagged, z.welded));
+    MLSB_CUDA(cudaMalloc(&w->weldedKeysFlagged, z.weldedKeys));
+    // [counters | per-chunk counts of the lattice scan]
+    MLSB_CUDA(cudaMalloc(&w->marchCounters, z.counters));
     w->latStatus = reinterpret_cast<uint64_t *>(w->marchCounters + CTR_COUNT);
-    w->maxTiles = c.maxCells * divUp(c.maxCells, (uint32_t) kGenRows);
-    MLSB_CUDA(cudaMalloc(&w->tileTotals, (size_t) w->maxTiles * sizeof(uint64_t)));
-    MLSB_CUDA(cudaMalloc(&w->tileList, (size_t) w->maxTiles * sizeof(uint32_t)));
-    MLSB_CUDA(cudaMalloc(&w->tables, sizeof(Tables)));
+    MLSB_CUDA(cudaMalloc(&w->tileTotals, z.tileTotals));
+    MLSB_CUDA(cudaMalloc(&w->tileList, z.tileList));
+    MLSB_CUDA(cudaMalloc(&w->tables, z.tables));
     MLSB_CUDA(cudaMemcpy(w->tables, &gTables.t, sizeof(Tables), cudaMemcpyHostToDevice));
-    mlsb_mesh_sizes worst{w->vertexSpace, w->indexSpace / 3, 0};
-    w->hostBlobBytes = mlsb_mesh_host_bytes(&worst) + 64;
-    MLSB_CUDA(cudaMallocHost(&w->hostBlob, w->hostBlobBytes));
+    MLSB_TRY(ensureHostBlob(w, (size_t) 8 << 20));
     MLSB_CUDA(cudaMallocHost(&w->hostCounters, CTR_COUNT * sizeof(uint32_t)));
     MLSB_CUDA(cudaFuncSetAttribute(generateCellsKernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (2 * kGenRows * 2 + (int) kMaxCellVertices) * kGenThreads * (int) sizeof(uint32_t)));
@@ -880,7 +941,7 @@ namespace
 // fit in the worker's mesh memory (the caller then splits the z range, as
 // src/marching.cpp:651-704 does with its per-slice histogram).
 int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, const uint32_t size[3], uint32_t zFirst,
-              uint32_t zLast, const uint32_t keyOffset[3], mlsb_mesh_sink sink, void *user)
+              uint32_t zLast, const uint32_t keyOffset[3], const MarchIo &io)
 {
     cudaStream_t s = w->stream;
     const uint32_t cellsX = size[0] - 1, cellsY = size[1] - 1;
@@ -1000,7 +1061,29 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     // unflagged vertices (internal, then the top plane) and flagged ones live in two buffers
     const uint64_t numUnflagged = hc[CTR_UNFLAGGED], numFlagged = sizes.numVertices - numUnflagged;
     const uint64_t numTop = numUnflagged - sizes.numInternalVertices;
+    if (io.deviceSink)
+    {
+        // DeviceKeyMesh (src/mesh.h:101-123): one vertex and one key array, internal vertices first.  The flagged
+        // vertices (and their keys) move in behind the unflagged ones, device to device.
+        if (numFlagged)
+        {
+            MLSB_CUDA(cudaMemcpyAsync(w->welded + 3 * numUnflagged, w->weldedFlagged, numFlagged * 3 * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, s));
+            MLSB_CUDA(cudaMemcpyAsync(w->weldedKeys + numUnflagged, w->weldedKeysFlagged, numFlagged * sizeof(uint64_t),
+                                      cudaMemcpyDeviceToDevice, s));
+        }
+        mlsb_device_mesh mesh{sizes, w->welded, w->weldedKeys, w->indices};
+        const int rc = io.deviceSink(&mesh, (void *) s, io.deviceUser);
+        MLSB_TRY(waitStream(w));
+        if (rc != 0)
+        {
+            setError("the device mesh sink returned %d", rc);
+            return MLSB_ERR_STATE;
+        }
+        return MLSB_OK;
+    }
     // HostKeyMesh layout, src/mesh.cpp:51-60
+    MLSB_TRY(ensureHostBlob(w, (size_t) mlsb_mesh_host_bytes(&sizes)));
     uint8_t *blob = static_cast<uint8_t *>(w->hostBlob);
     uint8_t *hKeys = blob;
     uint8_t *hVerts = hKeys + numExternal * sizeof(uint64_t);
@@ -1019,14 +1102,14 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     if (numUnflagged)
         MLSB_CUDA(cudaMemcpyAsync(hVerts, w->welded, numUnflagged * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
     MLSB_TRY(waitStream(w));
-    if (sink) sink(&sizes, blob, user);
+    if (io.sink) io.sink(&sizes, blob, io.user);
     return MLSB_OK;
 }
 
 int shipRange(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, const uint32_t size[3], uint32_t zFirst,
-              uint32_t zLast, const uint32_t keyOffset[3], mlsb_mesh_sink sink, void *user)
+              uint32_t zLast, const uint32_t keyOffset[3], const MarchIo &io)
 {
-    int st = shipBlock(w, useActive, pitch, zStride, size, zFirst, zLast, keyOffset, sink, user);
+    int st = shipBlock(w, useActive, pitch, zStride, size, zFirst, zLast, keyOffset, io);
     if (st != MLSB_ERR_OVERFLOW) return st;
     if (zLast - zFirst <= 1)
     {
@@ -1036,14 +1119,13 @@ int shipRange(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     // Too big for the mesh memory: split the slice range and ship the halves separately; the
     // seam is welded by the consumer through the external vertex keys.
     uint32_t mid = zFirst + (zLast - zFirst) / 2;
-    MLSB_TRY(shipRange(w, useActive, pitch, zStride, size, zFirst, mid, keyOffset, sink, user));
-    return shipRange(w, useActive, pitch, zStride, size, mid, zLast, keyOffset, sink, user);
+    MLSB_TRY(shipRange(w, useActive, pitch, zStride, size, zFirst, mid, keyOffset, io));
+    return shipRange(w, useActive, pitch, zStride, size, mid, zLast, keyOffset, io);
 }
 
 }  // namespace
 
-int marchingGenerate(mlsb_worker *w, bool useMls, const float *hostField, const uint32_t size[3],
-                     const uint32_t keyOffset[3], mlsb_mesh_sink sink, void *user)
+int marchingGenerate(mlsb_worker *w, const MarchIo &io, const uint32_t size[3], const uint32_t keyOffset[3])
 {
     // src/marching.cpp:767-769
     for (int i = 0; i < 3; i++)
@@ -1053,17 +1135,25 @@ int marchingGenerate(mlsb_worker *w, bool useMls, const float *hostField, const 
                      "global coordinates exceed MAX_GLOBAL_DIMENSION");
     const uint32_t pitch = roundUp(size[0], (uint32_t) kMlsWgs);
     const uint32_t zStride = roundUp(size[1], (uint32_t) kMlsWgs);
-    if (useMls)
-    {
-        mlsb_swathe sw{size[0], size[1], zStride, 0, 0, size[2] - 1};
+    const mlsb_swathe sw{size[0], size[1], zStride, 0, 0, size[2] - 1};
+    if (io.useMls)
         MLSB_TRY(mlsCorners(w, w->field, pitch, sw, true));
+    else if (io.generate)
+    {
+        // Marching::Generator::enqueue (src/marching.h:229-252): one swathe, the whole bin
+        const int rc = io.generate(io.generateUser, w->field, pitch, &sw, (void *) w->stream);
+        if (rc != 0)
+        {
+            setError("the field generator returned %d", rc);
+            return MLSB_ERR_STATE;
+        }
     }
     else
     {
-        MLSB_REQUIRE(hostField != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null field");
+        MLSB_REQUIRE(io.hostField != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null field");
         for (uint32_t z = 0; z < size[2]; z++)
             MLSB_CUDA(cudaMemcpy2DAsync(w->field + (size_t) z * zStride * pitch, pitch * sizeof(float),
-                                        hostField + (size_t) z * size[1] * size[0], size[0] * sizeof(float),
+                                        io.hostField + (size_t) z * size[1] * size[0], size[0] * sizeof(float),
                                         size[0] * sizeof(float), size[1], cudaMemcpyHostToDevice, w->stream));
     }
     if (size[0] < 2 || size[1] < 2 || size[2] < 2)
@@ -1071,7 +1161,25 @@ int marchingGenerate(mlsb_worker *w, bool useMls, const float *hostField, const 
         MLSB_TRY(waitStream(w));
         return MLSB_OK;
     }
-    return shipRange(w, useMls, pitch, zStride, size, 0, size[2] - 1, keyOffset, sink, user);
+    return shipRange(w, io.useMls, pitch, zStride, size, 0, size[2] - 1, keyOffset, io);
+}
+
+// enqueueReadMesh, src/mesh.cpp:62-102
+int marchingReadDeviceMesh(mlsb_worker *w, const mlsb_device_mesh *mesh, void *hostBlob)
+{
+    const mlsb_mesh_sizes &sz = mesh->sizes;
+    const uint64_t numExternal = sz.numVertices - sz.numInternalVertices;
+    uint8_t *hKeys = static_cast<uint8_t *>(hostBlob);
+    uint8_t *hVerts = hKeys + numExternal * sizeof(uint64_t);
+    uint8_t *hTris = hVerts + sz.numVertices * 3 * sizeof(float);
+    cudaStream_t s = w->stream;
+    if (numExternal)
+        MLSB_CUDA(cudaMemcpyAsync(hKeys, mesh->vertexKeys + sz.numInternalVertices, numExternal * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (sz.numVertices)
+        MLSB_CUDA(cudaMemcpyAsync(hVerts, mesh->vertices, sz.numVertices * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (sz.numTriangles)
+        MLSB_CUDA(cudaMemcpyAsync(hTris, mesh->triangles, sz.numTriangles * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    return waitStream(w);
 }
 
 }  // namespace mlsb

@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "scan.cuh"
 #include <cooperative_groups.h>
+#include <algorithm>
 
 namespace mlsb
 {
@@ -435,6 +436,23 @@ __global__ void __launch_bounds__(256) linkLevelsKernel(int32_t *__restrict__ st
 }
 
 }  // namespace
+
+// What octreeAlloc allocates, for mlsb_worker_resource_usage (SplatTreeCL::resourceUsage, src/splat_tree_cl.cpp:68-92).
+uint64_t octreeDeviceBytes(const mlsb_worker_config &c, uint64_t *maxAllocation)
+{
+    const uint64_t maxStart = (1ull << (3 * c.maxLevels)) / 7;
+    const uint64_t maxEntries = 8ull * c.maxSplats;
+    const uint64_t maxRanges = maxStart < maxEntries ? maxStart : maxEntries;
+    const bool planned = maxStart <= kPlanMaxKeys;
+    const uint64_t entryArray = (maxEntries + 8) * sizeof(uint32_t);
+    const uint64_t commands = (maxEntries + 2 * maxRanges) * sizeof(int32_t);
+    const uint64_t statusBytes = roundUp((uint64_t) (divUp(c.maxSplats, 256u) + 1) * sizeof(uint64_t), (uint64_t) 256);
+    const uint64_t countBytes = planned ? roundUp(maxStart * sizeof(uint32_t), (uint64_t) 256) : 0;
+    const uint64_t scratch = roundUp(countBytes + statusBytes + 256, (uint64_t) 256) + sortScratchBytes(maxEntries, 4);
+    uint64_t total = maxStart * 4 * (planned ? 2 : 6) + commands + (uint64_t) c.maxSplats * sizeof(float) + 4 * entryArray + scratch;
+    if (maxAllocation) *maxAllocation = std::max(std::max(commands, entryArray), scratch);
+    return total;
+}
 
 int octreeAlloc(mlsb_worker *w)
 {

@@ -205,6 +205,12 @@ sortOnesweepKernel(const uint32_t *__restrict__ keysIn, const uint32_t *__restri
 
 }  // namespace
 
+size_t sortScratchBytes(size_t maxItems, uint32_t maxPasses)
+{
+    const size_t tiles = divUp(maxItems, (size_t) (kSortThreadsSmall * kSortItems)) + 1;
+    return ((size_t) maxPasses * kRadix + 64 + (size_t) maxPasses * tiles * kRadix) * sizeof(uint32_t);
+}
+
 int sortScratchAlloc(SortScratch &s, size_t maxItems, uint32_t maxPasses, size_t prefixBytes, void **prefix)
 {
     s.maxItems = maxItems;

@@ -128,6 +128,12 @@ public:
             chunks.back()->id = chunkId;
         }
         Chunk &chunk = *chunks[found->second];
+        // vertex and clump ids are 32-bit, as in the reference (it aborts with "too many connected
+        // components", src/mesher.cpp:237-262): fail loudly instead of wrapping into a corrupt file
+        if (chunk.totalVertices + nv > (std::size_t) UINT32_MAX)
+            throw std::overflow_error("too many vertices in one output file (2^32): use --split");
+        if (clumps.size() + b.clumpVertices.size() > (std::size_t) UINT32_MAX)
+            throw std::overflow_error("too many connected components");
         b.firstClump = (std::uint32_t) clumps.size();
         for (std::size_t c = 0; c < b.clumpVertices.size(); c++)
             clumps.push_back(Clump{b.firstClump + (std::uint32_t) c, b.clumpVertices[c]});

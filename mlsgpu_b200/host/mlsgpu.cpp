@@ -13,7 +13,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <csignal>
 #include <dirent.h>
+#include <execinfo.h>
 #include <fstream>
 #include <future>
 #include <iostream>
@@ -287,10 +289,28 @@ void meshSink(std::uint64_t tag, const mlsb_mesh_sizes *sizes, const void *blob,
     st->prepareSeconds += local;
 }
 
+
+
+// A crash report that survives being run under a harness that swallows core dumps: the raw return
+// addresses (resolve with addr2line -e mlsgpu) go to stderr before the default action runs.
+void crashHandler(int sig)
+{
+    void *frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "mlsgpu: fatal signal, backtrace follows\n";
+    if (write(2, msg, sizeof(msg) - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+
 }  // namespace
 
 int main(int argc, char **argv)
 {
+    signal(SIGSEGV, crashHandler);
+    signal(SIGBUS, crashHandler);
+    signal(SIGABRT, crashHandler);
     try
     {
         const Options o = parse(argc, argv);
@@ -324,6 +344,18 @@ int main(int argc, char **argv)
                     std::cout << out.str();
             }
             return 0;
+        }
+
+        // ---- the inputs are opened (headers parsed) before any device is touched: a bad file name or a
+        // malformed PLY is reported at once, as the reference does when it builds its FileSet ----
+        std::vector<std::string> files;
+        collectInputs(o.inputs, files);
+        std::vector<std::unique_ptr<mlsb::PlyReader>> readers;
+        std::vector<std::size_t> firsts(1, 0);
+        for (const std::string &f : files)
+        {
+            readers.emplace_back(new mlsb::PlyReader(f, (float) o.fitSmooth, (float) o.maxRadius));
+            firsts.push_back(firsts.back() + readers.back()->size());
         }
 
         // ---- device workers: one group per device (the reference: one DeviceWorkerGroup per device,
@@ -392,13 +424,29 @@ int main(int argc, char **argv)
         } guard(creating);
 
         // ---- read and condition (FastPly::Reader) ----
-        std::vector<std::string> files;
-        collectInputs(o.inputs, files);
-        for (const std::string &f : files)
         {
-            mlsb::PlyReader reader(f, (float) o.fitSmooth, (float) o.maxRadius);
-            splats.reserve(splats.size() + reader.size());
-            reader.read(0, reader.size(), splats);
+            // sizes first, then one allocation and a parallel decode per file; non-finite splats are
+            // dropped afterwards (src/splat_set.cpp:221-240), keeping the order
+            splats.resize(firsts.back());
+            for (std::size_t f = 0; f < readers.size(); f++)
+                if (!readers[f]->readRaw(0, readers[f]->size(), splats.data() + firsts[f]))
+                {
+                    // a file that cannot be mapped (a pipe, say): the buffered path, into a side vector
+                    std::vector<mlsb_splat> part;
+                    readers[f]->read(0, readers[f]->size(), part);
+                    mlsb_splat bad;
+                    std::memset(&bad, 0xFF, sizeof(bad));   // NaN in every field: dropped below
+                    std::fill(splats.begin() + (std::ptrdiff_t) firsts[f], splats.begin() + (std::ptrdiff_t) firsts[f + 1], bad);
+                    std::copy(part.begin(), part.end(), splats.begin() + (std::ptrdiff_t) firsts[f]);
+                }
+            std::size_t kept = 0;
+            for (std::size_t i = 0; i < splats.size(); i++)
+                if (mlsb::PlyReader::isFinite(splats[i]))
+                {
+                    if (kept != i) splats[kept] = splats[i];
+                    kept++;
+                }
+            splats.resize(kept);
         }
         const std::size_t numSplats = splats.size();
         if (numSplats == 0) throw std::runtime_error("At least one input point is required.");

@@ -74,6 +74,34 @@ public:
         }
     }
 
+    /// Decodes vertices [first, first + count) into out[0 .. count) — every slot is written, finite or
+    /// not — with OpenMP over the vertices of a memory-mapped file (FileSet's reader thread + OpenMP
+    /// decode, src/splat_set.cpp:212-219).  Returns false if the file cannot be mapped.
+    bool readRaw(std::size_t first, std::size_t count, mlsb_splat *out) const
+    {
+        if (count == 0) return true;
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        const std::size_t begin = headerSize + first * vertexSize, bytes = count * vertexSize;
+        const std::size_t page = (std::size_t) ::sysconf(_SC_PAGESIZE), aligned = begin / page * page;
+        void *map = ::mmap(nullptr, bytes + (begin - aligned), PROT_READ, MAP_PRIVATE, fd, (off_t) aligned);
+        ::close(fd);
+        if (map == MAP_FAILED) return false;
+        const char *base = static_cast<const char *>(map) + (begin - aligned);
+#pragma omp parallel for schedule(static)
+        for (std::int64_t i = 0; i < (std::int64_t) count; i++) out[i] = decode(base + (std::size_t) i * vertexSize);
+        ::munmap(map, bytes + (begin - aligned));
+        return true;
+    }
+
+    static bool isFinite(const mlsb_splat &s)
+    {
+        const float *f = reinterpret_cast<const float *>(&s);
+        bool finite = true;
+        for (int k = 0; k < 8; k++) finite = finite && std::isfinite(f[k]);
+        return finite;
+    }
+
 private:
     mlsb_splat decode(const char *p) const
     {

@@ -128,6 +128,51 @@ inline void split(const std::vector<mlsb_splat> &splats, const std::int64_t lo[3
 }
 }  // namespace detail
 
+/// The first cut of the grid into blocks of at most maxCells cells per side (and, with --split, never
+/// across an output chunk), shared by the in-core binning below and the streaming front-end
+/// (stream.hpp), which must agree on it block for block.
+struct BlockLayout
+{
+    std::int64_t n[3], counts[3];
+    std::vector<float> edges[3];             // block b of axis a spans cells [edges[a][b], edges[a][b + 1]]
+    std::vector<std::uint32_t> chunkOf[3];   // chunk coordinate of block b
+
+    BlockLayout(const Grid &g, std::int64_t maxCells, std::int64_t chunkCells)
+    {
+        for (int a = 0; a < 3; a++)
+        {
+            n[a] = std::max<std::int64_t>(g.numCells(a), 1);
+            const std::int64_t chunkLen = chunkCells > 0 ? chunkCells : n[a];
+            for (std::int64_t c0 = 0, chunk = 0; c0 < n[a]; c0 += chunkLen, chunk++)
+            {
+                // a chunk is cut into equal blocks of at most maxCells cells
+                const std::int64_t len = std::min(chunkLen, n[a] - c0), parts = (len + maxCells - 1) / maxCells;
+                for (std::int64_t b = 0; b < parts; b++)
+                {
+                    edges[a].push_back((float) (c0 + b * len / parts));
+                    chunkOf[a].push_back((std::uint32_t) chunk);
+                }
+            }
+            edges[a].push_back((float) n[a]);
+            counts[a] = (std::int64_t) chunkOf[a].size();
+        }
+    }
+
+    std::size_t numBlocks() const { return (std::size_t) (counts[0] * counts[1] * counts[2]); }
+    std::size_t index(std::int64_t bx, std::int64_t by, std::int64_t bz) const { return (std::size_t) ((bz * counts[1] + by) * counts[0] + bx); }
+
+    /// The blocks a splat's ball reaches along axis a (closed-interval test); false if none.
+    bool range(const mlsb_splat &s, int a, std::int64_t &first, std::int64_t &last) const
+    {
+        const float l = s.position[a] - s.radius, h = s.position[a] + s.radius;
+        const std::vector<float> &e = edges[a];
+        // blocks b with h >= e[b] and l <= e[b + 1]
+        first = std::lower_bound(e.begin() + 1, e.end(), l) - (e.begin() + 1);      // first b with e[b + 1] >= l
+        last = (std::upper_bound(e.begin(), e.end() - 1, h) - e.begin()) - 1;      // last b with e[b] <= h
+        return first <= last && first < counts[a] && last >= 0;
+    }
+};
+
 /// splats: grid coordinates (after worldToGrid).  Bins come out in z-major block order.
 /// chunkCells > 0 (--split): the grid is first cut into output chunks of that many cells per side,
 /// counted from the grid's low corner, and no bin crosses a chunk boundary (Bucket::bucket's
@@ -135,38 +180,13 @@ inline void split(const std::vector<mlsb_splat> &splats, const std::int64_t lo[3
 inline std::vector<Bin> makeBins(const std::vector<mlsb_splat> &splats, const Grid &g, std::int64_t maxCells, std::size_t maxSplats,
                                  std::int64_t chunkCells = 0)
 {
-    std::int64_t n[3], counts[3];
-    std::vector<float> edges[3];             // block b of axis a spans cells [edges[a][b], edges[a][b + 1]]
-    std::vector<std::uint32_t> chunkOf[3];   // chunk coordinate of block b
-    for (int a = 0; a < 3; a++)
-    {
-        n[a] = std::max<std::int64_t>(g.numCells(a), 1);
-        const std::int64_t chunkLen = chunkCells > 0 ? chunkCells : n[a];
-        for (std::int64_t c0 = 0, chunk = 0; c0 < n[a]; c0 += chunkLen, chunk++)
-        {
-            // a chunk is cut into equal blocks of at most maxCells cells
-            const std::int64_t len = std::min(chunkLen, n[a] - c0), parts = (len + maxCells - 1) / maxCells;
-            for (std::int64_t b = 0; b < parts; b++)
-            {
-                edges[a].push_back((float) (c0 + b * len / parts));
-                chunkOf[a].push_back((std::uint32_t) chunk);
-            }
-        }
-        edges[a].push_back((float) n[a]);
-        counts[a] = (std::int64_t) chunkOf[a].size();
-    }
-    const std::size_t numBlocks = (std::size_t) (counts[0] * counts[1] * counts[2]);
+    const BlockLayout layout(g, maxCells, chunkCells);
+    const std::int64_t *counts = layout.counts;
+    const std::vector<float> *edges = layout.edges;
+    const std::vector<std::uint32_t> *chunkOf = layout.chunkOf;
+    const std::size_t numBlocks = layout.numBlocks();
     const std::int64_t numSplats = (std::int64_t) splats.size();
-
-    // The blocks a splat's ball reaches, per axis (the same closed-interval test as detail::split).
-    auto range = [&](const mlsb_splat &s, int a, std::int64_t &first, std::int64_t &last) {
-        const float l = s.position[a] - s.radius, h = s.position[a] + s.radius;
-        const std::vector<float> &e = edges[a];
-        // blocks b with h >= e[b] and l <= e[b + 1]
-        first = std::lower_bound(e.begin() + 1, e.end(), l) - (e.begin() + 1);      // first b with e[b + 1] >= l
-        last = (std::upper_bound(e.begin(), e.end() - 1, h) - e.begin()) - 1;      // last b with e[b] <= h
-        return first <= last && first < counts[a] && last >= 0;
-    };
+    auto range = [&](const mlsb_splat &s, int a, std::int64_t &first, std::int64_t &last) { return layout.range(s, a, first, last); };
 
     // Two passes over the splats with the same static schedule: count per (thread, block), then
     // fill exact-size lists.  Each thread owns a contiguous range of splats and the threads'

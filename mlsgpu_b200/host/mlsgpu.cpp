@@ -33,6 +33,7 @@
 #include "mesher.hpp"
 #include "mlsb200.hpp"
 #include "ply_io.hpp"
+#include "stream.hpp"
 
 namespace
 {
@@ -51,6 +52,10 @@ struct Options
     int leafCells = 63;
     int deviceThreads = 4;           // the reference defaults to 1 and recommends more (src/marching.h:573-576)
     std::uint64_t memBucketSplats = 64ull << 20;   // bytes
+    // Inputs larger than this are streamed from disk batch by batch (stream.hpp).  The reference's default is
+    // 256M (2013 hosts); with it every input above 8 M splats takes the multi-pass path, so the default here
+    // is sized for the hosts B200s sit in.  Pass the reference's value to get its behaviour.
+    std::uint64_t memLoadSplats = 16ull << 30;
     std::uint64_t memMesh = 512ull << 20;
     std::vector<int> devices;        // CUDA ordinals; empty = every device found (the reference's default, src/clh.cpp:180-240)
     bool quiet = false, statistics = false, statisticsCL = false, split = false;
@@ -79,6 +84,9 @@ void usage()
         "  --leaf-cells N              leaf size for initial histogram (63)\n"
         "  --device-threads N          worker threads per device (4)\n"
         "  --mem-bucket-splats SIZE    device memory for splats of one bin, K/M/G suffix (64M)\n"
+        "  --mem-load-splats SIZE      host memory for splats loaded at once; larger inputs are streamed from\n"
+        "                              disk in several passes (16G; the reference's default is 256M)\n"
+        "                              NOTE: the output mesh is always held in host memory until it is written\n"
         "  --mem-mesh SIZE             device memory for raw mesh data (512M)\n"
         "  --device N[,N...]|all       CUDA devices to use, one worker group each (replaces --cl-device; default: all)\n"
         "  --cl-gpu                    use every GPU (the default)\n"
@@ -111,7 +119,7 @@ Options parse(int argc, char **argv)
     static const std::map<std::string, bool> ignored = {
         {"--response-file", true}, {"--tmp-dir", true},
         {"--timeplot", true}, {"--max-split", true}, {"--reader", true}, {"--writer", true}, {"--omp-threads", true},
-        {"--decache", false}, {"--mem-load-splats", true},
+        {"--decache", false},
         {"--mem-host-splats", true}, {"--mem-reorder", true}, {"--mem-gather", true},
         {"--cl-device", true}, {"--cl-gpu", false}, {"--cl-cpu", false}, {"--debug", false}};
     for (int i = 1; i < argc; i++)
@@ -145,6 +153,7 @@ Options parse(int argc, char **argv)
         else if (a == "--device-threads") o.deviceThreads = std::stoi(value());
         else if (a == "--mem-bucket-splats") o.memBucketSplats = parseCapacity(value());
         else if (a == "--mem-mesh") o.memMesh = parseCapacity(value());
+        else if (a == "--mem-load-splats") o.memLoadSplats = parseCapacity(value());
         else if (a == "--device" || a == "--devices")
         {
             // --cl-device name[:n] selects among OpenCL devices (src/clh.cpp:170-178); CUDA has ordinals
@@ -183,6 +192,8 @@ Options parse(int argc, char **argv)
     if (o.fitShape != "sphere" && o.fitShape != "plane") throw std::invalid_argument("Value of --fit-shape must be sphere or plane.");
     if (!(o.fitGrid > 0.0)) throw std::invalid_argument("Value of --fit-grid must be positive.");
     if (o.memBucketSplats < sizeof(mlsb_splat)) throw std::invalid_argument("Value of --mem-bucket-splats is too small.");
+    if (o.memLoadSplats < o.memBucketSplats)   // src/mlsgpu_core.cpp:436-440
+        throw std::invalid_argument("Value of --mem-load-splats must be at least that of --mem-bucket-splats.");
     return o;
 }
 
@@ -257,7 +268,6 @@ struct SinkState
 {
     explicit SinkState(bool split) : mesher(split) {}
     mlsb::Mesher mesher;
-    const std::vector<mlsb::Bin> *bins = nullptr;   // the sink's tag is the bin's index: its chunk is looked up here
     std::mutex mutex;
     double prepareSeconds = 0.0;   // per-block work, concurrently on the worker threads (summed)
     double commitSeconds = 0.0;    // seam bookkeeping in the global mesh, serialised
@@ -268,8 +278,9 @@ struct SinkState
 void meshSink(std::uint64_t tag, const mlsb_mesh_sizes *sizes, const void *blob, void *user)
 {
     SinkState *st = static_cast<SinkState *>(user);
-    const mlsb::Bin &bin = (*st->bins)[(std::size_t) tag];
-    const mlsb::Mesher::chunk_type chunk = {{bin.chunk[0], bin.chunk[1], bin.chunk[2]}};
+    // the tag carries the bin's output chunk (ChunkId::coords), 21 bits per axis
+    const mlsb::Mesher::chunk_type chunk = {{(std::uint32_t) (tag & 0x1FFFFF), (std::uint32_t) ((tag >> 21) & 0x1FFFFF),
+                                             (std::uint32_t) ((tag >> 42) & 0x1FFFFF)}};
     const double t0 = now();
     std::unique_ptr<mlsb::Mesher::Block> prepared = mlsb::Mesher::prepare(*sizes, blob);
     const double t1 = now();
@@ -423,10 +434,20 @@ int main(int argc, char **argv)
             }
         } guard(creating);
 
-        // ---- read and condition (FastPly::Reader) ----
+        // ---- grid and bins, in core or streamed (doComputeBlobs / doBucket) ----
+        const std::int64_t bucketSize = std::min<std::int64_t>(o.leafCells, maxCells);             // :600-603
+        // --split: chunks of about --split-size bytes, assuming a surface cuts a chunk of x cells per
+        // side in ~20 x^2 vertices of 38 bytes each (src/mlsgpu_core.cpp:635-652)
+        std::int64_t chunkCells = 0;
+        if (o.split) chunkCells = std::max<std::int64_t>(1, (std::int64_t) std::ceil(std::sqrt(o.splitSize / 760.0)));
+        const bool streaming = (std::uint64_t) firsts.back() * sizeof(mlsb_splat) > o.memLoadSplats;
+        mlsb::SplatStream stream(readers);
+        mlsb::Grid grid;
+        std::size_t numSplats = 0;
+        if (!streaming)
         {
-            // sizes first, then one allocation and a parallel decode per file; non-finite splats are
-            // dropped afterwards (src/splat_set.cpp:221-240), keeping the order
+            // one allocation and a parallel decode per file; non-finite splats are dropped afterwards
+            // (src/splat_set.cpp:221-240), keeping the order
             splats.resize(firsts.back());
             for (std::size_t f = 0; f < readers.size(); f++)
                 if (!readers[f]->readRaw(0, readers[f]->size(), splats.data() + firsts[f]))
@@ -447,24 +468,28 @@ int main(int argc, char **argv)
                     kept++;
                 }
             splats.resize(kept);
+            numSplats = kept;
         }
-        const std::size_t numSplats = splats.size();
+        else
+            numSplats = stream.scan();   // pass 1: bounds and counts, one chunk per thread at a time
         if (numSplats == 0) throw std::runtime_error("At least one input point is required.");
         const double tRead = now();
-
-        // ---- grid, bins (doComputeBlobs / doBucket) ----
-        const std::int64_t bucketSize = std::min<std::int64_t>(o.leafCells, maxCells);             // :600-603
-        const mlsb::Grid grid = mlsb::boundingGrid(splats, (float) o.fitGrid, bucketSize);
+        grid = streaming ? stream.grid((float) o.fitGrid, bucketSize) : mlsb::boundingGrid(splats, (float) o.fitGrid, bucketSize);
         for (int a = 0; a < 3; a++)
             if (grid.numCells(a) + 1 > (1 << 20) - 1)   // src/mlsgpu_core.cpp:623-629
                 throw std::runtime_error("The bounding box is too big. Perhaps you have used the wrong units for --fit-grid.");
-        mlsb::worldToGrid(splats, grid);
-        // --split: chunks of about --split-size bytes, assuming a surface cuts a chunk of x cells per
-        // side in ~20 x^2 vertices of 38 bytes each (src/mlsgpu_core.cpp:635-652)
-        std::int64_t chunkCells = 0;
-        if (o.split) chunkCells = std::max<std::int64_t>(1, (std::int64_t) std::ceil(std::sqrt(o.splitSize / 760.0)));
-        bins = mlsb::makeBins(splats, grid, maxCells, maxBucketSplats, chunkCells);
-        state.bins = &bins;
+        const mlsb::BlockLayout layout(grid, maxCells, chunkCells);
+        std::vector<std::pair<std::size_t, std::size_t>> batches;   // streaming: runs of blocks loaded together
+        if (!streaming)
+        {
+            mlsb::worldToGrid(splats, grid);
+            bins = mlsb::makeBins(splats, grid, maxCells, maxBucketSplats, chunkCells);
+        }
+        else
+        {
+            const std::vector<std::uint64_t> counts = stream.countBlocks(grid, layout);   // pass 2
+            batches = mlsb::SplatStream::batches(counts, o.memLoadSplats / sizeof(mlsb_splat));
+        }
         const double tBucket = now();
 
         // ---- device pipeline ----
@@ -497,54 +522,79 @@ int main(int argc, char **argv)
             }
         }
         const double tCreateWait = now() - tCreate0;   // the part of the creation that was not hidden
-        double tGather = 0.0;
+        double tGather = 0.0, tLoad = 0.0;
         // Gather buffers are recycled (BucketLoader's circular buffer): a slot is reused once the
         // group it went to has released the bin that used it, which keeps the gather out of the
         // page-fault path.
-        std::size_t largest = 1;
-        for (const mlsb::Bin &bin : bins) largest = std::max(largest, bin.ids.size());
         const std::size_t queueDepth = 2 * (std::size_t) o.deviceThreads;   // mlsb_group_create's default
         ring.resize(numGroups * (queueDepth + (std::size_t) o.deviceThreads) + 1);
-        struct SlotUse { std::size_t group = 0; std::uint64_t sequence = 0; bool used = false; };
+        struct SlotUse { std::size_t group = 0; std::uint64_t sequence = 0; std::size_t capacity = 0; bool used = false; };
         std::vector<SlotUse> slotUse(ring.size());
         std::vector<std::uint64_t> submittedBins(numGroups, 0), submittedSplats(numGroups, 0);
-        for (std::size_t b = 0; b < bins.size(); b++)
-        {
-            // BucketLoader::operator(): gather the bin's splats (src/bucket_loader.cpp:104-126)
-            const double tg = now();
-            const std::vector<std::uint32_t> &ids = bins[b].ids;
-            const std::size_t slotIndex = b % ring.size();
-            std::unique_ptr<mlsb_splat[]> &slot = ring[slotIndex];
-            if (!slot) slot.reset(new mlsb_splat[largest]);
-            if (slotUse[slotIndex].used)
-                for (std::uint64_t released = 0;;)
-                {
-                    mlsb::check(mlsb_group_released(groups[slotUse[slotIndex].group], &released));
-                    if (released > slotUse[slotIndex].sequence) break;
-                    std::this_thread::yield();
-                }
-            mlsb_splat *dst = slot.get();
-            // a few threads are enough and leave the cores to the device workers
-#pragma omp parallel for schedule(static) num_threads(4)
-            for (std::int64_t i = 0; i < (std::int64_t) ids.size(); i++) dst[i] = splats[ids[(std::size_t) i]];
-            tGather += now() - tg;
-            // CopyGroupBase::Worker::flush (src/workers.cpp:329-343) hands a bin to the device with the most
-            // unallocated splat capacity: here, the group with the fewest splats submitted and not yet processed
-            std::size_t target = 0;
-            std::uint64_t least = ~0ull;
-            for (std::size_t g = 0; g < numGroups; g++)
+        std::size_t numBins = 0, chunksRead = 0;
+        // BucketLoader::operator() for a list of bins over `source` (src/bucket_loader.cpp:104-126)
+        auto dispatch = [&](const std::vector<mlsb_splat> &source, const std::vector<mlsb::Bin> &list, std::size_t blockBegin, std::size_t blockEnd) {
+            for (const mlsb::Bin &bin : list)
             {
-                std::uint64_t doneSplats = 0;
-                mlsb::check(mlsb_group_counters(groups[g], nullptr, &doneSplats, nullptr));
-                const std::uint64_t pending = submittedSplats[g] - doneSplats;
-                if (pending < least) { least = pending; target = g; }
+                if (streaming)
+                {
+                    const std::size_t block = mlsb::blockOfBin(layout, bin);
+                    if (block < blockBegin || block >= blockEnd) continue;   // incomplete here: another batch owns it
+                }
+                const double tg = now();
+                const std::vector<std::uint32_t> &ids = bin.ids;
+                const std::size_t slotIndex = numBins % ring.size();
+                SlotUse &use = slotUse[slotIndex];
+                if (use.used)
+                    for (std::uint64_t released = 0;;)
+                    {
+                        mlsb::check(mlsb_group_released(groups[use.group], &released));
+                        if (released > use.sequence) break;
+                        std::this_thread::yield();
+                    }
+                if (use.capacity < ids.size())
+                {
+                    use.capacity = std::max(ids.size(), use.capacity + use.capacity / 2);
+                    ring[slotIndex].reset(new mlsb_splat[use.capacity]);
+                }
+                mlsb_splat *dst = ring[slotIndex].get();
+                // a few threads are enough and leave the cores to the device workers
+#pragma omp parallel for schedule(static) num_threads(4)
+                for (std::int64_t i = 0; i < (std::int64_t) ids.size(); i++) dst[i] = source[ids[(std::size_t) i]];
+                tGather += now() - tg;
+                // CopyGroupBase::Worker::flush (src/workers.cpp:329-343) hands a bin to the device with the most
+                // unallocated splat capacity: here, the group with the fewest splats submitted and not yet processed
+                std::size_t target = 0;
+                std::uint64_t least = ~0ull;
+                for (std::size_t g = 0; g < numGroups; g++)
+                {
+                    std::uint64_t doneSplats = 0;
+                    mlsb::check(mlsb_group_counters(groups[g], nullptr, &doneSplats, nullptr));
+                    const std::uint64_t pending = submittedSplats[g] - doneSplats;
+                    if (pending < least) { least = pending; target = g; }
+                }
+                use.group = target;
+                use.sequence = submittedBins[target]++;
+                use.used = true;
+                submittedSplats[target] += ids.size();
+                const std::uint64_t tag = (std::uint64_t) bin.chunk[0] | ((std::uint64_t) bin.chunk[1] << 21) | ((std::uint64_t) bin.chunk[2] << 42);
+                mlsb::check(mlsb_group_submit(groups[target], dst, (std::uint32_t) ids.size(), bin.size, bin.offset, tag));
+                numBins++;
             }
-            slotUse[slotIndex].group = target;
-            slotUse[slotIndex].sequence = submittedBins[target]++;
-            slotUse[slotIndex].used = true;
-            submittedSplats[target] += ids.size();
-            mlsb::check(mlsb_group_submit(groups[target], dst, (std::uint32_t) ids.size(), bins[b].size, bins[b].offset, b));
-        }
+        };
+        if (!streaming)
+            dispatch(splats, bins, 0, layout.numBlocks());
+        else
+            for (const std::pair<std::size_t, std::size_t> &batch : batches)
+            {
+                const double tl = now();
+                std::size_t read = 0;
+                stream.load(grid, layout, batch.first, batch.second, splats, &read);   // BucketCollector + BucketLoader
+                chunksRead += read;
+                bins = mlsb::makeBins(splats, grid, maxCells, maxBucketSplats, chunkCells);
+                tLoad += now() - tl;
+                dispatch(splats, bins, batch.first, batch.second);   // gathered into the ring: splats is free again
+            }
         {
             std::string failure;
             for (mlsb_group *group : groups)
@@ -582,7 +632,7 @@ int main(int argc, char **argv)
             std::ostringstream out;
             out << "mlsgpu version: " << mlsb_version() << "\n"
                 << "files.splats: " << numSplats << "\n"
-                << "bins: " << bins.size() << "\n"
+                << "bins: " << numBins << "\n"
                 << "devices: " << numGroups << "\n"
                 << "components.total: " << mesh.totalComponents << "\ncomponents.kept: " << mesh.keptComponents << "\n"
                 << "output.vertices: " << mesh.numVertices << "\noutput.triangles: " << mesh.numTriangles << "\n"
@@ -595,6 +645,12 @@ int main(int argc, char **argv)
                           "mesher.prepare.time: %.3f\nmesher.commit.time: %.3f\n",
                           createSeconds, tCreateWait, tGather, state.prepareSeconds, state.commitSeconds);
             out << buf;
+            if (streaming)
+            {
+                std::snprintf(buf, sizeof(buf), "stream.batches: %zu\nstream.chunks: %zu\nstream.chunks.read: %zu\nstream.load.time: %.3f\n",
+                              batches.size(), stream.numChunks(), chunksRead, tLoad);
+                out << buf;
+            }
             for (std::size_t g = 0; g < numGroups; g++)
             {
                 std::snprintf(buf, sizeof(buf), "device.%d.bins: %llu\ndevice.%d.splats: %llu\n", devices[g], (unsigned long long) submittedBins[g],

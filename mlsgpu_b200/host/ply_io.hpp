@@ -46,7 +46,11 @@ public:
             throw;
         }
     }
-    ~PlyReader() { if (file) std::fclose(file); }
+    ~PlyReader()
+    {
+        if (file) std::fclose(file);
+        if (preadFd >= 0) ::close(preadFd);
+    }
     PlyReader(const PlyReader &) = delete;
     PlyReader &operator=(const PlyReader &) = delete;
 
@@ -92,6 +96,30 @@ public:
         for (std::int64_t i = 0; i < (std::int64_t) count; i++) out[i] = decode(base + (std::size_t) i * vertexSize);
         ::munmap(map, bytes + (begin - aligned));
         return true;
+    }
+
+    /// Decodes vertices [first, first + count) into out[0 .. count) on the calling thread (pread into
+    /// `scratch`): safe to call from several threads at once, which is how the streaming front-end
+    /// walks a file chunk by chunk.
+    void readRange(std::size_t first, std::size_t count, mlsb_splat *out, std::vector<char> &scratch) const
+    {
+        if (count == 0) return;
+        scratch.resize(count * vertexSize);
+        if (preadFd < 0)
+        {
+            const int fd = ::open(path.c_str(), O_RDONLY);
+            if (fd < 0) throw std::runtime_error("cannot open " + path);
+            int expected = -1;
+            if (!__atomic_compare_exchange_n(&preadFd, &expected, fd, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) ::close(fd);
+        }
+        std::size_t done = 0;
+        while (done < scratch.size())
+        {
+            const ssize_t got = ::pread(preadFd, scratch.data() + done, scratch.size() - done, (off_t) (headerSize + first * vertexSize + done));
+            if (got <= 0) throw std::runtime_error("short read in " + path);
+            done += (std::size_t) got;
+        }
+        for (std::size_t i = 0; i < count; i++) out[i] = decode(scratch.data() + i * vertexSize);
     }
 
     static bool isFinite(const mlsb_splat &s)
@@ -195,6 +223,7 @@ private:
 
     std::string path;
     std::FILE *file = nullptr;
+    mutable int preadFd = -1;
     float smooth, maxRadius;
     std::size_t numVertices = 0, vertexSize = 0, headerSize = 0;
     std::size_t offsets[7] = {};

@@ -479,3 +479,48 @@ def test_mesher_reference_empty_fixture(tmp_path, threads):
     assert len(verts) == 0 and len(tris) == 0
     verts, tris = run_mesher(tmp_path, [blk([], [], [], [])], 0.02, threads)
     assert len(verts) == 0 and len(tris) == 0
+
+
+# ---- out-of-core front-end (stream.hpp): BucketCollector / BucketLoader over chunked, re-read input ----
+
+def synth(tmp_path, config, points):
+    exe = build("gen_synth")
+    r = subprocess.run([exe, "--config", config, "--points", str(points), "--scans", "4", "--out", str(tmp_path / "in")],
+                       check=True, capture_output=True, text=True)
+    fit_grid = float(r.stdout.split("fit-grid ")[1])
+    return sorted(str(p) for p in tmp_path.glob("in_*.ply")), fit_grid
+
+
+@pytest.mark.parametrize("config,points,max_cells,max_bin,max_load,chunk_cells", [
+    ("C3", 600_000, 255, 1 << 21, 60_000, 0),       # many batches of whole blocks
+    ("C3", 600_000, 63, 5_000, 20_000, 150),        # blocks halved by the splat limit, --split chunks
+    ("C5", 400_000, 127, 1 << 21, 1 << 30, 0),      # one batch: everything at once
+])
+def test_streamed_bins_equal_in_core_bins(tmp_path, config, points, max_cells, max_bin, max_load, chunk_cells):
+    """The streaming front-end must hand over, for every bin, the same box, chunk and splats in the same
+    order as binning the whole input in memory — while never loading more than the limit at once."""
+    files, fit_grid = synth(tmp_path, config, points)
+    r = subprocess.run([build("stream_test"), repr(fit_grid), str(max_cells), str(max_bin), str(max_load), str(chunk_cells)] + files,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.startswith("ok:"), r.stdout
+    batches = int(r.stdout.split(" bins, ")[1].split(" batches")[0])
+    assert (batches > 3) == (max_load < points)
+
+
+@pytest.mark.gpu
+def test_cli_streamed_run_equals_in_core_run(tmp_path):
+    """mlsgpu with the reference's kind of --mem-load-splats (a fraction of the input): several passes
+    over the files, bounded host memory for splats, and the same mesh as the in-core run."""
+    files, fit_grid = synth(tmp_path, "C3", 1_500_000)
+    exe = build("mlsgpu")
+    common = [exe, "--fit-grid", repr(fit_grid), "--device", "0", "--device-threads", "3", "--statistics"]
+    a = subprocess.run(common + ["-o", str(tmp_path / "core.ply")] + files, capture_output=True, text=True)
+    b = subprocess.run(common + ["-o", str(tmp_path / "stream.ply"), "--mem-load-splats", "8M", "--mem-bucket-splats", "4M"] + files,
+                       capture_output=True, text=True)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    assert "stream.batches" not in a.stdout
+    sb = dict(l.split(": ", 1) for l in b.stdout.splitlines() if ": " in l)
+    assert int(sb["stream.batches"]) >= 4 and int(sb["files.splats"]) == 1_500_000
+    d = subprocess.run([build("meshdiff"), str(tmp_path / "core.ply"), str(tmp_path / "stream.ply")], capture_output=True, text=True)
+    assert d.returncode == 0, d.stdout + d.stderr

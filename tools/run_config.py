@@ -30,7 +30,7 @@ def stats_dict(text):
 
 
 def run(config, points, devices="all", threads=4, scans=8, boundary_limit=1.0, prune=0.02, shape="sphere", keep=None, extra=(),
-        tmp_root=None):
+        tmp_root=None, check=True):
     with tempfile.TemporaryDirectory(dir=tmp_root) as tmp:
         t0 = time.time()
         g = subprocess.run([os.path.join(HOST, "gen_synth"), "--config", config, "--points", str(points), "--scans", str(scans),
@@ -56,10 +56,11 @@ def run(config, points, devices="all", threads=4, scans=8, boundary_limit=1.0, p
         res["statistics"] = {k: st[k] for k in st if k.split(".")[0] in ("files", "bins", "devices", "components", "output", "read", "bucket",
                                                                         "device", "mesher", "run") or k.startswith("splats/s")}
         res["Msplats_per_s_end_to_end"] = n / float(st["run.time"]) / 1e6
-        t0 = time.time()
-        c = subprocess.run([os.path.join(HOST, "plymanifold"), out], capture_output=True, text=True)
-        res["plymanifold"] = c.stdout.strip().replace("\n", "; ")
-        res["plymanifold_s"] = round(time.time() - t0, 2)
+        if check:
+            t0 = time.time()
+            c = subprocess.run([os.path.join(HOST, "plymanifold"), out], capture_output=True, text=True)
+            res["plymanifold"] = c.stdout.strip().replace("\n", "; ")
+            res["plymanifold_s"] = round(time.time() - t0, 2)
         res["output_bytes"] = os.path.getsize(out)
         if keep:
             os.replace(out, keep)
@@ -78,9 +79,10 @@ def main():
     ap.add_argument("--shape", default="sphere")
     ap.add_argument("--keep", default=None, help="move the output mesh here")
     ap.add_argument("--tmp", default=None)
+    ap.add_argument("--no-check", action="store_true", help="skip plymanifold (minutes for a 100 M-splat mesh)")
     ap.add_argument("extra", nargs="*")
     a = ap.parse_args()
-    res = run(a.config, a.points, a.devices, a.threads, a.scans, a.boundary_limit, a.prune, a.shape, a.keep, a.extra, a.tmp)
+    res = run(a.config, a.points, a.devices, a.threads, a.scans, a.boundary_limit, a.prune, a.shape, a.keep, a.extra, a.tmp, not a.no_check)
     print(json.dumps(res), flush=True)
     return 0 if res["exit"] == 0 else 1
 

@@ -271,25 +271,32 @@ class ShardedTorus:
         return self._owners
 
     def block_chunks(self, bx, by):
-        """Sectors that can hold a splat reaching block column (bx, by)."""
+        """Sectors that can hold a splat reaching block column (bx, by): the column's footprint, grown by
+        the largest radius, is cut into 8 x 8 pieces; a piece counts if it meets the annulus the torus
+        projects to, and then contributes the angles its corners span (exact for a rectangle that misses
+        the axis; a piece around the axis lies inside the annulus' hole and is skipped)."""
         m = self.rmax_cells + 1.0
-        x0, x1 = self.edges[0][bx] + self.lo[0] - m, self.edges[0][bx + 1] + self.lo[0] + m
-        y0, y1 = self.edges[1][by] + self.lo[1] - m, self.edges[1][by + 1] + self.lo[1] + m
-        # no splat closer to the axis than R - r - bump, nor further than R + r + bump (grid units)
-        near = np.hypot(max(x0, -x1, 0.0), max(y0, -y1, 0.0))
-        far = np.hypot(max(abs(x0), abs(x1)), max(abs(y0), abs(y1)))
-        if far < (self.R - self.r - self.bump) / float(self.spacing) or near > (self.R + self.r + self.bump) / float(self.spacing):
-            return set()
-        if x0 <= 0.0 <= x1 and y0 <= 0.0 <= y1:
-            return set(range(self.chunks))            # the column holds the axis: every angle
-        # the angular extent of a rectangle that misses the origin is spanned by its corners, all within
-        # less than pi of the centre direction
-        pts = [(x0, y0), (x0, y1), (x1, y0), (x1, y1)]
-        mid = np.arctan2(0.5 * (y0 + y1), 0.5 * (x0 + x1))
-        d = [((np.arctan2(y, x) - mid + np.pi) % (2 * np.pi)) - np.pi for x, y in pts]
+        X0, X1 = self.edges[0][bx] + self.lo[0] - m, self.edges[0][bx + 1] + self.lo[0] + m
+        Y0, Y1 = self.edges[1][by] + self.lo[1] - m, self.edges[1][by + 1] + self.lo[1] + m
+        rho_min = (self.R - self.r - self.bump) / float(self.spacing)
+        rho_max = (self.R + self.r + self.bump) / float(self.spacing)
         w = 2 * np.pi / self.chunks
-        c0, c1 = int(np.floor((mid + min(d)) / w)), int(np.floor((mid + max(d)) / w))
-        return {c % self.chunks for c in range(c0, c1 + 1)}
+        need = set()
+        for i in range(8):
+            for j in range(8):
+                x0, x1 = X0 + (X1 - X0) * i / 8, X0 + (X1 - X0) * (i + 1) / 8
+                y0, y1 = Y0 + (Y1 - Y0) * j / 8, Y0 + (Y1 - Y0) * (j + 1) / 8
+                near = np.hypot(max(x0, -x1, 0.0), max(y0, -y1, 0.0))
+                far = np.hypot(max(abs(x0), abs(x1)), max(abs(y0), abs(y1)))
+                if far < rho_min or near > rho_max:
+                    continue
+                if x0 <= 0.0 <= x1 and y0 <= 0.0 <= y1:
+                    return set(range(self.chunks))        # cannot happen for a torus with a hole wider than a piece
+                mid = np.arctan2(0.5 * (y0 + y1), 0.5 * (x0 + x1))
+                d = [((np.arctan2(y, x) - mid + np.pi) % (2 * np.pi)) - np.pi for x, y in ((x0, y0), (x0, y1), (x1, y0), (x1, y1))]
+                c0, c1 = int(np.floor((mid + min(d)) / w)), int(np.floor((mid + max(d)) / w))
+                need |= {c % self.chunks for c in range(c0, c1 + 1)}
+        return need
 
     def rank_share(self, rank):
         """(grid splats, bins, lo, spacing) of `rank`: only its blocks' bins, complete."""

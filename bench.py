@@ -318,7 +318,7 @@ def reference_opencl(wl, runner, nbins=3):
     ref_s, corners, max_err = 0.0, 0, 0.0
     for i in order:
         b = wl["bins"][i]
-        s = np.ascontiguousarray(wl["splats"][b["first"]:b["first"] + b["n"]])
+        s = wl["splats"][b["first"]:b["first"] + b["n"]].copy()     # the build overwrites the radii: never on the workload itself
         tree = orc.octree_build(s, 0, len(s), b["offset"], 3, 6)
         size = [int(v) for v in b["size"]]
         pitch, zs, depth = (-(-v // 8) * 8 for v in size)
@@ -423,7 +423,9 @@ def main():
         os.environ.setdefault("MLSB_SYNC", "block")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL_DEBUG is left to the environment; NCCL logs to stderr/its own file, stdout carries the one JSON line
+        # NCCL_DEBUG is left to the environment (the driver reads the communicator set-up from it); NCCL would
+        # print to stdout, which carries the one JSON line, so its log goes to stderr unless a file is named
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import mlsgpu_b200 as m

@@ -281,6 +281,19 @@ MLSB_API int mlsb_group_worker(mlsb_group *g, uint32_t index, mlsb_worker **work
 /* Totals since creation: bins and splats processed, bytes of mesh handed to the sink. */
 MLSB_API int mlsb_group_counters(mlsb_group *g, uint64_t *bins, uint64_t *splats, uint64_t *meshBytes);
 
+/* ---- timeplot (--timeplot, src/timeplot.cpp:134-186) -------------------------------------- */
+
+/* Seconds on the library's monotonic clock (the Timer::currentTime() the events below are stamped with). */
+MLSB_API double mlsb_timeplot_now(void);
+/* enabled != 0: every worker thread of the group records what it does per bin as the reference's
+ * Timeplot::Action does — worker "device.<ordinal>.<index>", actions "get" (waiting for a bin),
+ * "copy" (staging + H2D enqueue, CopyGroup's "write") and "compute" (the per-bin path including the
+ * mesh sink).  Set before the first submit. */
+MLSB_API int mlsb_group_set_timeplot(mlsb_group *g, int enabled);
+/* Calls visit once per recorded event, in no particular order (call after mlsb_group_wait). */
+typedef void (*mlsb_timeplot_visitor)(void *user, const char *worker, const char *action, double t0, double t1);
+MLSB_API int mlsb_group_timeplot(mlsb_group *g, mlsb_timeplot_visitor visit, void *user);
+
 /* ---- statistics (--statistics-cl, src/statistics_cl.cpp) -------------------------------- */
 
 /* CUDA-event timing under the reference's statistic names (kernel.octree.*.time,

@@ -94,6 +94,9 @@ API = {
     "mlsb_group_set_concurrent_sink": (C.c_int, [_P, C.c_int]),
     "mlsb_group_released": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "mlsb_group_worker": (C.c_int, [_P, C.c_uint32, C.POINTER(_P)]),
+    "mlsb_timeplot_now": (C.c_double, []),
+    "mlsb_group_set_timeplot": (C.c_int, [_P, C.c_int]),
+    "mlsb_group_timeplot": (C.c_int, [_P, C.CFUNCTYPE(None, _P, C.c_char_p, C.c_char_p, C.c_double, C.c_double), _P]),
     "mlsb_group_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "mlsb_worker_set_profiling": (C.c_int, [_P, C.c_int]),
     "mlsb_worker_get_statistic": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -535,6 +538,17 @@ class WorkerGroup:
 
     def set_concurrent_sink(self, enabled=True):
         _check(lib().mlsb_group_set_concurrent_sink(self.h, int(enabled)))
+
+    def set_timeplot(self, enabled=True):
+        _check(lib().mlsb_group_set_timeplot(self.h, int(enabled)))
+
+    def timeplot(self):
+        """[(worker, action, t0, t1)] recorded since set_timeplot (Timeplot::Action events)."""
+        out = []
+        cb = C.CFUNCTYPE(None, _P, C.c_char_p, C.c_char_p, C.c_double, C.c_double)(
+            lambda _u, w, a, t0, t1: out.append((w.decode(), a.decode(), t0, t1)))
+        _check(lib().mlsb_group_timeplot(self.h, cb, None))
+        return out
 
     def counters(self):
         b, s, m = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -7,6 +7,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -51,6 +52,17 @@ struct mlsb_group
     std::string message;
 
     std::atomic<uint64_t> bins{0}, splats{0}, meshBytes{0};
+
+    // --timeplot: one record per action, appended by the worker threads
+    struct Event
+    {
+        uint32_t worker;
+        const char *action;
+        double t0, t1;
+    };
+    bool timeplot = false;
+    std::mutex eventMutex;
+    std::vector<Event> events;
 };
 
 namespace
@@ -125,12 +137,26 @@ void releaseSplats(mlsb_group *g, uint64_t sequence)
     }
 }
 
+double clockNow()
+{
+    static const std::chrono::steady_clock::time_point epoch = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - epoch).count();
+}
+
+void record(mlsb_group *g, size_t index, const char *action, double t0, double t1)
+{
+    if (!g->timeplot) return;
+    std::lock_guard<std::mutex> lock(g->eventMutex);
+    g->events.push_back(mlsb_group::Event{(uint32_t) index, action, t0, t1});
+}
+
 void workerLoop(mlsb_group *g, size_t index)
 {
     mlsb_worker *w = g->workers[index];
     for (;;)
     {
         mlsb_group::Item item;
+        const double tGet = g->timeplot ? clockNow() : 0.0;
         {
             std::unique_lock<std::mutex> lock(g->mutex);
             g->canPop.wait(lock, [g] { return g->stopping || !g->queue.empty(); });
@@ -140,6 +166,8 @@ void workerLoop(mlsb_group *g, size_t index)
             g->inFlight++;
         }
         g->canPush.notify_one();
+        const double tCopy = g->timeplot ? clockNow() : 0.0;
+        record(g, index, "get", tGet, tCopy);
 
         // CopyGroupBase::Worker::operator() + flush, src/workers.cpp:354-418
         const mlsb_splat *src = item.splats;
@@ -150,6 +178,8 @@ void workerLoop(mlsb_group *g, size_t index)
         }
         if (g->stage) releaseSplats(g, item.sequence);
         int st = mlsb_splats_upload_async(w, src, 0, item.numSplats);
+        const double tCompute = g->timeplot ? clockNow() : 0.0;
+        record(g, index, "copy", tCopy, tCompute);
         // DeviceWorkerGroupBase::Worker::operator(), src/workers.cpp:232-286
         SinkContext ctx{g, item.tag};
         if (st == MLSB_OK) st = mlsb_worker_process_bin(w, 0, item.numSplats, item.size, item.offset, groupTrampoline, &ctx);
@@ -165,6 +195,7 @@ void workerLoop(mlsb_group *g, size_t index)
                 g->message = mlsb_last_error_string();
             }
         }
+        if (g->timeplot) record(g, index, "compute", tCompute, clockNow());
         if (!g->stage) releaseSplats(g, item.sequence);   // process_bin has waited for the upload
         g->bins++;
         g->splats += item.numSplats;
@@ -281,6 +312,29 @@ int mlsb_group_set_concurrent_sink(mlsb_group *g, int enabled)
 {
     MLSB_REQUIRE(g != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null group");
     g->concurrentSink = enabled != 0;
+    return MLSB_OK;
+}
+
+double mlsb_timeplot_now(void) { return clockNow(); }
+
+int mlsb_group_set_timeplot(mlsb_group *g, int enabled)
+{
+    MLSB_REQUIRE(g != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null group");
+    clockNow();   // fixes the epoch
+    g->timeplot = enabled != 0;
+    return MLSB_OK;
+}
+
+int mlsb_group_timeplot(mlsb_group *g, mlsb_timeplot_visitor visit, void *user)
+{
+    MLSB_REQUIRE(g != nullptr && visit != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
+    std::lock_guard<std::mutex> lock(g->eventMutex);
+    char name[64];
+    for (const mlsb_group::Event &e : g->events)
+    {
+        snprintf(name, sizeof(name), "device.%d.%u", g->workers[0]->cfg.device, e.worker);
+        visit(user, name, e.action, e.t0, e.t1);
+    }
     return MLSB_OK;
 }
 

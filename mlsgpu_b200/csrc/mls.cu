@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
+#include <cstring>
 
 namespace mlsb
 {
@@ -396,6 +398,249 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
     for (int j = 0; j < kSlots; j++) dst[2 * j] = out[j];
 }
 
+// The same kernel with a TWO-LEVEL cull (MLSB_MLS_CULL=block; measured, not the default — see mlsCorners).
+// Above, each of the eight warps walks the block's whole
+// command chain on its own: it fetches every splat (36 bytes), tests it against its brick and packs
+// the survivors — a quarter of the kernel's instructions and 40 % of its stall samples (ncu, C2) go
+// into doing that eight times over.  Here the BLOCK walks the chain once, 256 entries at a time:
+// thread t fetches entry t, tests it against all eight 4x4x4 bricks at once (the per-axis distances to
+// the two half-intervals, combined per brick with exactly the arithmetic of the per-warp test, so the
+// same splats reach the same bricks) and the entries that reach at least one brick are compacted, in
+// chain order, into shared memory together with their 8-bit brick mask.  A warp then only lists the
+// staged entries whose mask has its bit (a ballot per 32 entries) and pair-tests those straight out of
+// the block's staging buffer.  Staging is double-buffered: two barriers per 256 chain entries, and the
+// next batch's global loads are in flight while the current one is processed.  Per-corner
+// accumulation order is still the chain order: the field is bit-identical.
+constexpr int kStage = kThreads;   // chain entries per block batch
+template <int SHAPE, bool COUNT, bool PRE>
+__global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersBlockCullKernel(MlsParams P)
+{
+    static_assert(kSlots == 2 && kThreads == 256, "the brick layout below is the 8 x (4x4x4) one");
+    __shared__ float4 sPosT[2][kStage];      // x, y, z, hit threshold on |p|^2
+    __shared__ float4 sNormQ[2][kStage];     // normal, quality
+    __shared__ float sInvR[2][kStage];       // 1/r^2
+    __shared__ uint8_t sMask[2][kStage];     // bricks the splat's ball can reach
+    __shared__ uint16_t sIdx[kThreads / 32][kStage];   // per warp: staged entries of its brick, in order
+    __shared__ uint32_t sWarpCount[2][kThreads / 32];
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31, quad = tid >> 5;
+    const int qx = 4 * (int) (quad & 1), qy = 4 * (int) ((quad >> 1) & 1), qz = 4 * (int) (quad >> 2);
+    const int lx = qx + (int) (lane & 1);
+    const int ly = qy + (int) ((lane >> 1) & 3);
+    const int lz = qz + (int) ((lane >> 3) & 3);
+    const int wx = blockIdx.x * kMlsWgs, wy = blockIdx.y * kMlsWgs, wz = blockIdx.z * kMlsWgs + (int) P.zFirst;
+
+    const uint32_t code = (spread3(wx) | (spread3(wy) << 1) | (spread3(wz) << 2)) >> P.startShift;
+    int32_t pos = P.start[code];
+    if (P.blockActive != nullptr && tid == 0)
+        P.blockActive[((size_t) (wz >> 3) * P.activeDimY + blockIdx.y) * P.activeDimX + blockIdx.x] = pos >= 0;
+
+    float out[kSlots];
+#pragma unroll
+    for (int j = 0; j < kSlots; j++) out[j] = __uint_as_float(0x7FC00000u);
+
+    if (pos >= 0)   // uniform over the block: the barriers below are safe
+    {
+        const float cy = (float) (wy + ly + P.offset.y);
+        const float cz = (float) (wz + lz + P.offset.z);
+        float cx[kSlots];
+#pragma unroll
+        for (int j = 0; j < kSlots; j++) cx[j] = (float) (wx + lx + 2 * j + P.offset.x);
+
+        Accum acc[kSlots];
+#pragma unroll
+        for (int j = 0; j < kSlots; j++)
+        {
+            acc[j].sumW = acc[j].sumWpx = acc[j].sumWpy = acc[j].sumWpz = 0.0f;
+            acc[j].sumWnx = acc[j].sumWny = acc[j].sumWnz = acc[j].sumWpp = acc[j].sumWpn = 0.0f;
+            acc[j].hits = 0;
+        }
+        unsigned long long tests = 0;
+
+        // the block's low corner; brick (hx, hy, hz) spans [4h, 4h + 3] along each axis from there
+        const float ox = (float) (wx + P.offset.x), oy = (float) (wy + P.offset.y), oz = (float) (wz + P.offset.z);
+
+        int32_t end = P.commands[pos++];
+        float4 rPos = make_float4(0.f, 0.f, 0.f, 0.f), rNq = rPos;
+        float rThr = 0.0f;
+        bool rHave = false;
+        int nextCount = 0;
+        // the next kStage entries of the chain, entry t to thread t; a batch may span several ranges
+        auto fetch = [&]() {
+            int filled = 0;
+            int32_t id = -1;
+            while (filled < kStage && pos >= 0)
+            {
+                const int take = min(end - pos, kStage - filled);
+                const int s = (int) tid - filled;
+                if (s >= 0 && s < take) id = P.commands[pos + s];
+                filled += take;
+                pos += take;
+                if (pos >= end)
+                {
+                    pos = P.commands[end];
+                    end = pos >= 0 ? P.commands[pos++] : INT_MIN;
+                }
+            }
+            nextCount = filled;
+            rHave = id >= 0;
+            if (rHave)
+            {
+                const float4 *sp = reinterpret_cast<const float4 *>(P.splats + id);
+                rPos = __ldg(sp);
+                rNq = __ldg(sp + 1);
+                if (PRE) rThr = __ldg(P.thresholds + id);
+            }
+        };
+
+        fetch();
+        for (int buf = 0; nextCount > 0; buf ^= 1)
+        {
+            if (COUNT) tests += (unsigned long long) kSlots * nextCount;   // per warp: its 64 corners against every entry
+            // ---- block-level cull: which bricks can the splat's ball reach? ----
+            uint32_t mask = 0;
+            if (rHave)
+            {
+                float sx[2], sy[2], sz[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                {
+                    const float x0 = ox + 4.0f * h, y0 = oy + 4.0f * h, z0 = oz + 4.0f * h;
+                    const float dx = fmaxf(fmaxf(x0 - rPos.x, rPos.x - (x0 + 3.0f)), 0.0f);
+                    const float dy = fmaxf(fmaxf(y0 - rPos.y, rPos.y - (y0 + 3.0f)), 0.0f);
+                    const float dz = fmaxf(fmaxf(z0 - rPos.z, rPos.z - (z0 + 3.0f)), 0.0f);
+                    sx[h] = dx * dx;
+                    sy[h] = dy * dy;
+                    sz[h] = dz * dz;
+                }
+                // a hit needs RN(|p|^2 * invr2) < 0.99 and |p|^2 >= dist^2 to the box for every corner
+                // of the brick; the 1e-4 of slack dwarfs the few ulp of rounding on either side
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if ((sx[q & 1] + sy[(q >> 1) & 1] + sz[q >> 2]) * rPos.w < 0.9901f) mask |= 1u << q;
+            }
+            const unsigned ball = __ballot_sync(0xFFFFFFFFu, mask != 0);
+            if (lane == 0) sWarpCount[buf][quad] = __popc(ball);
+            __syncthreads();
+            uint32_t before = 0, n = 0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; w++)
+            {
+                const uint32_t c = sWarpCount[buf][w];
+                before += (uint32_t) w < quad ? c : 0u;
+                n += c;
+            }
+            if (mask)
+            {
+                const uint32_t p = before + __popc(ball & ((1u << lane) - 1));
+                sPosT[buf][p] = make_float4(rPos.x, rPos.y, rPos.z, PRE ? rThr : hitThreshold(rPos.w));
+                sNormQ[buf][p] = rNq;
+                sInvR[buf][p] = rPos.w;
+                sMask[buf][p] = (uint8_t) mask;
+            }
+            __syncthreads();
+            fetch();   // next batch: its global loads stay in flight while this one is processed
+
+            // ---- this warp's entries, in chain order ----
+            uint16_t *const wIdx = sIdx[quad];
+            uint32_t m = 0;
+            for (uint32_t e0 = 0; e0 < n; e0 += 32)
+            {
+                const uint32_t e = e0 + lane;
+                const bool mine = e < n && ((sMask[buf][e] >> quad) & 1);
+                const unsigned b = __ballot_sync(0xFFFFFFFFu, mine);
+                if (mine) wIdx[m + __popc(b & ((1u << lane) - 1))] = (uint16_t) e;
+                m += __popc(b);
+            }
+            __syncwarp();
+
+            // ---- pair tests over them ----
+            const float4 *const bPosT = sPosT[buf];
+            const float4 *const bNormQ = sNormQ[buf];
+            const float *const bInvR = sInvR[buf];
+            for (uint32_t i = 0; i < m; i++)
+            {
+                const uint32_t e = wIdx[i];
+                const float4 s = bPosT[e];
+                const float pz = __fsub_rn(s.z, cz);
+                const float py = __fsub_rn(s.y, cy);
+                const float t = __fmaf_rn(py, py, __fmul_rn(pz, pz));
+                float px[kSlots], pp[kSlots];
+                bool hit[kSlots];
+#pragma unroll
+                for (int j = 0; j < kSlots; j++)
+                {
+                    px[j] = __fsub_rn(s.x, cx[j]);
+                    pp[j] = __fmaf_rn(px[j], px[j], t);
+                    hit[j] = pp[j] < s.w;   // <=> pp * invr2 < 0.99f, see hitThreshold()
+                }
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < kSlots; j++) any |= hit[j];
+                if (__any_sync(0xFFFFFFFFu, any))
+                {
+                    const float4 nq = bNormQ[e];
+                    const float invr2 = bInvR[e];
+                    const float u = __fmaf_rn(nq.y, py, __fmul_rn(nq.z, pz));   // shared part of dot3(n, p)
+#pragma unroll
+                    for (int j = 0; j < kSlots; j++)
+                    {
+                        const float d = __fmul_rn(pp[j], invr2);
+                        float w = __fsub_rn(1.0f, d);
+                        w = __fmul_rn(w, w);
+                        w = __fmul_rn(w, w);
+                        w = __fmul_rn(w, nq.w);
+                        w = hit[j] ? w : 0.0f;   // adding w = 0 terms is exact: no divergent region
+                        const float ppj = pp[j];
+                        Accum &a = acc[j];
+                        a.sumW = __fadd_rn(a.sumW, w);
+                        a.sumWpx = __fmaf_rn(w, px[j], a.sumWpx);
+                        a.sumWpy = __fmaf_rn(w, py, a.sumWpy);
+                        a.sumWpz = __fmaf_rn(w, pz, a.sumWpz);
+                        a.sumWnx = __fmaf_rn(w, nq.x, a.sumWnx);
+                        a.sumWny = __fmaf_rn(w, nq.y, a.sumWny);
+                        a.sumWnz = __fmaf_rn(w, nq.z, a.sumWnz);
+                        a.sumWpp = __fmaf_rn(w, ppj, a.sumWpp);
+                        a.sumWpn = __fmaf_rn(w, __fmaf_rn(nq.x, px[j], u), a.sumWpn);
+                        asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}"
+                            : "+r"(a.hits) : "f"(pp[j]), "f"(s.w));
+                    }
+                }
+            }
+            // no barrier here: the next batch goes to the other buffer, and nobody can be two batches
+            // ahead of a warp that is still reading this one (the two barriers of the next batch are in between)
+        }
+
+        unsigned long long hits = 0;
+#pragma unroll
+        for (int j = 0; j < kSlots; j++)
+        {
+            out[j] = finish<SHAPE>(acc[j], P.boundaryFactor);
+            if (COUNT) hits += acc[j].hits;
+        }
+        if (COUNT)
+        {
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                tests += __shfl_xor_sync(0xFFFFFFFFu, tests, o);
+                hits += __shfl_xor_sync(0xFFFFFFFFu, hits, o);
+            }
+            if (lane == 0)
+            {
+                atomicAdd(&P.work[0], tests);
+                atomicAdd(&P.work[1], hits);
+            }
+        }
+    }
+
+    // write_imagef(corners, (x, y + z*zStride + zBias)), kernels/mls.cl:429-432
+    const long row = (long) (wy + ly) + (long) (wz + lz) * P.zStride + P.zBias;
+    float *dst = P.field + row * P.pitch + wx + lx;
+#pragma unroll
+    for (int j = 0; j < kSlots; j++) dst[2 * j] = out[j];
+}
+
 // Dependent-free FFMA stream: 8 independent accumulators per thread, every issue slot an FFMA.
 __global__ void __launch_bounds__(256) fp32PeakKernel(float *out, float a, float b, int iters)
 {
@@ -501,9 +746,21 @@ int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &
         s = w->mlsStream;
     }
     const bool pre = P.thresholds != nullptr;
+    // MLSB_MLS_CULL=block selects the two-level cull.  It is bit-identical and executes fewer instructions, but
+    // measured on C2 it is no faster (lone worker 20.4 against 19.4 ms per step, bench 356 against 358 Msplats/s):
+    // its two barriers per 256 chain entries tie the eight warps of a block to the slowest brick, and the
+    // independent per-warp walks hide their own fetch latency better.  The per-warp kernel stays the default.
+    static const bool blockCull = [] { const char *e = getenv("MLSB_MLS_CULL"); return e != nullptr && strcmp(e, "block") == 0; }();
 #define MLSB_LAUNCH(SHAPE)                                                                                  \
     do {                                                                                                    \
-        if (count && pre) processCornersKernel<SHAPE, true, true><<<grid, kThreads, 0, s>>>(P);             \
+        if (blockCull)                                                                                      \
+        {                                                                                                   \
+            if (count && pre) processCornersBlockCullKernel<SHAPE, true, true><<<grid, kThreads, 0, s>>>(P);    \
+            else if (count) processCornersBlockCullKernel<SHAPE, true, false><<<grid, kThreads, 0, s>>>(P);     \
+            else if (pre) processCornersBlockCullKernel<SHAPE, false, true><<<grid, kThreads, 0, s>>>(P);       \
+            else processCornersBlockCullKernel<SHAPE, false, false><<<grid, kThreads, 0, s>>>(P);               \
+        }                                                                                                   \
+        else if (count && pre) processCornersKernel<SHAPE, true, true><<<grid, kThreads, 0, s>>>(P);        \
         else if (count) processCornersKernel<SHAPE, true, false><<<grid, kThreads, 0, s>>>(P);              \
         else if (pre) processCornersKernel<SHAPE, false, true><<<grid, kThreads, 0, s>>>(P);                \
         else processCornersKernel<SHAPE, false, false><<<grid, kThreads, 0, s>>>(P);                        \

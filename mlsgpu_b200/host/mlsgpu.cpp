@@ -61,7 +61,7 @@ struct Options
     bool quiet = false, statistics = false, statisticsCL = false, split = false;
     std::uint64_t splitSize = 100ull << 20;   // src/mlsgpu_core.cpp:162
     std::string checkpoint, resume;           // src/mlsgpu_core.cpp:121-122
-    std::string statisticsFile;
+    std::string statisticsFile, timeplot;
     std::string output;
     std::vector<std::string> inputs;
 };
@@ -96,7 +96,8 @@ void usage()
         "  --resume FILE               write the output from a checkpoint (no input is read, no device is used)\n"
         "  --statistics                print statistics at the end\n"
         "  --statistics-file FILE      direct statistics to FILE instead of stdout (implies --statistics)\n"
-        "  --statistics-cl             collect timings for the device kernels (kernel.*.time)\n";
+        "  --statistics-cl             collect timings for the device kernels (kernel.*.time)\n"
+        "  --timeplot FILE             write an EVENT log of what every thread did when (utils/timeplot.py's input)\n";
 }
 
 // Capacity, src/options.cpp:38-69
@@ -118,7 +119,7 @@ Options parse(int argc, char **argv)
     // accepted for compatibility, value ignored
     static const std::map<std::string, bool> ignored = {
         {"--response-file", true}, {"--tmp-dir", true},
-        {"--timeplot", true}, {"--max-split", true}, {"--reader", true}, {"--writer", true}, {"--omp-threads", true},
+        {"--max-split", true}, {"--reader", true}, {"--writer", true}, {"--omp-threads", true},
         {"--decache", false},
         {"--mem-host-splats", true}, {"--mem-reorder", true}, {"--mem-gather", true},
         {"--cl-device", true}, {"--cl-gpu", false}, {"--cl-cpu", false}, {"--debug", false}};
@@ -171,6 +172,7 @@ Options parse(int argc, char **argv)
         else if (a == "--statistics") o.statistics = true;
         else if (a == "--statistics-file") { o.statisticsFile = value(); o.statistics = true; }
         else if (a == "--statistics-cl") o.statisticsCL = true;
+        else if (a == "--timeplot") o.timeplot = value();
         else if (a == "--checkpoint") o.checkpoint = value();
         else if (a == "--resume") o.resume = value();
         else if (a == "--split") o.split = true;
@@ -264,9 +266,26 @@ Written writeMesh(mlsb::Mesher &mesher, bool split, const std::string &output, d
     return w;
 }
 
+// --timeplot (src/timeplot.cpp:134-186): "EVENT worker action t0 t1" lines, seconds on one clock
+struct TimeplotLog
+{
+    bool enabled = false;
+    std::mutex mutex;
+    std::vector<std::string> lines;
+    void add(const std::string &worker, const char *action, double t0, double t1)
+    {
+        if (!enabled) return;
+        char buf[256];
+        std::snprintf(buf, sizeof(buf), "EVENT %s %s %.6f %.6f", worker.c_str(), action, t0, t1);
+        std::lock_guard<std::mutex> lock(mutex);
+        lines.push_back(buf);
+    }
+};
+
 struct SinkState
 {
     explicit SinkState(bool split) : mesher(split) {}
+    TimeplotLog timeplot;
     mlsb::Mesher mesher;
     std::mutex mutex;
     double prepareSeconds = 0.0;   // per-block work, concurrently on the worker threads (summed)
@@ -278,6 +297,7 @@ struct SinkState
 void meshSink(std::uint64_t tag, const mlsb_mesh_sizes *sizes, const void *blob, void *user)
 {
     SinkState *st = static_cast<SinkState *>(user);
+    const double tSink = st->timeplot.enabled ? mlsb_timeplot_now() : 0.0;
     // the tag carries the bin's output chunk (ChunkId::coords), 21 bits per axis
     const mlsb::Mesher::chunk_type chunk = {{(std::uint32_t) (tag & 0x1FFFFF), (std::uint32_t) ((tag >> 21) & 0x1FFFFF),
                                              (std::uint32_t) ((tag >> 42) & 0x1FFFFF)}};
@@ -296,8 +316,11 @@ void meshSink(std::uint64_t tag, const mlsb_mesh_sizes *sizes, const void *blob,
     const double t3 = now();
     mlsb::Mesher::complete(*block);
     const double local = (t1 - t0) + (now() - t3);
-    std::lock_guard<std::mutex> lock(st->mutex);
-    st->prepareSeconds += local;
+    {
+        std::lock_guard<std::mutex> lock(st->mutex);
+        st->prepareSeconds += local;
+    }
+    if (st->timeplot.enabled) st->timeplot.add("mesher", "compute", tSink, mlsb_timeplot_now());   // MesherGroup's worker
 }
 
 
@@ -400,6 +423,8 @@ int main(int argc, char **argv)
         // Everything the worker threads and the sink read is declared BEFORE the guard that joins them,
         // so that on any exit path (an exception included) it outlives the workers.
         SinkState state(o.split);
+        state.timeplot.enabled = !o.timeplot.empty();
+        const double tp0 = mlsb_timeplot_now();
         std::vector<mlsb_splat> splats;
         std::vector<mlsb::Bin> bins;
         std::vector<std::unique_ptr<mlsb_splat[]>> ring;
@@ -521,9 +546,11 @@ int main(int argc, char **argv)
         }
         float origin[3];
         grid.getVertex0(origin);
+        state.timeplot.add("main", "load", tp0, mlsb_timeplot_now());       // read + grid + bins: the loader's part
         for (mlsb_group *group : groups)
         {
             mlsb::check(mlsb_group_set_concurrent_sink(group, 1));
+            if (state.timeplot.enabled) mlsb::check(mlsb_group_set_timeplot(group, 1));
             for (int i = 0; i < o.deviceThreads; i++)
             {
                 mlsb_worker *w = nullptr;
@@ -613,6 +640,7 @@ int main(int argc, char **argv)
             if (!failure.empty()) throw std::runtime_error(failure);
         }
         const double tDevice = now();
+        const double tpDevice = mlsb_timeplot_now();
 
         // ---- mesher: prune, write (OOCMesher::write) ----
         mlsb::PlyWriter writer;
@@ -633,6 +661,17 @@ int main(int argc, char **argv)
         }
         else
             written = writeMesh(state.mesher, o.split, o.output, o.fitPrune, writer);
+        state.timeplot.add("main", "write", tpDevice, mlsb_timeplot_now());   // OOCMesher::write
+        if (state.timeplot.enabled)
+        {
+            for (mlsb_group *group : groups)
+                mlsb::check(mlsb_group_timeplot(group, [](void *user, const char *worker, const char *action, double t0, double t1) {
+                    static_cast<TimeplotLog *>(user)->add(worker, action, t0, t1);
+                }, &state.timeplot));
+            std::ofstream file(o.timeplot.c_str());
+            for (const std::string &line : state.timeplot.lines) file << line << "\n";
+            if (!file) throw std::runtime_error("Could not write " + o.timeplot);
+        }
         const mlsb::Mesher::Result &mesh = written.totals;
         const std::size_t outputFiles = written.files;
         const double tEnd = now();

@@ -524,3 +524,23 @@ def test_cli_streamed_run_equals_in_core_run(tmp_path):
     assert int(sb["stream.batches"]) >= 4 and int(sb["files.splats"]) == 1_500_000
     d = subprocess.run([build("meshdiff"), str(tmp_path / "core.ply"), str(tmp_path / "stream.ply")], capture_output=True, text=True)
     assert d.returncode == 0, d.stdout + d.stderr
+
+
+@pytest.mark.gpu
+def test_cli_timeplot(tmp_path):
+    """--timeplot: EVENT lines in the reference's format (src/timeplot.cpp:134-186) for the loader, every
+    device worker thread (get / copy / compute per bin) and the mesher, on one clock."""
+    files, fit_grid = synth(tmp_path, "C3", 400_000)
+    log = tmp_path / "timeplot.txt"
+    r = subprocess.run([build("mlsgpu"), "-o", str(tmp_path / "o.ply"), "--fit-grid", repr(fit_grid), "--device", "0",
+                        "--device-threads", "2", "--timeplot", str(log), "--statistics"] + files, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    bins = int(dict(l.split(": ", 1) for l in r.stdout.splitlines() if ": " in l)["bins"])
+    events = [l.split() for l in log.read_text().splitlines()]
+    assert all(e[0] == "EVENT" and len(e) == 5 and float(e[3]) <= float(e[4]) for e in events)
+    workers = {e[1] for e in events}
+    assert {"main", "mesher", "device.0.0", "device.0.1"} <= workers
+    compute = [e for e in events if e[1].startswith("device.") and e[2] == "compute"]
+    assert len(compute) == bins and len([e for e in events if e[2] == "copy"]) == bins
+    load = [e for e in events if e[1] == "main" and e[2] == "load"][0]
+    assert float(load[4]) <= min(float(e[3]) for e in compute) + 1e-3      # bins are computed after they were loaded

@@ -43,11 +43,12 @@ def main():
                 s_, c_ = w.statistic(name)
                 tot[group] += s_ / args.repeat
                 print("  %-44s %9.1f us" % (name, 1e6 * s_ / args.repeat))
-        corners = int(np.prod([-(-int(v) // 8) * 8 for v in b["size"]]))
         oct_bytes = 472.0 * n
-        # SURVEY 8d marching model: field read + per unwelded vertex 24 W + sort 4 x 16 + weld 36 R + 24 W, per index 4 W + 12
-        v_unwelded = 6.0 * nv
-        mar_bytes = 4.0 * corners + v_unwelded * (24 + 64 + 36) + nv * 24 + 3 * nt * 16
+        # SURVEY 8d marching model, as bench.py states it: field read 4 B per corner; per occupied cell 24 W + 56 R; per
+        # per-cell vertex 24 W + a 4-pass (8 B key, 4 B index) sort read and written + 36 R; per welded vertex 24 W;
+        # per index 4 W + 12 (reindex).  The counts are the worker's own (mlsb_worker_get_marching_work).
+        mc, mk, mv, mi, mw = (x / args.repeat for x in w.marching_work())
+        mar_bytes = 4.0 * mc + 80.0 * mk + 156.0 * mv + 24.0 * mw + 16.0 * mi
         print("octree   : %.1f us, model %.0f MB -> %.0f GB/s (%.1f%% of 6541 GB/s)" % (
             1e6 * tot["octree"], oct_bytes / 1e6, oct_bytes / tot["octree"] / 1e9, 100 * oct_bytes / tot["octree"] / 6541.1e9))
         print("marching : %.1f us, model %.0f MB -> %.0f GB/s (%.1f%% of 6541 GB/s)" % (

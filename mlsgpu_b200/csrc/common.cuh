@@ -135,7 +135,8 @@ struct mlsb_worker
     uint64_t *entryStatus = nullptr;
     uint32_t entryTilesMax = 0;
     uint32_t *entryCounters = nullptr;   // [0] tile ticket, [1] number of accepted entries
-    uint32_t *keyCount = nullptr;        // only when the octree is small enough for the one-CTA plan kernel
+    uint32_t *keyCount = nullptr;        // only when the octree is small enough for the cluster plan kernel
+    uint32_t *tileBucket = nullptr;      // [entry tile][bucket]: entries per 256-key bucket, then their base in the bucketed layout
     float *hitThresholds = nullptr;      // per splat: the |p|^2 below which the splat counts (mls.cu), by the build
     uint64_t *scanStatus = nullptr;   // decoupled look-back words for device-wide scans
     uint32_t scanStatusWords = 0;

@@ -12,8 +12,9 @@
 //                 (each cell finds its nearest non-empty ancestor directly, so the six
 //                 level-serial launches of src/splat_tree_cl.cpp:320-331 collapse into one)
 //
-// With the default six levels the key space (37 449 cells) fits the shared memory of one cluster and the build is
-// four launches and one memset ("planned" path below):
+// With the default six levels the key space (37 449 cells) fits the shared memory of one cluster ("planned"
+// paths below).  The default is the BUCKET path further down (five launches, one memset, no CTA ever waits on
+// another); MLSB_OCTREE_SORT=onesweep selects the one-sweep path described here (four launches, one memset):
 //
 //   writeEntriesFused   splats read ONCE: candidates, tile base by decoupled look-back, packed
 //                       (key, id) pairs, 1/r^2 and the MLS hit threshold per splat, and the number of
@@ -29,6 +30,8 @@
 #include "scan.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace mlsb
 {
@@ -314,6 +317,255 @@ planKernel(uint32_t *__restrict__ keyCount, uint32_t numStart, LevelInfo lv, uin
     cluster.sync();   // no CTA may leave while its shared memory can still be read
 }
 
+// ---- the entry sort without any CTA waiting on another (MLSB_OCTREE_SORT=bucket) -------------------
+// The one-sweep passes above spend most of their life in the look-back: every tile waits for the
+// digit counts of the tiles in front of it, 25 us per pass whatever the size, and a CTA that waits
+// holds its share of the SM all the while.  But the number of entries of every KEY is
+// known before anything is sorted (keyCount), and with it every key's final run of command slots
+// (start[]).  So the sort becomes two scatters whose destinations are computed, not negotiated:
+//
+//   countEntriesKernel          (replaces the counting half of the fused entry kernel) per tile of 256
+//                               splats: entries per key (-> keyCount) and per BUCKET of 256 keys
+//   planKernel                  as before; its high-byte histogram is the size of every bucket
+//   bucketPrefixKernel          one CTA per bucket: base of every tile's entries inside the bucket
+//   writeEntriesBucketedKernel  candidates again (cheap), ranked inside the tile, written straight to
+//                               their bucket in (tile, splat, slot) order: a stable partition by high byte
+//   bucketSortEmitKernel        one CTA per bucket: stable ranking by low byte with running counters,
+//                               id written to start[key] + 1 + rank — the command list
+//
+// Five launches instead of four, none of which waits.  (A bucket is walked by ONE CTA in chunks of
+// 2048 entries: an input with millions of entries in one 256-key bucket serialises there.)
+constexpr uint32_t kBucketBits = 8;
+constexpr uint32_t kMaxBuckets = kPlanMaxKeys >> kBucketBits;   // 160
+
+__global__ void __launch_bounds__(256) countEntriesKernel(const mlsb_splat *__restrict__ splats, int3 bias, LevelInfo lv,
+                                                          uint32_t firstSplat, uint32_t numSplats, uint32_t numBuckets,
+                                                          uint32_t tileStride, uint32_t *__restrict__ keyCount,
+                                                          uint32_t *__restrict__ tileBucket)
+{
+    __shared__ uint32_t sBucket[kMaxBuckets];
+    const uint32_t tile = blockIdx.x, lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < numBuckets; i += blockDim.x) sBucket[i] = 0;
+    __syncthreads();
+    const uint32_t g = tile * blockDim.x + threadIdx.x;
+    uint32_t k[8];
+#pragma unroll
+    for (int o = 0; o < 8; o++) k[o] = 0xFFFFFFFFu;
+    if (g < numSplats) splatEntries<true>(*reinterpret_cast<const float4 *>(&splats[g + firstSplat]), bias, lv, k);
+#pragma unroll
+    for (int o = 0; o < 8; o++)
+    {
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, k[o]);
+        if (k[o] != 0xFFFFFFFFu && lane == (uint32_t) __ffs(peers) - 1)
+        {
+            const uint32_t c = (uint32_t) __popc(peers);
+            atomicAdd(&keyCount[k[o]], c);
+            atomicAdd(&sBucket[k[o] >> kBucketBits], c);
+        }
+    }
+    __syncthreads();
+    // [bucket][tile], zeroed by the build's memset: a tile of coherent input touches a handful of buckets
+    for (uint32_t i = threadIdx.x; i < numBuckets; i += blockDim.x)
+        if (sBucket[i]) tileBucket[(size_t) i * tileStride + tile] = sBucket[i];
+}
+
+// bucketSizes = the high-byte digit histogram planKernel leaves (hist[256 ..]).  Turns tileBucket[t][b] (entries of
+// tile t in bucket b) into the position of the tile's first entry of that bucket in the bucketed layout.
+__global__ void __launch_bounds__(256) bucketPrefixKernel(uint32_t *__restrict__ tileBucket, uint32_t tiles, uint32_t tileStride,
+                                                          const uint32_t *__restrict__ bucketSizes)
+{
+    __shared__ uint32_t sScan[33];
+    const uint32_t b = blockIdx.x, tid = threadIdx.x;
+    uint32_t bucketStart;
+    blockExclusiveScan(tid < b ? bucketSizes[tid] : 0u, sScan, &bucketStart);   // numBuckets <= 160 < 256 threads
+    if (bucketSizes[b] == 0) return;
+    // the bucket's row, 256 consecutive tiles at a time (coalesced), carrying the running total
+    uint32_t *const row = tileBucket + (size_t) b * tileStride;
+    uint32_t carry = bucketStart;
+    for (uint32_t t0 = 0; t0 < tiles; t0 += blockDim.x)
+    {
+        const uint32_t t = t0 + tid;
+        const uint32_t c = t < tiles ? row[t] : 0u;
+        uint32_t total;
+        const uint32_t excl = blockExclusiveScan(c, sScan, &total);
+        if (c) row[t] = carry + excl;
+        carry += total;
+    }
+}
+
+constexpr int kTileEntries = 8 * 256;   // at most 8 entries per splat
+__global__ void __launch_bounds__(256) writeEntriesBucketedKernel(uint32_t *__restrict__ keysOut, uint32_t *__restrict__ idsOut,
+                                                                  mlsb_splat *__restrict__ splats, float *__restrict__ thresholds,
+                                                                  int3 bias, LevelInfo lv, uint32_t firstSplat, uint32_t numSplats,
+                                                                  uint32_t numBuckets, uint32_t tileStride,
+                                                                  const uint32_t *__restrict__ tileBucketBase)
+{
+    __shared__ uint32_t sScan[33];
+    __shared__ uint32_t sKey[kTileEntries], sId[kTileEntries];
+    __shared__ uint32_t sCnt[8][kMaxBuckets];   // per warp and bucket: entries so far, then the base of the warp's entries
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < 8 * kMaxBuckets; i += blockDim.x) (&sCnt[0][0])[i] = 0;
+    const uint32_t g = tile * blockDim.x + tid, gid = g + firstSplat;
+    uint32_t k[8];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int o = 0; o < 8; o++) k[o] = 0xFFFFFFFFu;
+    if (g < numSplats)
+    {
+        const float4 pr = *reinterpret_cast<const float4 *>(&splats[gid]);
+        cnt = splatEntries<true>(pr, bias, lv, k);
+        const float invR2 = __fdiv_rn(1.0f, __fmul_rn(pr.w, pr.w));
+        splats[gid].radius = invR2;   // kernels/octree.cl:193
+        thresholds[gid] = hitThreshold(invR2);
+    }
+    // the tile's entries in (splat, slot) order, in shared memory
+    uint32_t n;
+    uint32_t p = blockExclusiveScan(cnt, sScan, &n);
+#pragma unroll
+    for (int o = 0; o < 8; o++)
+        if (k[o] != 0xFFFFFFFFu)
+        {
+            sKey[p] = k[o];
+            sId[p] = gid;
+            p++;
+        }
+    __syncthreads();
+    // stable rank inside the tile, per bucket: a warp takes a contiguous span, lanes stride through it
+    const uint32_t span = ((n + 7) / 8 + 31) / 32 * 32;   // <= 256
+    const uint32_t spanEnd = min((warp + 1) * span, n);
+    uint32_t key[8], rank[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+    {
+        const uint32_t idx = warp * span + j * 32 + lane;
+        const bool valid = (uint32_t) j * 32 < span && idx < spanEnd;
+        key[j] = valid ? sKey[idx] : 0xFFFFFFFFu;
+        const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        if (valid)
+        {
+            const uint32_t b = key[j] >> kBucketBits;
+            const unsigned peers = __match_any_sync(vmask, b);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if ((int) lane == leader)
+            {
+                base = sCnt[warp][b];
+                sCnt[warp][b] = base + __popc(peers);
+            }
+            base = __shfl_sync(peers, base, leader);
+            rank[j] = base + __popc(peers & ((1u << lane) - 1));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (uint32_t b = tid; b < numBuckets; b += blockDim.x)
+    {
+        uint32_t any = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) any |= sCnt[w][b];
+        if (!any) continue;   // the tile has nothing in this bucket: its base was never computed
+        uint32_t run = tileBucketBase[(size_t) b * tileStride + tile];
+#pragma unroll
+        for (int w = 0; w < 8; w++)
+        {
+            const uint32_t t = sCnt[w][b];
+            sCnt[w][b] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (key[j] != 0xFFFFFFFFu)
+        {
+            const uint32_t idx = warp * span + j * 32 + lane;
+            const uint32_t dst = sCnt[warp][key[j] >> kBucketBits] + rank[j];
+            keysOut[dst] = key[j];
+            idsOut[dst] = sId[idx];
+        }
+}
+
+constexpr int kBucketThreads = 1024, kBucketWarps = kBucketThreads / 32;
+constexpr int kBucketChunk = 8 * kBucketThreads;
+__global__ void __launch_bounds__(kBucketThreads) bucketSortEmitKernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ ids,
+                                                            const uint32_t *__restrict__ bucketSizes, uint32_t numStart,
+                                                            const int32_t *__restrict__ start, int32_t *__restrict__ commands)
+{
+    __shared__ uint32_t sScan[33];
+    __shared__ uint32_t sCnt[kBucketWarps][256];   // per warp and low byte: entries of this chunk so far, then the warp's base
+    __shared__ uint32_t sRun[256];      // entries of each low byte in the chunks already done
+    __shared__ int32_t sStart[256];     // start[] of the bucket's keys: the slot in front of the key's first id
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t bucketStart;
+    blockExclusiveScan(tid < b ? bucketSizes[tid] : 0u, sScan, &bucketStart);
+    const uint32_t size = bucketSizes[b];
+    if (size == 0) return;
+    if (tid < 256)
+    {
+        sRun[tid] = 0;
+        const uint32_t key = (b << kBucketBits) | tid;
+        sStart[tid] = key < numStart ? start[key] : -1;
+    }
+    for (uint32_t chunk = 0; chunk < size; chunk += kBucketChunk)
+    {
+        for (uint32_t i = tid; i < kBucketWarps * 256; i += blockDim.x) (&sCnt[0][0])[i] = 0;
+        __syncthreads();
+        const uint32_t n = min((uint32_t) kBucketChunk, size - chunk);
+        const uint32_t *const ck = keys + bucketStart + chunk, *const ci = ids + bucketStart + chunk;
+        uint32_t key[8], id[8], rank[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+        {
+            const uint32_t idx = warp * 256 + j * 32 + lane;
+            key[j] = idx < n ? ck[idx] : 0xFFFFFFFFu;
+            id[j] = idx < n ? ci[idx] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+        {
+            const bool valid = key[j] != 0xFFFFFFFFu;
+            const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
+            if (valid)
+            {
+                const uint32_t d = key[j] & 255u;
+                const unsigned peers = __match_any_sync(vmask, d);
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if ((int) lane == leader)
+                {
+                    base = sCnt[warp][d];
+                    sCnt[warp][d] = base + __popc(peers);
+                }
+                base = __shfl_sync(peers, base, leader);
+                rank[j] = base + __popc(peers & ((1u << lane) - 1));
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        if (tid < 256)
+        {
+            uint32_t run = sRun[tid];
+#pragma unroll 8
+            for (int w = 0; w < kBucketWarps; w++)
+            {
+                const uint32_t t = sCnt[w][tid];
+                sCnt[w][tid] = run;
+                run += t;
+            }
+            sRun[tid] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (key[j] != 0xFFFFFFFFu)
+            {
+                const uint32_t d = key[j] & 255u;
+                commands[sStart[d] + 1 + (int32_t) (sCnt[warp][d] + rank[j])] = (int32_t) id[j];   // writeSplatIds, kernels/octree.cl:256-279
+            }
+        __syncthreads();
+    }
+}
+
 // First and last sorted position of each key (boundaries of equal-key runs).
 __global__ void __launch_bounds__(256) findRunsKernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ numValid,
                                                       int32_t *__restrict__ runFirst, int32_t *__restrict__ runLast)
@@ -449,7 +701,8 @@ uint64_t octreeDeviceBytes(const mlsb_worker_config &c, uint64_t *maxAllocation)
     const uint64_t statusBytes = roundUp((uint64_t) (divUp(c.maxSplats, 256u) + 1) * sizeof(uint64_t), (uint64_t) 256);
     const uint64_t countBytes = planned ? roundUp(maxStart * sizeof(uint32_t), (uint64_t) 256) : 0;
     const uint64_t scratch = roundUp(countBytes + statusBytes + 256, (uint64_t) 256) + sortScratchBytes(maxEntries, 4);
-    uint64_t total = maxStart * 4 * (planned ? 2 : 6) + commands + (uint64_t) c.maxSplats * sizeof(float) + 4 * entryArray + scratch;
+    const uint64_t tileBucket = planned ? (512 + (uint64_t) roundUp(divUp(c.maxSplats, 256u) + 1, 32u) * kMaxBuckets) * sizeof(uint32_t) : 0;
+    uint64_t total = maxStart * 4 * (planned ? 2 : 6) + commands + (uint64_t) c.maxSplats * sizeof(float) + 4 * entryArray + scratch + tileBucket;
     if (maxAllocation) *maxAllocation = std::max(std::max(commands, entryArray), scratch);
     return total;
 }
@@ -494,6 +747,8 @@ int octreeAlloc(mlsb_worker *w)
     w->entryCounters = reinterpret_cast<uint32_t *>(static_cast<char *>(prefix) + countBytes + statusBytes);
     if (planned)
     {
+        // [digit histograms of the bucket path: 512 words | tileBucket rows]: zeroed by one memset per build
+        MLSB_CUDA(cudaMalloc(&w->tileBucket, (512 + (size_t) roundUp(w->entryTilesMax, 32u) * kMaxBuckets) * sizeof(uint32_t)));
         MLSB_CUDA(cudaMemset(w->keyCount, 0, countBytes));
     }
     return MLSB_OK;
@@ -509,6 +764,7 @@ void octreeFree(mlsb_worker *w)
     cudaFree(w->runIndex);
     cudaFree(w->commands);
     cudaFree(w->hitThresholds);
+    cudaFree(w->tileBucket);
     for (int i = 0; i < 2; i++)
     {
         cudaFree(w->entryKeys[i]);
@@ -546,6 +802,42 @@ int octreeBuild(mlsb_worker *w, uint32_t firstSplat, uint32_t numSplats, const i
     const int3 bias = make_int3(offset[0], offset[1], offset[2]);
     uint32_t *numValid = w->entryCounters + 1;   // device-side count of accepted entries
 
+    static const bool bucketSort = [] { const char *e = getenv("MLSB_OCTREE_SORT"); return e == nullptr || strcmp(e, "onesweep") != 0; }();
+    if (planned && bucketSort && bits > kBucketBits && numSplats > 0)
+    {
+        const uint32_t numBuckets = divUp(numStart, 1u << kBucketBits);
+        const uint32_t tileStride = roundUp(tiles, 32u);
+        uint32_t *const bucketHist = w->tileBucket, *const tileBucket = w->tileBucket + 512;
+        {
+            // one memset: the digit histograms planKernel adds to, and the (sparse) per-tile bucket counts
+            ScopedStat st(w, "kernel.octree.fill.time", 0);
+            MLSB_CUDA(cudaMemsetAsync(bucketHist, 0, (512 + (size_t) numBuckets * tileStride) * sizeof(uint32_t), s));
+        }
+        {
+            ScopedStat st(w, "kernel.octree.writeEntries.time");
+            countEntriesKernel<<<tiles, 256, 0, s>>>(w->splats, bias, lv, firstSplat, numSplats, numBuckets, tileStride, w->keyCount,
+                                                     tileBucket);
+        }
+        {
+            ScopedStat st(w, "kernel.octree.scan.time");
+            planKernel<<<kPlanCluster, kPlanThreads, 0, s>>>(w->keyCount, numStart, lv, bits, w->runIndex, w->start, w->commands,
+                                                              bucketHist, numValid);
+            bucketPrefixKernel<<<numBuckets, 256, 0, s>>>(tileBucket, tiles, tileStride, bucketHist + 256);
+        }
+        {
+            ScopedStat st(w, "kernel.octree.writeEntries.time");
+            writeEntriesBucketedKernel<<<tiles, 256, 0, s>>>(w->entryKeys[0], w->entryValues[0], w->splats, w->hitThresholds, bias, lv,
+                                                             firstSplat, numSplats, numBuckets, tileStride, tileBucket);
+        }
+        {
+            ScopedStat st(w, "kernel.octree.sort.time");
+            bucketSortEmitKernel<<<numBuckets, kBucketThreads, 0, s>>>(w->entryKeys[0], w->entryValues[0], bucketHist + 256, numStart, w->start,
+                                                                       w->commands);
+        }
+        w->launches += 5;
+        MLSB_CUDA(cudaGetLastError());
+        return MLSB_OK;
+    }
     if (planned)
     {
         {

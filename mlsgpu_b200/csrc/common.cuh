@@ -192,7 +192,10 @@ struct mlsb_worker
     uint64_t marchWork[5] = {0, 0, 0, 0, 0};   // corners, cells, unwelded vertices, indices, welded vertices
     // host waits: spin (lowest latency) or block on an event (frees the core; MLSB_SYNC=block)
     bool blockingSync = false;
-    bool yieldingSync = false;    // MLSB_SYNC=yield: poll cudaStreamQuery with sched_yield between polls
+    bool yieldingSync = false;
+    // mesh read-back by a kernel writing pinned host memory (one host wait per block) instead of the copy engine
+    // (two waits, no SM): MLSB_READBACK=pack|copy, default pack exactly when the host waits are blocking ones
+    bool packReadback = false;    // MLSB_SYNC=yield: poll cudaStreamQuery with sched_yield between polls
     cudaEvent_t syncEvent = nullptr;
 };
 

@@ -64,6 +64,7 @@ enum
     CTR_UNFLAGGED = 7,  // welded vertices without the external flag (internal + the top z plane)
     CTR_GEN_TICKET = 8,
     CTR_WELD_TICKET = 9,
+    CTR_PACKED = 10,    // host copy only: the pack kernel has written the block into the pinned blob
     CTR_COUNT = 16
 };
 
@@ -792,6 +793,58 @@ __global__ void __launch_bounds__(kLatThreads) latticeEmitKernel(LatticeParams P
     }
 }
 
+// enqueueReadMesh (src/mesh.cpp:62-102) without the host in the loop: the block's sizes live on the
+// device, so a copy-engine read-back needs a round trip first (sizes to the host, wait, five
+// cudaMemcpyAsync of the right lengths, wait again).  This kernel reads the sizes where they are and
+// writes the HostKeyMesh blob — [keys of external vertices][vertices][triangles] — and the counters
+// straight into PINNED HOST memory (zero-copy stores, 128 bytes per warp and instruction): one wait per
+// block.  If the blob is too small it only reports the sizes; the host grows it and launches again.
+// Which way is better depends on who is short of what (mlsb_worker::packReadback): with the host to spare
+// (one GPU, 12 workers on 16 cores) the copy engine wins — 369 against 331 Msplats/s, the packing CTAs
+// hold SM slots for the length of a PCIe transfer —; with eight ranks on 32 cores it is the host's
+// round trips that the GPUs wait for.
+constexpr int kPackThreads = 256, kPackBlocks = 8, kPackUnroll = 8;   // a few CTAs keep PCIe busy; each holds an SM slot for the whole transfer
+__global__ void __launch_bounds__(kPackThreads) packMeshKernel(const uint32_t *__restrict__ counters, const float *__restrict__ welded,
+                                                               const float *__restrict__ weldedFlagged,
+                                                               const uint64_t *__restrict__ keys, const uint64_t *__restrict__ keysFlagged,
+                                                               const uint32_t *__restrict__ indices, uint32_t *__restrict__ blob,
+                                                               uint64_t capacityBytes, uint32_t *__restrict__ hostCounters,
+                                                               uint32_t vertexSpace, uint32_t indexSpace)
+{
+    const uint32_t nV = counters[CTR_WELDED], nI = counters[CTR_INDICES], nInt = counters[CTR_FIRST_EXTERNAL], nU = counters[CTR_UNFLAGGED];
+    const bool overflow = counters[CTR_OVERFLOW] || counters[CTR_VERTS] > vertexSpace || nI > indexSpace;
+    const uint64_t nExt = nV - nInt, nTop = nU - nInt, nF = nV - nU;
+    const uint64_t words = 2 * nExt + 3 * (uint64_t) nV + nI;
+    const bool fits = !overflow && counters[CTR_VERTS] != 0 && 4 * words <= capacityBytes;
+    if (blockIdx.x == 0 && threadIdx.x < CTR_COUNT)
+        hostCounters[threadIdx.x] = threadIdx.x == CTR_PACKED ? (uint32_t) fits : counters[threadIdx.x];
+    if (!fits) return;
+    // the blob as 32-bit words: five source segments, in blob order
+    const uint32_t *const src0 = reinterpret_cast<const uint32_t *>(keys + nInt);      // keys of the top plane (unflagged externals)
+    const uint32_t *const src1 = reinterpret_cast<const uint32_t *>(keysFlagged);
+    const uint32_t *const src2 = reinterpret_cast<const uint32_t *>(welded);
+    const uint32_t *const src3 = reinterpret_cast<const uint32_t *>(weldedFlagged);
+    const uint64_t e0 = 2 * nTop, e1 = e0 + 2 * nF, e2 = e1 + 3 * (uint64_t) nU, e3 = e2 + 3 * nF;
+    const uint64_t stride = (uint64_t) gridDim.x * kPackThreads * kPackUnroll;
+    for (uint64_t base = ((uint64_t) blockIdx.x * kPackUnroll) * kPackThreads + threadIdx.x; base < words; base += stride)
+    {
+        uint32_t v[kPackUnroll];
+#pragma unroll
+        for (int u = 0; u < kPackUnroll; u++)
+        {
+            const uint64_t i = base + (uint64_t) u * kPackThreads;
+            if (i < words)
+                v[u] = i < e0 ? src0[i] : i < e1 ? src1[i - e0] : i < e2 ? src2[i - e1] : i < e3 ? src3[i - e2] : indices[i - e3];
+        }
+#pragma unroll
+        for (int u = 0; u < kPackUnroll; u++)
+        {
+            const uint64_t i = base + (uint64_t) u * kPackThreads;
+            if (i < words) blob[i] = v[u];
+        }
+    }
+}
+
 }  // namespace
 
 int marchingTablesHost(uint8_t *count, uint16_t *start, uint8_t *data, uint32_t *key)
@@ -1041,11 +1094,25 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     }
     MLSB_CUDA(cudaGetLastError());
 
-    // ---- readback of the sizes (src/marching.cpp:587-617), then the mesh itself ----
+    // ---- sizes and mesh to the host: the pack kernel writes both into pinned memory (one wait); the device-mesh
+    // variant only needs the sizes (src/marching.cpp:587-617) ----
+    auto pack = [&]() {
+        ScopedStat st(w, "kernel.marching.readback.time");
+        packMeshKernel<<<kPackBlocks, kPackThreads, 0, s>>>(w->marchCounters, w->welded, w->weldedFlagged, w->weldedKeys,
+                                                            w->weldedKeysFlagged, w->indices, static_cast<uint32_t *>(w->hostBlob),
+                                                            w->hostBlobBytes, w->hostCounters, (uint32_t) w->vertexSpace,
+                                                            (uint32_t) w->indexSpace);
+        w->launches++;
+    };
+    const bool packed = !io.deviceSink && w->packReadback;
+    if (packed)
+        pack();
+    else
     {
         ScopedStat st(w, "kernel.marching.readback.time", 0);
         MLSB_CUDA(cudaMemcpyAsync(w->hostCounters, w->marchCounters, CTR_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     }
+    MLSB_CUDA(cudaGetLastError());
     MLSB_TRY(waitStream(w));
     const uint32_t *hc = w->hostCounters;
     w->marchWork[0] += (uint64_t) size[0] * size[1] * (zLast - zFirst + 1);
@@ -1083,25 +1150,39 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
         return MLSB_OK;
     }
     // HostKeyMesh layout, src/mesh.cpp:51-60
-    MLSB_TRY(ensureHostBlob(w, (size_t) mlsb_mesh_host_bytes(&sizes)));
-    uint8_t *blob = static_cast<uint8_t *>(w->hostBlob);
-    uint8_t *hKeys = blob;
-    uint8_t *hVerts = hKeys + numExternal * sizeof(uint64_t);
-    uint8_t *hTris = hVerts + sizes.numVertices * 3 * sizeof(float);
-    // enqueueReadMesh, src/mesh.cpp:62-102
-    MLSB_CUDA(cudaMemcpyAsync(hTris, w->indices, sizes.numTriangles * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    if (numTop)
-        MLSB_CUDA(cudaMemcpyAsync(hKeys, w->weldedKeys + sizes.numInternalVertices, numTop * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    if (numFlagged)
+    MLSB_TRY(ensureHostBlob(w, (size_t) mlsb_mesh_host_bytes(&sizes)));   // keeps the pointer if it is large enough
+    if (packed)
     {
-        MLSB_CUDA(cudaMemcpyAsync(hKeys + numTop * sizeof(uint64_t), w->weldedKeysFlagged, numFlagged * sizeof(uint64_t),
-                                  cudaMemcpyDeviceToHost, s));
-        MLSB_CUDA(cudaMemcpyAsync(hVerts + numUnflagged * 3 * sizeof(float), w->weldedFlagged, numFlagged * 3 * sizeof(float),
-                                  cudaMemcpyDeviceToHost, s));
+        // already in the blob unless it was too small
+        if (!hc[CTR_PACKED])
+        {
+            pack();
+            MLSB_CUDA(cudaGetLastError());
+            MLSB_TRY(waitStream(w));
+            MLSB_REQUIRE(w->hostCounters[CTR_PACKED], MLSB_ERR_STATE, "the mesh did not fit the grown read-back blob");
+        }
     }
-    if (numUnflagged)
-        MLSB_CUDA(cudaMemcpyAsync(hVerts, w->welded, numUnflagged * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    MLSB_TRY(waitStream(w));
+    else
+    {
+        // enqueueReadMesh, src/mesh.cpp:62-102, on the copy engine: no SM is involved
+        uint8_t *hKeys = static_cast<uint8_t *>(w->hostBlob);
+        uint8_t *hVerts = hKeys + numExternal * sizeof(uint64_t);
+        uint8_t *hTris = hVerts + sizes.numVertices * 3 * sizeof(float);
+        MLSB_CUDA(cudaMemcpyAsync(hTris, w->indices, sizes.numTriangles * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (numTop)
+            MLSB_CUDA(cudaMemcpyAsync(hKeys, w->weldedKeys + sizes.numInternalVertices, numTop * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        if (numFlagged)
+        {
+            MLSB_CUDA(cudaMemcpyAsync(hKeys + numTop * sizeof(uint64_t), w->weldedKeysFlagged, numFlagged * sizeof(uint64_t),
+                                      cudaMemcpyDeviceToHost, s));
+            MLSB_CUDA(cudaMemcpyAsync(hVerts + numUnflagged * 3 * sizeof(float), w->weldedFlagged, numFlagged * 3 * sizeof(float),
+                                      cudaMemcpyDeviceToHost, s));
+        }
+        if (numUnflagged)
+            MLSB_CUDA(cudaMemcpyAsync(hVerts, w->welded, numUnflagged * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        MLSB_TRY(waitStream(w));
+    }
+    const uint8_t *blob = static_cast<const uint8_t *>(w->hostBlob);
     if (io.sink) io.sink(&sizes, blob, io.user);
     return MLSB_OK;
 }

@@ -238,7 +238,7 @@ int mlsb_worker_create(const mlsb_worker_config *config, mlsb_worker **out)
         w->blockingSync = mode != nullptr && strcmp(mode, "block") == 0;
         w->yieldingSync = mode != nullptr && strcmp(mode, "yield") == 0;
         const char *readback = getenv("MLSB_READBACK");
-        w->packReadback = readback != nullptr ? strcmp(readback, "pack") == 0 : w->blockingSync;
+        w->packReadback = readback != nullptr && strcmp(readback, "pack") == 0;
         if (cudaEventCreateWithFlags(&w->syncEvent, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
         {
             setError("event creation failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -194,7 +194,7 @@ struct mlsb_worker
     bool blockingSync = false;
     bool yieldingSync = false;
     // mesh read-back by a kernel writing pinned host memory (one host wait per block) instead of the copy engine
-    // (two waits, no SM): MLSB_READBACK=pack|copy, default pack exactly when the host waits are blocking ones
+    // (two waits, no SM): MLSB_READBACK=pack, off by default (see packMeshKernel for the measurements)
     bool packReadback = false;    // MLSB_SYNC=yield: poll cudaStreamQuery with sched_yield between polls
     cudaEvent_t syncEvent = nullptr;
 };

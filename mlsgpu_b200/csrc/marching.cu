@@ -799,10 +799,9 @@ __global__ void __launch_bounds__(kLatThreads) latticeEmitKernel(LatticeParams P
 // writes the HostKeyMesh blob — [keys of external vertices][vertices][triangles] — and the counters
 // straight into PINNED HOST memory (zero-copy stores, 128 bytes per warp and instruction): one wait per
 // block.  If the blob is too small it only reports the sizes; the host grows it and launches again.
-// Which way is better depends on who is short of what (mlsb_worker::packReadback): with the host to spare
-// (one GPU, 12 workers on 16 cores) the copy engine wins — 369 against 331 Msplats/s, the packing CTAs
-// hold SM slots for the length of a PCIe transfer —; with eight ranks on 32 cores it is the host's
-// round trips that the GPUs wait for.
+// MLSB_READBACK=pack selects it; the copy engine stays the default.  Measured: one GPU, 12 workers — 364–369
+// Msplats/s either way with 8 packing CTAs (331 with 64: they hold SM slots for the length of a PCIe transfer);
+// eight GPUs on a 32-vCPU box — HBM-resident 1067 against 1345 Msplats/s, from host memory 1124 against 960.
 constexpr int kPackThreads = 256, kPackBlocks = 8, kPackUnroll = 8;   // a few CTAs keep PCIe busy; each holds an SM slot for the whole transfer
 __global__ void __launch_bounds__(kPackThreads) packMeshKernel(const uint32_t *__restrict__ counters, const float *__restrict__ welded,
                                                                const float *__restrict__ weldedFlagged,

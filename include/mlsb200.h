@@ -129,6 +129,14 @@ typedef struct
  * enqueues must have been waited for, or be on `stream`, when it returns.  A non-zero return aborts. */
 typedef int (*mlsb_device_mesh_sink)(const mlsb_device_mesh *mesh, void *stream, void *user);
 
+/* MeshFilter (src/mesh_filter.h:55-67): reads *in and describes its result in *out, with any device work
+ * ENQUEUED on `stream` (a cudaStream_t).  *out arrives as a copy of *in: a filter that works in place only
+ * edits out->sizes; one that writes elsewhere points out's arrays at its own device buffers, which must
+ * stay valid until the block has been handed over.  Sizes are host values (as in DeviceKeyMesh), so a filter
+ * that changes them must know the new counts on the host.  A non-zero return aborts the generate call with
+ * MLSB_ERR_STATE. */
+typedef int (*mlsb_mesh_filter)(void *user, const mlsb_device_mesh *in, mlsb_device_mesh *out, void *stream);
+
 /* Receives one shipped-out block, the equivalent of Marching::OutputFunctor after
  * enqueueReadMesh (src/marching.h:516-546, src/mesh.cpp:62-102).  hostBlob has the HostKeyMesh
  * layout (src/mesh.cpp:51-60): [uint64 keys of external vertices][float[3] vertices]
@@ -223,6 +231,16 @@ MLSB_API int mlsb_marching_generate_cb(mlsb_worker *w, mlsb_field_generator gene
 MLSB_API int mlsb_marching_generate_device(mlsb_worker *w, mlsb_field_generator generate, void *generatorUser,
                                            const uint32_t size[3], const uint32_t keyOffset[3],
                                            mlsb_device_mesh_sink sink, void *user);
+/* MeshFilterChain::addFilter (src/mesh_filter.h:96-99) for this worker: every block a generate or process_bin
+ * call ships passes through the filters, in the order added, between the marching output (already scaled and
+ * biased: the reference's ScaleBiasFilter is the first link of its chain, src/workers.cpp:224) and the sink —
+ * the host sink then receives the FILTERED mesh, read back by enqueueReadMesh.  Blocks a filter empties are
+ * still handed over, as MeshFilterChain does (test/test_mesh_filter.cpp:233-249). */
+MLSB_API int mlsb_worker_add_mesh_filter(mlsb_worker *w, mlsb_mesh_filter filter, void *user);
+MLSB_API int mlsb_worker_clear_mesh_filters(mlsb_worker *w);
+/* MeshFilterChain::operator() on a mesh of the caller's (src/mesh_filter.cpp:44-64): runs the worker's filters on
+ * `mesh` and hands the result to `sink` (then waits for the stream). */
+MLSB_API int mlsb_mesh_filter_chain_apply(mlsb_worker *w, const mlsb_device_mesh *mesh, mlsb_device_mesh_sink sink, void *user);
 /* enqueueReadMesh (src/mesh.cpp:62-102): reads a device mesh into a HostKeyMesh blob of
  * mlsb_mesh_host_bytes(&mesh->sizes) bytes (pinned memory for speed) and waits for it. */
 MLSB_API int mlsb_device_mesh_read(mlsb_worker *w, const mlsb_device_mesh *mesh, void *hostBlob);
@@ -302,6 +320,13 @@ MLSB_API int mlsb_group_timeplot(mlsb_group *g, mlsb_timeplot_visitor visit, voi
 MLSB_API int mlsb_worker_set_profiling(mlsb_worker *w, int level);
 /* Sum (seconds) and count of a named statistic since the last reset. */
 MLSB_API int mlsb_worker_get_statistic(mlsb_worker *w, const char *name, double *sum, uint64_t *count);
+/* Every statistic of the worker that has samples, in name order: sum, sum of squares and count,
+ * which is what Statistics::Variable holds (src/statistics.h:164-209) — the caller adds them to
+ * its registry.  Besides the kernel times: "marching.shipouts" (blocks shipped per generate call)
+ * and "marching.overflow" (blocks that did not fit the mesh memory and were split),
+ * src/marching.cpp:350-352. */
+typedef void (*mlsb_statistic_visitor)(void *user, const char *name, double sum, double sum2, uint64_t count);
+MLSB_API int mlsb_worker_visit_statistics(mlsb_worker *w, mlsb_statistic_visitor visit, void *user);
 MLSB_API int mlsb_worker_reset_statistics(mlsb_worker *w);
 /* Work model of SURVEY 8(d): while counting is enabled every MLS launch also accumulates its
  * pair tests T and hits H on the device (slower kernel variant: enable only for an untimed
@@ -325,6 +350,9 @@ MLSB_API int mlsb_device_free(void *ptr);
 MLSB_API int mlsb_memcpy_h2d(void *dst, const void *src, size_t bytes);
 MLSB_API int mlsb_memcpy_d2h(void *dst, const void *src, size_t bytes);
 MLSB_API int mlsb_device_memset(void *dst, int value, size_t bytes);
+/* Device-to-device copy enqueued on `stream` (a cudaStream_t; what a MeshFilter or a device mesh sink uses,
+ * CLH::enqueueCopyBuffer in test/test_mesh_filter.cpp:84-103). */
+MLSB_API int mlsb_memcpy_d2d_async(void *dst, const void *src, size_t bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,7 @@ MAX_LEVELS, MAX_SPLATS, MAX_DIMENSION, MAX_GLOBAL_DIMENSION = 10, (1 << 31) // 1
 MESH_SINK = C.CFUNCTYPE(None, C.POINTER(MeshSizes), C.c_void_p, C.c_void_p)
 FIELD_GENERATOR = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Swathe), C.c_void_p)
 DEVICE_MESH_SINK = C.CFUNCTYPE(C.c_int, C.POINTER(DeviceMesh), C.c_void_p, C.c_void_p)
+MESH_FILTER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(DeviceMesh), C.POINTER(DeviceMesh), C.c_void_p)
 GROUP_SINK = C.CFUNCTYPE(None, C.c_uint64, C.POINTER(MeshSizes), C.c_void_p, C.c_void_p)
 
 # every symbol include/mlsb200.h declares: name -> (restype, argtypes)
@@ -84,6 +85,9 @@ API = {
     "mlsb_marching_generate_cb": (C.c_int, [_P, FIELD_GENERATOR, _P, _P, _P, MESH_SINK, _P]),
     "mlsb_marching_generate_device": (C.c_int, [_P, FIELD_GENERATOR, _P, _P, _P, DEVICE_MESH_SINK, _P]),
     "mlsb_device_mesh_read": (C.c_int, [_P, C.POINTER(DeviceMesh), _P]),
+    "mlsb_worker_add_mesh_filter": (C.c_int, [_P, MESH_FILTER, _P]),
+    "mlsb_worker_clear_mesh_filters": (C.c_int, [_P]),
+    "mlsb_mesh_filter_chain_apply": (C.c_int, [_P, C.POINTER(DeviceMesh), DEVICE_MESH_SINK, _P]),
     "mlsb_mesh_host_bytes": (C.c_uint64, [C.POINTER(MeshSizes)]),
     "mlsb_marching_tables": (C.c_int, [_P, _P, _P, _P]),
     "mlsb_worker_process_bin": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, MESH_SINK, _P]),
@@ -100,6 +104,7 @@ API = {
     "mlsb_group_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "mlsb_worker_set_profiling": (C.c_int, [_P, C.c_int]),
     "mlsb_worker_get_statistic": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "mlsb_worker_visit_statistics": (C.c_int, [_P, C.CFUNCTYPE(None, _P, C.c_char_p, C.c_double, C.c_double, C.c_uint64), _P]),
     "mlsb_worker_reset_statistics": (C.c_int, [_P]),
     "mlsb_worker_set_work_counting": (C.c_int, [_P, C.c_int]),
     "mlsb_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
@@ -111,6 +116,7 @@ API = {
     "mlsb_memcpy_h2d": (C.c_int, [_P, _P, C.c_size_t]),
     "mlsb_memcpy_d2h": (C.c_int, [_P, _P, C.c_size_t]),
     "mlsb_device_memset": (C.c_int, [_P, C.c_int, C.c_size_t]),
+    "mlsb_memcpy_d2d_async": (C.c_int, [_P, _P, C.c_size_t, _P]),
 }
 
 _lib = None
@@ -439,6 +445,40 @@ class Worker:
         _check(lib().mlsb_marching_generate_device(self.h, gen, None, size.ctypes.data, ko.ctypes.data, cb, None))
         return blocks
 
+    def add_mesh_filter(self, fn):
+        """MeshFilterChain::addFilter: fn(in_mesh: DeviceMesh, out_mesh: DeviceMesh, stream) -> 0 / None on success.
+        out_mesh starts as a copy of in_mesh; device work goes on `stream`."""
+        cb = MESH_FILTER(lambda _u, i, o, stream: int(fn(i.contents, o.contents, stream) or 0))
+        self._filters = getattr(self, "_filters", []) + [cb]      # keep the thunks alive
+        _check(lib().mlsb_worker_add_mesh_filter(self.h, cb, None))
+
+    def clear_mesh_filters(self):
+        _check(lib().mlsb_worker_clear_mesh_filters(self.h))
+        self._filters = []
+
+    def read_device_mesh(self, mesh):
+        """enqueueReadMesh into numpy arrays: dict(vertices, external_keys, triangles, num_internal)."""
+        s = mesh.sizes
+        nv, nt, ni = int(s.numVertices), int(s.numTriangles), int(s.numInternalVertices)
+        ne = nv - ni
+        raw = np.empty(max(8 * ne + 12 * nv + 12 * nt, 1), np.uint8)
+        _check(lib().mlsb_device_mesh_read(self.h, C.byref(mesh), raw.ctypes.data))
+        return dict(vertices=raw[8 * ne:8 * ne + 12 * nv].view(np.float32).reshape(nv, 3).copy(),
+                    external_keys=raw[:8 * ne].view(np.uint64).copy(),
+                    triangles=raw[8 * ne + 12 * nv:8 * ne + 12 * nv + 12 * nt].view(np.uint32).reshape(nt, 3).copy(),
+                    num_internal=ni)
+
+    def mesh_filter_chain_apply(self, mesh):
+        """MeshFilterChain::operator() on a caller's DeviceMesh: the filtered mesh, read back."""
+        out = []
+
+        def sink(mesh_p, _stream, _user):
+            out.append(self.read_device_mesh(mesh_p.contents))
+            return 0
+        cb = DEVICE_MESH_SINK(sink)
+        _check(lib().mlsb_mesh_filter_chain_apply(self.h, C.byref(mesh), cb, None))
+        return out[0]
+
     def process_bin(self, first, n, size, offset, collect=True):
         """DeviceWorkerGroupBase::Worker::operator() for one bin."""
         blocks = []
@@ -458,6 +498,14 @@ class Worker:
         s, c = C.c_double(), C.c_uint64()
         _check(lib().mlsb_worker_get_statistic(self.h, name.encode(), C.byref(s), C.byref(c)))
         return s.value, c.value
+
+    def statistics(self):
+        """{name: (sum, sum of squares, count)} of every statistic with samples (kernel times need set_profiling)."""
+        out = {}
+        visitor = C.CFUNCTYPE(None, _P, C.c_char_p, C.c_double, C.c_double, C.c_uint64)(
+            lambda _u, name, s, s2, c: out.__setitem__(name.decode(), (s, s2, c)))
+        _check(lib().mlsb_worker_visit_statistics(self.h, visitor, None))
+        return out
 
     def reset_statistics(self):
         _check(lib().mlsb_worker_reset_statistics(self.h))

@@ -32,6 +32,14 @@ int statId(mlsb_worker *w, const char *name)
     return id;
 }
 
+void addSample(mlsb_worker *w, const char *name, double value)
+{
+    StatAccum &a = w->stats[statId(w, name)];
+    a.sum += value;
+    a.sum2 += value * value;
+    a.count++;
+}
+
 static cudaEvent_t takeEvent(mlsb_worker *w)
 {
     if (!w->eventPool.empty())
@@ -68,7 +76,9 @@ void collectStats(mlsb_worker *w)
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, sp.begin, sp.end) == cudaSuccess)
         {
-            w->stats[sp.stat].sum += ms * 1e-3;
+            const double seconds = ms * 1e-3;
+            w->stats[sp.stat].sum += seconds;
+            w->stats[sp.stat].sum2 += seconds * seconds;
             w->stats[sp.stat].count++;
         }
         w->eventPool.push_back(sp.begin);
@@ -473,6 +483,38 @@ int mlsb_marching_generate_device(mlsb_worker *w, mlsb_field_generator generate,
     return st;
 }
 
+int mlsb_worker_add_mesh_filter(mlsb_worker *w, mlsb_mesh_filter filter, void *user)
+{
+    MLSB_REQUIRE(w != nullptr && filter != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
+    w->meshFilters.push_back(std::make_pair(filter, user));
+    return MLSB_OK;
+}
+
+int mlsb_worker_clear_mesh_filters(mlsb_worker *w)
+{
+    MLSB_REQUIRE(w != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null worker");
+    w->meshFilters.clear();
+    return MLSB_OK;
+}
+
+int mlsb_mesh_filter_chain_apply(mlsb_worker *w, const mlsb_device_mesh *mesh, mlsb_device_mesh_sink sink, void *user)
+{
+    MLSB_REQUIRE(w != nullptr && mesh != nullptr && sink != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
+    MLSB_REQUIRE(mesh->sizes.numInternalVertices <= mesh->sizes.numVertices, MLSB_ERR_INVALID_ARGUMENT,
+                 "more internal vertices than vertices");
+    MLSB_CUDA(cudaSetDevice(w->device));
+    mlsb_device_mesh current = *mesh;
+    MLSB_TRY(runMeshFilters(w, current));
+    const int rc = sink(&current, (void *) w->stream, user);
+    MLSB_TRY(waitStream(w));
+    if (rc != 0)
+    {
+        setError("the device mesh sink returned %d", rc);
+        return MLSB_ERR_STATE;
+    }
+    return MLSB_OK;
+}
+
 int mlsb_device_mesh_read(mlsb_worker *w, const mlsb_device_mesh *mesh, void *hostBlob)
 {
     MLSB_REQUIRE(w != nullptr && mesh != nullptr && hostBlob != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
@@ -533,6 +575,19 @@ int mlsb_worker_get_statistic(mlsb_worker *w, const char *name, double *sum, uin
     }
     if (sum) *sum = s;
     if (count) *count = c;
+    return MLSB_OK;
+}
+
+int mlsb_worker_visit_statistics(mlsb_worker *w, mlsb_statistic_visitor visit, void *user)
+{
+    MLSB_REQUIRE(w != nullptr && visit != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
+    MLSB_CUDA(cudaStreamSynchronize(w->stream));
+    collectStats(w);
+    for (const auto &entry : w->statIndex)   // name order
+    {
+        const StatAccum &a = w->stats[entry.second];
+        if (a.count) visit(user, entry.first.c_str(), a.sum, a.sum2, a.count);
+    }
     return MLSB_OK;
 }
 
@@ -608,6 +663,14 @@ int mlsb_memcpy_h2d(void *dst, const void *src, size_t bytes)
 int mlsb_memcpy_d2h(void *dst, const void *src, size_t bytes)
 {
     MLSB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return MLSB_OK;
+}
+
+int mlsb_memcpy_d2d_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (bytes == 0) return MLSB_OK;
+    MLSB_REQUIRE(dst != nullptr && src != nullptr, MLSB_ERR_INVALID_ARGUMENT, "null pointer");
+    MLSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     return MLSB_OK;
 }
 

@@ -83,6 +83,7 @@ struct TimedSpan
 struct StatAccum
 {
     double sum = 0.0;
+    double sum2 = 0.0;   // sum of squares, for the sample standard deviation the reference prints
     uint64_t count = 0;
 };
 
@@ -180,6 +181,9 @@ struct mlsb_worker
     uint32_t *hostCounters = nullptr;   // pinned
     uint8_t *tables = nullptr;          // device copy of the marching LUTs
 
+    // MeshFilterChain (src/mesh_filter.h:69-116): device-side filters between the marching output and the read-back
+    std::vector<std::pair<mlsb_mesh_filter, void *>> meshFilters;
+
     // ---- statistics ----
     int profiling = 0;        // 0 off, 1 processCorners only, 2 every kernel
     bool countWork = false;   // MLS kernels also count pair tests / hits (slower; never timed)
@@ -189,6 +193,7 @@ struct mlsb_worker
     std::vector<mlsb::TimedSpan> pendingSpans;
     std::vector<cudaEvent_t> eventPool;
     uint64_t launches = 0;
+    uint32_t shipouts = 0;    // blocks shipped by the current generate call (statistic marching.shipouts)
     uint64_t marchWork[5] = {0, 0, 0, 0, 0};   // corners, cells, unwelded vertices, indices, welded vertices
     // host waits: spin (lowest latency) or block on an event (frees the core; MLSB_SYNC=block)
     bool blockingSync = false;
@@ -217,6 +222,8 @@ private:
 };
 
 int statId(mlsb_worker *w, const char *name);
+// One host-side sample of a named statistic (marching.shipouts, marching.overflow: src/marching.cpp:350-352).
+void addSample(mlsb_worker *w, const char *name, double value);
 int waitStream(mlsb_worker *w);   // host wait for the worker's compute stream
 void collectStats(mlsb_worker *w);   // requires the stream to be idle
 
@@ -273,6 +280,7 @@ struct MarchIo
     void *deviceUser = nullptr;
 };
 int marchingGenerate(mlsb_worker *w, const MarchIo &io, const uint32_t size[3], const uint32_t keyOffset[3]);
+int runMeshFilters(mlsb_worker *w, mlsb_device_mesh &mesh);
 int marchingReadDeviceMesh(mlsb_worker *w, const mlsb_device_mesh *mesh, void *hostBlob);
 uint64_t marchingDeviceBytes(const mlsb_worker_config &c, uint64_t *maxAllocation, uint64_t *pinnedHost);
 uint64_t octreeDeviceBytes(const mlsb_worker_config &c, uint64_t *maxAllocation);

@@ -988,6 +988,32 @@ void marchingFree(mlsb_worker *w)
 namespace
 {
 
+}  // namespace
+
+// MeshFilterChain::operator() (src/mesh_filter.cpp:44-64) without the output functor: `mesh` becomes the last
+// filter's output.  Filters enqueue on the worker's stream, so they are ordered by it.
+int runMeshFilters(mlsb_worker *w, mlsb_device_mesh &mesh)
+{
+    for (const std::pair<mlsb_mesh_filter, void *> &f : w->meshFilters)
+    {
+        mlsb_device_mesh out = mesh;
+        const int rc = f.first(f.second, &mesh, &out, (void *) w->stream);
+        if (rc != 0)
+        {
+            waitStream(w);
+            setError("a mesh filter returned %d", rc);
+            return MLSB_ERR_STATE;
+        }
+        MLSB_REQUIRE(out.sizes.numInternalVertices <= out.sizes.numVertices, MLSB_ERR_STATE,
+                     "a mesh filter produced more internal vertices than vertices");
+        mesh = out;
+    }
+    return MLSB_OK;
+}
+
+namespace
+{
+
 // One shipped-out block: the cells between corner slices zFirst..zLast (Marching::addSlices +
 // shipOut with zTop = zFirst, zMax = zLast).  Returns MLSB_ERR_OVERFLOW if the block does not
 // fit in the worker's mesh memory (the caller then splits the z range, as
@@ -1103,7 +1129,7 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
                                                             (uint32_t) w->indexSpace);
         w->launches++;
     };
-    const bool packed = !io.deviceSink && w->packReadback;
+    const bool packed = !io.deviceSink && w->meshFilters.empty() && w->packReadback;
     if (packed)
         pack();
     else
@@ -1118,6 +1144,7 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     if (hc[CTR_OVERFLOW] || hc[CTR_VERTS] > w->vertexSpace || hc[CTR_INDICES] > w->indexSpace) return MLSB_ERR_OVERFLOW;
     if (hc[CTR_VERTS] == 0) return MLSB_OK;
 
+    w->shipouts++;
     w->marchWork[1] += hc[CTR_CELLS];
     w->marchWork[2] += hc[CTR_VERTS];
     w->marchWork[3] += hc[CTR_INDICES];
@@ -1127,7 +1154,7 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     // unflagged vertices (internal, then the top plane) and flagged ones live in two buffers
     const uint64_t numUnflagged = hc[CTR_UNFLAGGED], numFlagged = sizes.numVertices - numUnflagged;
     const uint64_t numTop = numUnflagged - sizes.numInternalVertices;
-    if (io.deviceSink)
+    if (io.deviceSink || !w->meshFilters.empty())
     {
         // DeviceKeyMesh (src/mesh.h:101-123): one vertex and one key array, internal vertices first.  The flagged
         // vertices (and their keys) move in behind the unflagged ones, device to device.
@@ -1139,13 +1166,23 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
                                       cudaMemcpyDeviceToDevice, s));
         }
         mlsb_device_mesh mesh{sizes, w->welded, w->weldedKeys, w->indices};
-        const int rc = io.deviceSink(&mesh, (void *) s, io.deviceUser);
-        MLSB_TRY(waitStream(w));
-        if (rc != 0)
+        // MeshFilterChain::operator() (src/mesh_filter.cpp:44-64): each filter reads the previous one's output;
+        // the scale-bias step of the reference's chain has already happened in the vertex pass
+        MLSB_TRY(runMeshFilters(w, mesh));
+        if (io.deviceSink)
         {
-            setError("the device mesh sink returned %d", rc);
-            return MLSB_ERR_STATE;
+            const int rc = io.deviceSink(&mesh, (void *) s, io.deviceUser);
+            MLSB_TRY(waitStream(w));
+            if (rc != 0)
+            {
+                setError("the device mesh sink returned %d", rc);
+                return MLSB_ERR_STATE;
+            }
+            return MLSB_OK;
         }
+        MLSB_TRY(ensureHostBlob(w, (size_t) mlsb_mesh_host_bytes(&mesh.sizes)));
+        MLSB_TRY(marchingReadDeviceMesh(w, &mesh, w->hostBlob));
+        if (io.sink) io.sink(&mesh.sizes, w->hostBlob, io.user);
         return MLSB_OK;
     }
     // HostKeyMesh layout, src/mesh.cpp:51-60
@@ -1191,6 +1228,7 @@ int shipRange(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
 {
     int st = shipBlock(w, useActive, pitch, zStride, size, zFirst, zLast, keyOffset, io);
     if (st != MLSB_ERR_OVERFLOW) return st;
+    addSample(w, "marching.overflow", 1.0);
     if (zLast - zFirst <= 1)
     {
         setError("a single slice of cells does not fit in meshBytes");
@@ -1241,7 +1279,10 @@ int marchingGenerate(mlsb_worker *w, const MarchIo &io, const uint32_t size[3], 
         MLSB_TRY(waitStream(w));
         return MLSB_OK;
     }
-    return shipRange(w, io.useMls, pitch, zStride, size, 0, size[2] - 1, keyOffset, io);
+    w->shipouts = 0;
+    const int status = shipRange(w, io.useMls, pitch, zStride, size, 0, size[2] - 1, keyOffset, io);
+    if (status == MLSB_OK) addSample(w, "marching.shipouts", (double) w->shipouts);
+    return status;
 }
 
 // enqueueReadMesh, src/mesh.cpp:62-102

@@ -322,6 +322,34 @@ def prepare(splats, fit_grid, smooth=4.0, max_cells=255, max_splats=1 << 21, buc
     return g, bins, lo, np.float32(fit_grid)
 
 
+def parse_statistics(text):
+    """{name: value} from a `mlsgpu --statistics` listing (the reference's Statistics::Registry stream,
+    src/statistics.cpp:99-101,175-182,206-208): counters and peaks are ints; variables
+    ("sum : mean [+/- stddev] [n]") become {"sum", "mean", "stddev", "n"}; header lines stay strings."""
+    out = {}
+    for line in text.splitlines():
+        name, sep, value = line.partition(": ")
+        if not sep:
+            continue
+        value = value.strip()
+        if value.endswith("]") and "[" in value:
+            body, _, n = value[:-1].rpartition("[")
+            var = {"n": int(n), "sum": 0.0, "mean": None, "stddev": None}
+            if body.strip():
+                head, _, dev = body.partition("+/-")
+                total, _, mean = head.partition(" : ")
+                var["sum"], var["mean"] = float(total), float(mean)
+                if dev.strip():
+                    var["stddev"] = float(dev)
+            out[name] = var
+        else:
+            try:
+                out[name] = int(value)
+            except ValueError:
+                out[name] = value
+    return out
+
+
 def partition_bins(bins, world):
     """Static partition of bins over `world` GPUs (one worker group per GPU, no collective on the
     data path): longest-processing-time greedy on the splat count, deterministic.  The

@@ -23,8 +23,10 @@
 #include <array>
 #include <cstdint>
 #include <functional>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/mlsb200.h"
 
@@ -215,6 +217,46 @@ public:
 
 private:
     Worker &worker;
+};
+
+/// DeviceKeyMesh, src/mesh.h:101-123: a block still on the device.
+typedef mlsb_device_mesh DeviceKeyMesh;
+
+/// MeshFilterChain, src/mesh_filter.h:69-116: device-side filters between marching and the output functor.
+/// The chain lives in the worker (DeviceWorkerGroup's workers each own one, src/workers.h:193); filters are
+/// held by reference and must outlive it.  MeshFilter: void(stream, inMesh, outMesh) — outMesh starts as a copy
+/// of inMesh; device work goes on the stream (a cudaStream_t); throw to abort.
+class MeshFilterChain
+{
+public:
+    typedef std::function<void(void *stream, const DeviceKeyMesh &inMesh, DeviceKeyMesh &outMesh)> MeshFilter;
+
+    explicit MeshFilterChain(Worker &worker) : worker(worker) {}
+    ~MeshFilterChain() { mlsb_worker_clear_mesh_filters(worker.get()); }
+    MeshFilterChain(const MeshFilterChain &) = delete;
+    MeshFilterChain &operator=(const MeshFilterChain &) = delete;
+
+    void addFilter(const MeshFilter &filter)
+    {
+        filters.emplace_back(new MeshFilter(filter));
+        check(mlsb_worker_add_mesh_filter(worker.get(), &MeshFilterChain::trampoline, filters.back().get()));
+    }
+
+private:
+    static int trampoline(void *user, const mlsb_device_mesh *in, mlsb_device_mesh *out, void *stream)
+    {
+        try
+        {
+            (*static_cast<const MeshFilter *>(user))(stream, *in, *out);
+            return 0;
+        }
+        catch (...)
+        {
+            return 1;
+        }
+    }
+    Worker &worker;
+    std::vector<std::unique_ptr<MeshFilter>> filters;
 };
 
 /// Marching, src/marching.h:564-608.

@@ -33,10 +33,13 @@
 #include "mesher.hpp"
 #include "mlsb200.hpp"
 #include "ply_io.hpp"
+#include "statistics.hpp"
 #include "stream.hpp"
 
 namespace
 {
+
+namespace st = mlsb::statistics;
 
 struct Options
 {
@@ -247,6 +250,7 @@ Written writeMesh(mlsb::Mesher &mesher, bool split, const std::string &output, d
         writer.write(output, mesh.vertexChunks, mesh.triangleChunks);
         w.totals.totalComponents = mesh.totalComponents;
         w.totals.keptComponents = mesh.keptComponents;
+        w.totals.thresholdVertices = mesh.thresholdVertices;
         w.totals.numVertices = mesh.numVertices;
         w.totals.numTriangles = mesh.numTriangles;
         w.files = 1;
@@ -257,6 +261,7 @@ Written writeMesh(mlsb::Mesher &mesher, bool split, const std::string &output, d
     {
         w.totals.totalComponents = c.totalComponents;
         w.totals.keptComponents = c.keptComponents;
+        w.totals.thresholdVertices = c.thresholdVertices;
         w.totals.numVertices += c.numVertices;
         w.totals.numTriangles += c.numTriangles;
         if (c.numTriangles == 0) continue;
@@ -264,6 +269,44 @@ Written writeMesh(mlsb::Mesher &mesher, bool split, const std::string &output, d
         w.files++;
     }
     return w;
+}
+
+// The mesher's summary, under the reference's names and kinds (src/mesher.cpp:530-536, :850)
+void recordMeshStatistics(const Written &w, std::size_t verticesBeforePruning)
+{
+    const mlsb::Mesher::Result &m = w.totals;
+    st::getStatistic<st::Variable>("components.vertices.threshold").add((double) m.thresholdVertices);
+    st::getStatistic<st::Variable>("components.vertices.total").add((double) verticesBeforePruning);
+    st::getStatistic<st::Variable>("components.vertices.kept").add((double) m.numVertices);
+    st::getStatistic<st::Variable>("components.triangles.kept").add((double) m.numTriangles);
+    st::getStatistic<st::Variable>("components.total").add((double) m.totalComponents);
+    st::getStatistic<st::Variable>("components.kept").add((double) m.keptComponents);
+    st::getStatistic<st::Counter>("output.files").add(w.files);
+    st::getStatistic<st::Counter>("output.vertices").add(m.numVertices);
+    st::getStatistic<st::Counter>("output.triangles").add(m.numTriangles);
+}
+
+// writeStatistics (src/mlsgpu_core.cpp:313-352): version, options, then the registry in name order
+// with 15 significant digits, to --statistics-file or stdout.
+void writeStatistics(const std::string &file, int argc, char **argv)
+{
+    std::ostringstream out;
+    out << "mlsgpu version: " << mlsb_version() << "\n";
+    out << "mlsgpu variant: mlsb200 sm_100a\n";
+    out << "mlsgpu options:";
+    for (int i = 1; i < argc; i++) out << ' ' << argv[i];
+    out << "\n";
+    out.precision(15);
+    out << st::Registry::getInstance();
+    if (!file.empty())
+    {
+        std::ofstream f(file.c_str());
+        f << out.str();
+        f.close();
+        if (!f) throw std::runtime_error("Could not write statistics to " + file);
+    }
+    else
+        std::cout << out.str();
 }
 
 // --timeplot (src/timeplot.cpp:134-186): "EVENT worker action t0 t1" lines, seconds on one clock
@@ -360,23 +403,11 @@ int main(int argc, char **argv)
             mesher.load(file);
             mlsb::PlyWriter writer;
             writer.addComment("mlsgpu (mlsb200) resumed from " + o.resume);
+            const std::size_t before = mesher.numVertices();
             const Written written = writeMesh(mesher, mesher.isSplit(), o.output, o.fitPrune, writer);
-            if (!o.quiet || o.statistics)
-            {
-                std::ostringstream out;
-                out << "mlsgpu version: " << mlsb_version() << "\n"
-                    << "components.total: " << written.totals.totalComponents << "\ncomponents.kept: " << written.totals.keptComponents << "\n"
-                    << "output.vertices: " << written.totals.numVertices << "\noutput.triangles: " << written.totals.numTriangles << "\n"
-                    << "output.files: " << written.files << "\n"
-                    << "run.time: " << now() - t0 << "\n";
-                if (!o.statisticsFile.empty())
-                {
-                    std::ofstream stats(o.statisticsFile.c_str());
-                    stats << out.str();
-                }
-                else
-                    std::cout << out.str();
-            }
+            recordMeshStatistics(written, before);
+            st::getStatistic<st::Variable>("run.time").add(now() - t0);
+            if (!o.quiet || o.statistics) writeStatistics(o.statisticsFile, argc, argv);
             return 0;
         }
 
@@ -390,6 +421,14 @@ int main(int argc, char **argv)
         {
             readers.emplace_back(new mlsb::PlyReader(f, (float) o.fitSmooth, (float) o.maxRadius));
             firsts.push_back(firsts.back() + readers.back()->size());
+        }
+        {
+            // src/mlsgpu_core.cpp:568-570
+            std::uint64_t totalBytes = 0;
+            for (const std::unique_ptr<mlsb::PlyReader> &r : readers) totalBytes += (std::uint64_t) r->size() * r->vertexBytes();
+            st::getStatistic<st::Counter>("files.scans").add(files.size());
+            st::getStatistic<st::Counter>("files.splats").add(firsts.back());
+            st::getStatistic<st::Counter>("files.bytes").add(totalBytes);
         }
 
         // ---- device workers: one group per device (the reference: one DeviceWorkerGroup per device,
@@ -422,6 +461,17 @@ int main(int argc, char **argv)
         }
         // Everything the worker threads and the sink read is declared BEFORE the guard that joins them,
         // so that on any exit path (an exception included) it outlives the workers.
+        for (std::size_t g = 0; g < numGroups; g++)
+        {
+            // CLH::ResourceUsage::addStatistics (src/clh.cpp:156-162) for what the groups will allocate
+            mlsb_resource_usage usage;
+            mlsb::check(mlsb_worker_resource_usage_ex(&cfgs[g], &usage));
+            char name[64];
+            std::snprintf(name, sizeof(name), "mem.device.%d", devices[g]);
+            st::getStatistic<st::Peak>(name) += (std::int64_t) (usage.deviceBytes * (std::uint64_t) o.deviceThreads);
+            st::getStatistic<st::Peak>("mem.device.all") += (std::int64_t) (usage.deviceBytes * (std::uint64_t) o.deviceThreads);
+            st::getStatistic<st::Peak>("mem.pinned") += (std::int64_t) (usage.pinnedHostBytes * (std::uint64_t) o.deviceThreads);
+        }
         SinkState state(o.split);
         state.timeplot.enabled = !o.timeplot.empty();
         const double tp0 = mlsb_timeplot_now();
@@ -509,11 +559,16 @@ int main(int argc, char **argv)
         else
             numSplats = stream.scan();   // pass 1: bounds and counts, one chunk per thread at a time
         if (numSplats == 0) throw std::runtime_error("At least one input point is required.");
+        st::getStatistic<st::Counter>("splats.nonfinite").add(firsts.back() - numSplats);
+        st::Peak &memSplats = st::getStatistic<st::Peak>("mem.splats");   // host bytes of the splats loaded at once
+        memSplats = (std::int64_t) (splats.capacity() * sizeof(mlsb_splat));
         const double tRead = now();
         grid = streaming ? stream.grid((float) o.fitGrid, bucketSize) : mlsb::boundingGrid(splats, (float) o.fitGrid, bucketSize);
         for (int a = 0; a < 3; a++)
             if (grid.numCells(a) + 1 > (1 << 20) - 1)   // src/mlsgpu_core.cpp:623-629
                 throw std::runtime_error("The bounding box is too big. Perhaps you have used the wrong units for --fit-grid.");
+        for (int a = 0; a < 3; a++)   // postprocessGrid, src/mlsgpu_core.cpp:618-622
+            st::getStatistic<st::Variable>(std::string("bbox") + "XYZ"[a]).add((double) grid.numCells(a) * grid.spacing);
         const mlsb::BlockLayout layout(grid, maxCells, chunkCells);
         std::vector<std::pair<std::size_t, std::size_t>> batches;   // streaming: runs of blocks loaded together
         if (!streaming)
@@ -571,7 +626,11 @@ int main(int argc, char **argv)
         std::vector<std::uint64_t> submittedBins(numGroups, 0), submittedSplats(numGroups, 0);
         std::size_t numBins = 0, chunksRead = 0;
         // BucketLoader::operator() for a list of bins over `source` (src/bucket_loader.cpp:104-126)
+        st::Variable &loaderWrite = st::getStatistic<st::Variable>("bucket.loader.write");
+        st::Variable &copySplats = st::getStatistic<st::Variable>("copy.splats"), &copySize = st::getStatistic<st::Variable>("copy.size");
+        st::Peak &memRing = st::getStatistic<st::Peak>("mem.ring");   // host bytes of the gather buffers in flight
         auto dispatch = [&](const std::vector<mlsb_splat> &source, const std::vector<mlsb::Bin> &list, std::size_t blockBegin, std::size_t blockEnd) {
+            std::size_t collectedBins = 0, collectedSplats = 0;
             for (const mlsb::Bin &bin : list)
             {
                 if (streaming)
@@ -592,14 +651,21 @@ int main(int argc, char **argv)
                     }
                 if (use.capacity < ids.size())
                 {
+                    memRing -= (std::int64_t) (use.capacity * sizeof(mlsb_splat));
                     use.capacity = std::max(ids.size(), use.capacity + use.capacity / 2);
                     ring[slotIndex].reset(new mlsb_splat[use.capacity]);
+                    memRing += (std::int64_t) (use.capacity * sizeof(mlsb_splat));
                 }
                 mlsb_splat *dst = ring[slotIndex].get();
                 // a few threads are enough and leave the cores to the device workers
 #pragma omp parallel for schedule(static) num_threads(4)
                 for (std::int64_t i = 0; i < (std::int64_t) ids.size(); i++) dst[i] = source[ids[(std::size_t) i]];
                 tGather += now() - tg;
+                loaderWrite.add(now() - tg);                 // BucketLoader's "write" action, src/bucket_loader.cpp:109
+                copySplats.add((double) ids.size());         // src/workers.cpp:414-415
+                copySize.add((double) (bin.size[0] - 1) * (double) (bin.size[1] - 1) * (double) (bin.size[2] - 1));
+                collectedBins++;
+                collectedSplats += ids.size();
                 // CopyGroupBase::Worker::flush (src/workers.cpp:329-343) hands a bin to the device with the most
                 // unallocated splat capacity: here, the group with the fewest splats submitted and not yet processed
                 std::size_t target = 0;
@@ -619,6 +685,9 @@ int main(int argc, char **argv)
                 mlsb::check(mlsb_group_submit(groups[target], dst, (std::uint32_t) ids.size(), bin.size, bin.offset, tag));
                 numBins++;
             }
+            // one flush of the collector (src/bucket_collector.cpp:71-80): the bins handed over together
+            st::getStatistic<st::Variable>("bucket.collector.bins").add((double) collectedBins);
+            st::getStatistic<st::Variable>("bucket.collector.splats").add((double) collectedSplats);
         };
         if (!streaming)
             dispatch(splats, bins, 0, layout.numBlocks());
@@ -629,7 +698,11 @@ int main(int argc, char **argv)
                 std::size_t read = 0;
                 stream.load(grid, layout, batch.first, batch.second, splats, &read);   // BucketCollector + BucketLoader
                 chunksRead += read;
+                const double tc = now();
+                st::getStatistic<st::Variable>("bucket.loader.load").add(tc - tl);
+                memSplats = (std::int64_t) (splats.capacity() * sizeof(mlsb_splat));
                 bins = mlsb::makeBins(splats, grid, maxCells, maxBucketSplats, chunkCells);
+                st::getStatistic<st::Variable>("bucket.loader.compute").add(now() - tc);
                 tLoad += now() - tl;
                 dispatch(splats, bins, batch.first, batch.second);   // gathered into the ring: splats is free again
             }
@@ -660,7 +733,11 @@ int main(int argc, char **argv)
             state.mesher.save(file);
         }
         else
+        {
+            const std::size_t before = state.mesher.numVertices();
             written = writeMesh(state.mesher, o.split, o.output, o.fitPrune, writer);
+            recordMeshStatistics(written, before);
+        }
         state.timeplot.add("main", "write", tpDevice, mlsb_timeplot_now());   // OOCMesher::write
         if (state.timeplot.enabled)
         {
@@ -672,86 +749,57 @@ int main(int argc, char **argv)
             for (const std::string &line : state.timeplot.lines) file << line << "\n";
             if (!file) throw std::runtime_error("Could not write " + o.timeplot);
         }
-        const mlsb::Mesher::Result &mesh = written.totals;
-        const std::size_t outputFiles = written.files;
         const double tEnd = now();
 
-        if (!o.quiet || o.statistics)
         {
-            // writeStatistics, src/mlsgpu_core.cpp:313-352: "name: value" lines, to --statistics-file if given
-            std::ostringstream out;
-            out << "mlsgpu version: " << mlsb_version() << "\n"
-                << "files.splats: " << numSplats << "\n"
-                << "bins: " << numBins << "\n"
-                << "devices: " << numGroups << "\n"
-                << "components.total: " << mesh.totalComponents << "\ncomponents.kept: " << mesh.keptComponents << "\n"
-                << "output.vertices: " << mesh.numVertices << "\noutput.triangles: " << mesh.numTriangles << "\n"
-                << "output.files: " << outputFiles << "\n";
-            char buf[512];
-            std::snprintf(buf, sizeof(buf), "read.time: %.3f\nbucket.time: %.3f\ndevice.time: %.3f\nmesher.time: %.3f\nrun.time: %.3f\n",
-                          tRead - t0, tBucket - tRead, tDevice - tBucket, tEnd - tDevice, tEnd - t0);
-            out << buf;
-            std::snprintf(buf, sizeof(buf), "device.create.time: %.3f\ndevice.create.wait: %.3f\ndevice.gather.time: %.3f\n"
-                          "mesher.prepare.time: %.3f\nmesher.commit.time: %.3f\n",
-                          createSeconds, tCreateWait, tGather, state.prepareSeconds, state.commitSeconds);
-            out << buf;
+            // ---- everything measured goes through the registry (src/statistics.h) ----
+            st::getStatistic<st::Counter>("bins").add(numBins);
+            st::getStatistic<st::Counter>("devices").add(numGroups);
+            st::getStatistic<st::Variable>("read.time").add(tRead - t0);
+            st::getStatistic<st::Variable>("bucket.time").add(tBucket - tRead);
+            st::getStatistic<st::Variable>("device.time").add(tDevice - tBucket);
+            st::getStatistic<st::Variable>("mesher.time").add(tEnd - tDevice);
+            st::getStatistic<st::Variable>("run.time").add(tEnd - t0);
+            st::getStatistic<st::Variable>("device.create.time").add(createSeconds);
+            // the CUDA driver's start-up (no persistence daemon: the GPU is initialised per process) that
+            // reading and bucketing did not hide
+            st::getStatistic<st::Variable>("device.create.wait").add(tCreateWait);
+            st::getStatistic<st::Variable>("device.gather.time").add(tGather);
+            st::getStatistic<st::Variable>("mesher.prepare.time").add(state.prepareSeconds);
+            st::getStatistic<st::Variable>("mesher.commit.time").add(state.commitSeconds);
             if (streaming)
             {
-                std::snprintf(buf, sizeof(buf), "stream.batches: %zu\nstream.chunks: %zu\nstream.chunks.read: %zu\nstream.load.time: %.3f\n",
-                              batches.size(), stream.numChunks(), chunksRead, tLoad);
-                out << buf;
+                st::getStatistic<st::Counter>("stream.batches").add(batches.size());
+                st::getStatistic<st::Counter>("stream.chunks").add(stream.numChunks());
+                st::getStatistic<st::Counter>("stream.chunks.read").add(chunksRead);
+                st::getStatistic<st::Variable>("stream.load.time").add(tLoad);
             }
+            char name[64];
             for (std::size_t g = 0; g < numGroups; g++)
             {
-                std::snprintf(buf, sizeof(buf), "device.%d.bins: %llu\ndevice.%d.splats: %llu\n", devices[g], (unsigned long long) submittedBins[g],
-                              devices[g], (unsigned long long) submittedSplats[g]);
-                out << buf;
+                std::snprintf(name, sizeof(name), "device.%d.bins", devices[g]);
+                st::getStatistic<st::Counter>(name).add(submittedBins[g]);
+                std::snprintf(name, sizeof(name), "device.%d.splats", devices[g]);
+                st::getStatistic<st::Counter>(name).add(submittedSplats[g]);
             }
-            if (o.statisticsCL)
-            {
-                // Statistics::Variable::write (src/statistics.cpp:175-182): "sum : mean [n]", summed over the workers
-                static const char *const names[] = {
-                    "kernel.octree.writeEntries.time", "kernel.octree.sort.time", "kernel.octree.fill.time",
-                    "kernel.octree.countCommands.time", "kernel.octree.scan.time", "kernel.octree.writeSplatIds.time",
-                    "kernel.octree.writeStart.time", "kernel.mls.processCorners.time", "kernel.marching.zero.time",
-                    "kernel.marching.genOccupied.time", "kernel.marching.countUniqueVertices.time",
-                    "kernel.marching.compactVertices.time", "kernel.marching.generateElements.time",
-                    "kernel.marching.readback.time"};
-                for (const char *name : names)
+            // the workers' own statistics: kernel.*.time with --statistics-cl (CUDA events under the reference's names,
+            // src/statistics_cl.cpp), marching.shipouts and marching.overflow always (src/marching.cpp:350-352)
+            for (mlsb_group *group : groups)
+                for (int i = 0; i < o.deviceThreads; i++)
                 {
-                    double sum = 0.0;
-                    std::uint64_t count = 0;
-                    for (mlsb_group *group : groups)
-                        for (int i = 0; i < o.deviceThreads; i++)
-                        {
-                            mlsb_worker *w = nullptr;
-                            double s1 = 0.0;
-                            std::uint64_t c1 = 0;
-                            mlsb::check(mlsb_group_worker(group, (std::uint32_t) i, &w));
-                            mlsb::check(mlsb_worker_get_statistic(w, name, &s1, &c1));
-                            sum += s1;
-                            count += c1;
-                        }
-                    if (count == 0) continue;
-                    std::snprintf(buf, sizeof(buf), "%s: %.9g : %.9g [%llu]\n", name, sum, sum / (double) count, (unsigned long long) count);
-                    out << buf;
+                    mlsb_worker *w = nullptr;
+                    mlsb::check(mlsb_group_worker(group, (std::uint32_t) i, &w));
+                    mlsb::check(mlsb_worker_visit_statistics(w, [](void *, const char *statName, double sum, double sum2, std::uint64_t count) {
+                        if (std::string(statName) == "marching.overflow")
+                            st::getStatistic<st::Counter>(statName).add((unsigned long long) sum);
+                        else
+                            st::getStatistic<st::Variable>(statName).addSamples(sum, sum2, count);
+                    }, nullptr));
                 }
-            }
-            std::snprintf(buf, sizeof(buf), "splats/s end-to-end: %.3g\n", numSplats / (tEnd - t0));
-            out << buf;
-            // the CUDA driver's start-up (no persistence daemon: the GPU is initialised per process)
-            // is a fixed cost; this is the rate a long run converges to
-            std::snprintf(buf, sizeof(buf), "splats/s excluding device start-up: %.3g\n", numSplats / (tEnd - t0 - tCreateWait));
-            out << buf;
-            if (!o.statisticsFile.empty())
-            {
-                std::ofstream file(o.statisticsFile.c_str());
-                file << out.str();
-                if (!file) throw std::runtime_error("Could not write statistics to " + o.statisticsFile);
-            }
-            else
-                std::cout << out.str();
+            st::getStatistic<st::Variable>("splats/s end-to-end").add(numSplats / (tEnd - t0));
+            st::getStatistic<st::Variable>("splats/s excluding device start-up").add(numSplats / (tEnd - t0 - tCreateWait));
         }
+        if (!o.quiet || o.statistics) writeStatistics(o.statisticsFile, argc, argv);
         return 0;
     }
     catch (const std::exception &e)

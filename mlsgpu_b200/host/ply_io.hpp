@@ -55,6 +55,7 @@ public:
     PlyReader &operator=(const PlyReader &) = delete;
 
     std::size_t size() const { return numVertices; }
+    std::size_t vertexBytes() const { return vertexSize; }   // FastPly::Reader::getVertexSize
 
     /// Reads vertices [first, last) and appends the finite ones as conditioned splats
     /// (non-finite splats are dropped, src/splat_set.cpp:221-240).

@@ -144,3 +144,113 @@ def test_device_mesh_from_bound_mls(orc):
     assert len(want) == len(got) == 1
     for k in ("vertices", "triangles", "external_keys"):
         np.testing.assert_array_equal(got[0][k], want[0][k])
+
+
+class TruncateFilter:
+    """The test filter of test/test_mesh_filter.cpp:42-108: copies the mesh into its own device buffers,
+    dropping the FIRST triangle."""
+
+    def __init__(self, max_vertices, max_triangles):
+        import torch
+        self.vertices = torch.empty(3 * max_vertices, dtype=torch.float32, device="cuda")
+        self.keys = torch.empty(max_vertices, dtype=torch.int64, device="cuda")
+        self.triangles = torch.empty(3 * max_triangles, dtype=torch.int32, device="cuda")
+        self.calls = 0
+
+    def __call__(self, inp, out, stream):
+        from mlsgpu_b200.capi import lib
+        self.calls += 1
+        nv, nt = int(inp.sizes.numVertices), int(inp.sizes.numTriangles)
+        assert inp.vertices != self.vertices.data_ptr() and inp.triangles != self.triangles.data_ptr()
+        assert 3 * nv <= self.vertices.numel() and 3 * nt <= self.triangles.numel()
+        assert lib().mlsb_memcpy_d2d_async(self.vertices.data_ptr(), inp.vertices, 12 * nv, stream) == 0
+        assert lib().mlsb_memcpy_d2d_async(self.keys.data_ptr(), inp.vertexKeys, 8 * nv, stream) == 0
+        if nt > 0:
+            assert lib().mlsb_memcpy_d2d_async(self.triangles.data_ptr(), inp.triangles + 12, 12 * (nt - 1), stream) == 0
+        out.vertices, out.vertexKeys, out.triangles = self.vertices.data_ptr(), self.keys.data_ptr(), self.triangles.data_ptr()
+        out.sizes.numTriangles = max(nt - 1, 0)
+        return 0
+
+
+def five_vertex_mesh():
+    """test/test_mesh_filter.cpp:179-192: 5 vertices (4 internal), 3 triangles."""
+    import torch
+    from mlsgpu_b200 import capi
+    v = torch.arange(15, dtype=torch.float32, device="cuda")
+    k = torch.tensor([100, 200, 300, 400, 500], dtype=torch.int64, device="cuda")
+    t = torch.tensor([0, 1, 2, 1, 2, 3, 2, 3, 4], dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    mesh = capi.DeviceMesh(capi.MeshSizes(5, 3, 4), v.data_ptr(), k.data_ptr(), t.data_ptr())
+    return mesh, (v, k, t)
+
+
+def test_mesh_filter_chain_reference_cases():
+    """TestMeshFilterChain (test/test_mesh_filter.cpp:204-268): no filters, two filters, a chain that empties the
+    mesh (still handed over), an empty mesh going in."""
+    import mlsgpu_b200 as m
+    with m.Worker(max_splats=16, max_cells=31) as w:
+        mesh, keep = five_vertex_mesh()
+        got = w.mesh_filter_chain_apply(mesh)                                   # testNoFilters
+        assert (len(got["vertices"]), got["num_internal"], len(got["triangles"])) == (5, 4, 3)
+        np.testing.assert_array_equal(got["vertices"].ravel(), np.arange(15, dtype=np.float32))
+        np.testing.assert_array_equal(got["external_keys"], [500])
+        f1, f2 = TruncateFilter(10, 10), TruncateFilter(10, 10)
+        w.add_mesh_filter(f1)
+        w.add_mesh_filter(f2)
+        got = w.mesh_filter_chain_apply(mesh)                                   # testFilters
+        assert (len(got["vertices"]), got["num_internal"], len(got["triangles"])) == (5, 4, 1)
+        np.testing.assert_array_equal(got["triangles"], [[2, 3, 4]])            # the first two were dropped, in order
+        np.testing.assert_array_equal(got["external_keys"], [500])
+        w.add_mesh_filter(f1)
+        got = w.mesh_filter_chain_apply(mesh)                                   # testCull
+        assert (len(got["vertices"]), len(got["external_keys"]), len(got["triangles"])) == (5, 1, 0)
+        empty, keep2 = five_vertex_mesh()
+        empty.sizes = type(empty.sizes)(0, 0, 0)
+        got = w.mesh_filter_chain_apply(empty)                                  # testEmpty
+        assert (len(got["vertices"]), got["num_internal"], len(got["triangles"])) == (0, 0, 0)
+        assert (f1.calls, f2.calls) == (1 + 2 + 2, 1 + 1 + 1)
+        w.add_mesh_filter(lambda i, o, s: 3)                                    # a failing filter aborts
+        with pytest.raises(m.MlsbError):
+            w.mesh_filter_chain_apply(mesh)
+        w.clear_mesh_filters()
+        got = w.mesh_filter_chain_apply(mesh)
+        assert len(got["triangles"]) == 3
+
+
+def check_truncated(cut, plain, f):
+    assert len(cut) == len(plain) == f.calls
+    for c, p in zip(cut, plain):
+        np.testing.assert_array_equal(c["vertices"], p["vertices"])
+        np.testing.assert_array_equal(c["external_keys"], p["external_keys"])
+        np.testing.assert_array_equal(c["triangles"], p["triangles"][1:])
+        assert c["num_internal"] == p["num_internal"]
+
+
+def test_mesh_filters_apply_to_every_block():
+    """Filters installed on a worker sit between marching and the host sink (the place of DeviceWorkerGroup's
+    filterChain, src/workers.cpp:224,263-274): each block arrives without its first triangle, everything else
+    unchanged — for process_bin, and for a generate call that ships several blocks."""
+    import mlsgpu_b200 as m
+    from mlsgpu_b200 import host
+    from test_oracle_marching import MARCHING_CASES
+    s = host.sphere_splats(20000, seed=1, radius=0.02, noise=0.004)
+    g, bins, lo, spacing = host.prepare(s, 0.04)
+    b = bins[0]
+    splats = np.ascontiguousarray(g[b["ids"]])
+    with m.Worker(max_splats=len(splats), max_cells=int(b["size"].max()) - 1) as w:
+        w.upload_splats(splats)
+        plain = w.process_bin(0, len(splats), b["size"], b["offset"])
+        f = TruncateFilter(len(plain[0]["vertices"]), len(plain[0]["triangles"]))
+        w.add_mesh_filter(f)
+        w.upload_splats(splats)
+        cut = w.process_bin(0, len(splats), b["size"], b["offset"])
+    assert len(plain) == 1
+    check_truncated(cut, plain, f)
+    vol = MARCHING_CASES["truncated"]()
+    with m.Worker(max_splats=16, max_cells=82, mesh_bytes=82 * 82 * 872) as w:      # the minimum: several blocks
+        plain = w.marching_generate_host_field(vol, (0, 0, 0))
+        f = TruncateFilter(max(len(p["vertices"]) for p in plain), max(len(p["triangles"]) for p in plain))
+        w.add_mesh_filter(f)
+        cut = w.marching_generate_host_field(vol, (0, 0, 0))
+    assert len(plain) > 1
+    check_truncated(cut, plain, f)

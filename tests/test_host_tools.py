@@ -119,9 +119,17 @@ def test_cli_end_to_end_sphere(tmp_path):
     r = subprocess.run([exe, "-o", str(out), "--fit-grid", "0.025", "--levels", "3", "--fit-prune", "0.02",
                         "--device-threads", "3", "--statistics", str(inp)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    stats = dict(line.split(": ") for line in r.stdout.strip().splitlines() if ": " in line)
-    assert int(stats["files.splats"]) == len(both) and int(stats["bins"]) >= 8
-    assert int(stats["components.total"]) >= 2 and int(stats["components.kept"]) == 1
+    stats = host.parse_statistics(r.stdout)
+    assert stats["files.splats"] == len(both) and stats["bins"] >= 8 and stats["files.scans"] == 1
+    assert stats["files.bytes"] == len(both) * 29            # 7 floats + the extra one-byte property
+    assert stats["components.total"]["sum"] >= 2 and stats["components.kept"]["sum"] == 1
+    # the registry's other kinds: peaks (bytes), per-bin variables with a spread, the marching counters
+    assert stats["mem.splats"] == len(both) * 32 and stats["mem.device.all"] > 0 and stats["mem.ring"] > 0
+    assert stats["copy.splats"]["n"] == stats["bins"] and stats["copy.splats"]["stddev"] is not None
+    assert stats["marching.shipouts"]["n"] == stats["bins"] and stats["marching.shipouts"]["sum"] >= 8
+    assert stats["bucket.collector.bins"]["sum"] == stats["bins"] and stats["run.time"]["n"] == 1
+    assert stats["components.vertices.kept"]["sum"] == stats["output.vertices"] < stats["components.vertices.total"]["sum"]
+    assert list(stats)[3:] == sorted(list(stats)[3:])        # version, variant, options; then name order
     verts, tris, header = plyfile.read_mesh_ply(out)
     assert is_manifold(len(verts), tris) == ""
     # the acceptance tool of the reference (extras/plymanifold.cpp): manifold, one component (the
@@ -166,9 +174,9 @@ def test_cli_end_to_end_sphere(tmp_path):
                         "--device-threads", "3", "--split", "--split-size", str(760 * 40 * 40), "--statistics", str(inp)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    stats = dict(line.split(": ", 1) for line in r.stdout.strip().splitlines() if ": " in line)
+    stats = host.parse_statistics(r.stdout)
     names = sorted(tmp_path.glob("split_*.ply"))
-    assert len(names) == int(stats["output.files"]) >= 8 and int(stats["components.kept"]) == 1
+    assert len(names) == stats["output.files"] >= 8 and stats["components.kept"]["sum"] == 1
     assert all(len(n.name) == len("split_0000_0000_0000.ply") for n in names)
 
     def soup(v, t):
@@ -185,7 +193,7 @@ def test_cli_end_to_end_sphere(tmp_path):
     whole = soup(verts, tris)
     np.testing.assert_array_equal(np.unique(np.concatenate(parts), axis=0), whole)
     assert sum(len(p) for p in parts) == len(whole) == len(tris)          # no triangle twice
-    assert nverts > len(verts) and nverts == int(stats["output.vertices"])  # border vertices are duplicated
+    assert nverts > len(verts) and nverts == stats["output.vertices"]  # border vertices are duplicated
 
 
 @pytest.mark.gpu
@@ -224,13 +232,14 @@ def test_cli_plane_fit_boundary_and_prune(tmp_path):
                         str(inp)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert r.stdout == ""                                   # --statistics-file: nothing on stdout
-    stats = dict(line.split(": ", 1) for line in stats_file.read_text().strip().splitlines() if ": " in line)
-    # --statistics-cl: per-kernel device times under the reference's names, "sum : mean [n]"
-    total, mean, count = stats["kernel.mls.processCorners.time"].replace("[", "").replace("]", "").replace(" : ", " ").split()
-    assert float(total) > 0 and int(count) == int(stats["bins"]) and abs(float(total) / int(count) - float(mean)) < 1e-6
+    stats = host.parse_statistics(stats_file.read_text())
+    # --statistics-cl: per-kernel device times under the reference's names, "sum : mean +/- stddev [n]"
+    mls = stats["kernel.mls.processCorners.time"]
+    assert mls["sum"] > 0 and mls["n"] == stats["bins"] and abs(mls["sum"] / mls["n"] - mls["mean"]) < 1e-6
+    assert mls["stddev"] is not None and 0 <= mls["stddev"] < mls["mean"] * 10
     assert "kernel.octree.sort.time" in stats and "kernel.marching.generateElements.time" in stats
     # (with the tightened boundary limit the tiny islands may be rejected by the boundary test already)
-    assert int(stats["components.total"]) >= 1 and int(stats["components.kept"]) == 1
+    assert stats["components.total"]["sum"] >= 1 and stats["components.kept"]["sum"] == 1
     verts, tris, _ = plyfile.read_mesh_ply(out)
     assert len(verts) > 5000 and is_manifold(len(verts), tris) == ""
     check = subprocess.run([build("plymanifold"), str(out)], capture_output=True, text=True)
@@ -434,10 +443,10 @@ def test_checkpoint_and_resume(tmp_path):
         r = subprocess.run([cli, "-o", str(out), "--resume", str(ckpt), "--fit-prune", prune, "--statistics"],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
-        stats = dict(line.split(": ", 1) for line in r.stdout.strip().splitlines() if ": " in line)
-        assert int(stats["components.total"]) == 2 and int(stats["components.kept"]) == kept
+        stats = host.parse_statistics(r.stdout)
+        assert stats["components.total"]["sum"] == 2 and stats["components.kept"]["sum"] == kept
         v, t, _ = plyfile.read_mesh_ply(out)
-        assert len(v) == nv == int(stats["output.vertices"]) and t.max() < len(v)
+        assert len(v) == nv == stats["output.vertices"] and t.max() < len(v)
     # a --split checkpoint resumes into chunk files
     chunks = [(0, 0, 0)] * 6 + [(1, 0, 0)] * 6 + [(2, 2, 2)]
     write_blocks(tmp_path / "blocks.bin", blocks, chunks)
@@ -508,6 +517,24 @@ def test_streamed_bins_equal_in_core_bins(tmp_path, config, points, max_cells, m
     assert (batches > 3) == (max_load < points)
 
 
+def test_statistics_registry_known_answers():
+    """host/statistics.hpp against the reference's own cases (test/test_statistics.cpp): counters, variables
+    (mean, sample stddev, length_error below two samples), peaks, registry order / merge / type clash, threads."""
+    r = subprocess.run([build("statistics_test")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "statistics_test: ok", r.stdout + r.stderr
+
+
+def test_parse_statistics_formats():
+    text = ("mlsgpu version: x\ncounter: 100\nstat0: [0]\nstat1: 1 : 1 [1]\nstat3: 12 : 4 +/- 2 [3]\n"
+            "splats/s end-to-end: 2.5e+07 : 2.5e+07 [1]\n")
+    st = host.parse_statistics(text)
+    assert st["mlsgpu version"] == "x" and st["counter"] == 100
+    assert st["stat0"] == {"n": 0, "sum": 0.0, "mean": None, "stddev": None}
+    assert st["stat1"] == {"n": 1, "sum": 1.0, "mean": 1.0, "stddev": None}
+    assert st["stat3"] == {"n": 3, "sum": 12.0, "mean": 4.0, "stddev": 2.0}
+    assert st["splats/s end-to-end"]["mean"] == 2.5e7
+
+
 @pytest.mark.gpu
 def test_cli_streamed_run_equals_in_core_run(tmp_path):
     """mlsgpu with the reference's kind of --mem-load-splats (a fraction of the input): several passes
@@ -520,8 +547,12 @@ def test_cli_streamed_run_equals_in_core_run(tmp_path):
                        capture_output=True, text=True)
     assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
     assert "stream.batches" not in a.stdout
-    sb = dict(l.split(": ", 1) for l in b.stdout.splitlines() if ": " in l)
-    assert int(sb["stream.batches"]) >= 4 and int(sb["files.splats"]) == 1_500_000
+    sb = host.parse_statistics(b.stdout)
+    assert sb["stream.batches"] >= 4 and sb["files.splats"] == 1_500_000
+    # one load / compute sample per batch; the splats held at once stayed near the limit (8 MB = 262 144 splats;
+    # a batch is a run of whole blocks, so it may exceed it by one block)
+    assert sb["bucket.loader.load"]["n"] == sb["stream.batches"] == sb["bucket.loader.compute"]["n"]
+    assert sb["mem.splats"] < host.parse_statistics(a.stdout)["mem.splats"] / 2
     d = subprocess.run([build("meshdiff"), str(tmp_path / "core.ply"), str(tmp_path / "stream.ply")], capture_output=True, text=True)
     assert d.returncode == 0, d.stdout + d.stderr
 
@@ -535,7 +566,7 @@ def test_cli_timeplot(tmp_path):
     r = subprocess.run([build("mlsgpu"), "-o", str(tmp_path / "o.ply"), "--fit-grid", repr(fit_grid), "--device", "0",
                         "--device-threads", "2", "--timeplot", str(log), "--statistics"] + files, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    bins = int(dict(l.split(": ", 1) for l in r.stdout.splitlines() if ": " in l)["bins"])
+    bins = host.parse_statistics(r.stdout)["bins"]
     events = [l.split() for l in log.read_text().splitlines()]
     assert all(e[0] == "EVENT" and len(e) == 5 and float(e[3]) <= float(e[4]) for e in events)
     workers = {e[1] for e in events}

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/mlsb200.h"
+#include "wire.h"
 
 namespace mlsb
 {
@@ -200,7 +201,16 @@ struct mlsb_worker
     bool yieldingSync = false;
     // mesh read-back by a kernel writing pinned host memory (one host wait per block) instead of the copy engine
     // (two waits, no SM): MLSB_READBACK=pack, off by default (see packMeshKernel for the measurements)
-    bool packReadback = false;    // MLSB_SYNC=yield: poll cudaStreamQuery with sched_yield between polls
+    bool packReadback = false;
+    // MLSB_READBACK=compact: the block crosses PCIe in a 48-byte-per-splat wire format (8 bytes per vertex, 8 per
+    // triangle instead of 12 and 12) and the worker thread expands it into the HostKeyMesh blob (unpack.cpp)
+    bool compactReadback = false;
+    uint2 *compactVerts = nullptr, *compactVertsFlagged = nullptr;   // (t, lattice point) per vertex, by rank
+    uint64_t *wireBlob = nullptr;      // device: [external keys][vertices][triangles], one 64-bit word each
+    size_t wireWords = 0;
+    void *hostWire = nullptr;          // pinned landing buffer of the wire blob (grows on demand)
+    size_t hostWireBytes = 0;
+    // MLSB_SYNC=yield: poll cudaStreamQuery with sched_yield between polls
     cudaEvent_t syncEvent = nullptr;
 };
 
@@ -281,6 +291,9 @@ struct MarchIo
 };
 int marchingGenerate(mlsb_worker *w, const MarchIo &io, const uint32_t size[3], const uint32_t keyOffset[3]);
 int runMeshFilters(mlsb_worker *w, mlsb_device_mesh &mesh);
+// MLSB_READBACK: 0 copy engine (default), 1 pack kernel into pinned memory, 2 compact wire format + host unpack
+int readbackModeFromEnv();
+
 int marchingReadDeviceMesh(mlsb_worker *w, const mlsb_device_mesh *mesh, void *hostBlob);
 uint64_t marchingDeviceBytes(const mlsb_worker_config &c, uint64_t *maxAllocation, uint64_t *pinnedHost);
 uint64_t octreeDeviceBytes(const mlsb_worker_config &c, uint64_t *maxAllocation);

@@ -45,6 +45,19 @@ namespace
 #ifndef MLSB_MC_PREFETCH
 #define MLSB_MC_PREFETCH EMIT      /* a C++ expression in the kernel's scope, not a preprocessor value */
 #endif
+// CTAs of 256 threads per SM that the register allocation of the classification and of the index pass aims for.
+// An explicit bound of 1 makes ptxas spend MORE registers than no bound at all (classification 30 -> 40, index pass
+// 64 -> 70, and with the same treatment the lattice pass 44 -> 48 and the octree's bucket sort 47 -> 64: the
+// 12-worker step went from 26.4 to 28.0 ms, 379 -> 357 Msplats/s), so the bounds restate what ptxas chose on its
+// own: 8 (<= 32 registers) and 4 (<= 64).  Capping the index pass harder does not pay: 5 (48 registers) and 6 (40,
+// 96 bytes of spills) measured 377 and 377-378 Msplats/s against 380 at 4; capping the lattice pass or the bucket
+// sort at 32 registers is within the noise as well.
+#ifndef MLSB_MC_CLASSIFY_MINBLOCKS
+#define MLSB_MC_CLASSIFY_MINBLOCKS 8
+#endif
+#ifndef MLSB_MC_EMIT_MINBLOCKS
+#define MLSB_MC_EMIT_MINBLOCKS 4
+#endif
 #ifndef MLSB_MC_EMIT
 #define MLSB_MC_EMIT 0
 #endif
@@ -296,7 +309,7 @@ __device__ __forceinline__ uint32_t latticeRank(const uint4 *__restrict__ record
 //               computed, so that all stores are contiguous.
 // Splitting the pass keeps every CTA free of inter-CTA waits; only the few percent of tiles that
 // hold surface are classified twice.  CHUNKS = ceil(cellsX / 256).
-template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads) generateCellsKernel(GenParams P)
+template <bool EMIT, int CHUNKS> __global__ void __launch_bounds__(kGenThreads, EMIT ? MLSB_MC_EMIT_MINBLOCKS : MLSB_MC_CLASSIFY_MINBLOCKS) generateCellsKernel(GenParams P)
 {
     constexpr int kVRows = kGenRows * CHUNKS;
     extern __shared__ uint32_t sList[];   // EMIT: [2][kVRows * 256]: cell, index base; then [13][256] vertex ranks
@@ -598,6 +611,7 @@ struct LatticeParams
     uint3 gridOffset;
     float *welded, *weldedFlagged;   // unflagged vertices by rank; flagged ones by their own rank
     uint64_t *weldedKeys, *weldedKeysFlagged;
+    uint2 *compact, *compactFlagged; // optional: (t, lattice point) per vertex for the compact read-back
     uint64_t keyOffset;              // src/marching.cpp:594-599
     float scale, bx, by, bz;         // ScaleBiasFilter
     uint32_t vertexSpace, indexSpace;
@@ -660,7 +674,11 @@ __global__ void __launch_bounds__(kLatThreads) latticeCountKernel(LatticeParams 
     if (threadIdx.x == 0) const_cast<uint64_t *>(P.status)[tile] = total;
 }
 
-__global__ void __launch_bounds__(kLatThreads) latticeEmitKernel(LatticeParams P, uint32_t numChunks)
+#ifdef MLSB_MC_LATEMIT_MINBLOCKS
+__global__ void __launch_bounds__(kLatThreads, MLSB_MC_LATEMIT_MINBLOCKS) latticeEmitKernel(LatticeParams P, uint32_t numChunks)
+#else
+__global__ void __launch_bounds__(kLatThreads) latticeEmitKernel(LatticeParams P, uint32_t numChunks)   // 44 registers; capped at 32 (spills) it measures the same
+#endif
 {
     __shared__ uint64_t sScan[33];
     __shared__ uint64_t sBefore;
@@ -787,6 +805,8 @@ __global__ void __launch_bounds__(kLatThreads) latticeEmitKernel(LatticeParams P
         out[0] = __fmaf_rn(px, P.scale, P.bx);
         out[1] = __fmaf_rn(py, P.scale, P.by);
         out[2] = __fmaf_rn(pz, P.scale, P.bz);
+        // what the host needs to redo the four lines above bit for bit (unpackWireMesh): t and the lattice point
+        if (P.compact) (flagged ? P.compactFlagged : P.compact)[rank] = make_uint2(__float_as_uint(t), x2 | (vy2 << 11) | (vz2 << 22));
         if (flagged || vz2 == P.planes - 1)
             (flagged ? P.weldedKeysFlagged : P.weldedKeys)[rank] =
                 ((uint64_t) x2 | ((uint64_t) vy2 << kKeyAxisBits) | ((uint64_t) (vz2 + 2 * P.zFirst) << (2 * kKeyAxisBits))) + P.keyOffset;
@@ -846,6 +866,64 @@ __global__ void __launch_bounds__(kPackThreads) packMeshKernel(const uint32_t *_
 
 }  // namespace
 
+namespace
+{
+
+// MLSB_READBACK=compact.  The HostKeyMesh blob costs 72 bytes of PCIe per input splat on C2 (two vertices of 12
+// bytes, four triangles of 12), and with eight GPUs copying at once the box delivers 15 GB/s per GPU
+// (profiles/r2_probe_d2h_8gpu.txt): the read-back IS the step.  A block's vertices are determined by their lattice
+// point and the interpolation parameter t (latticeEmitKernel), its indices are below 2^21 whenever it has at most
+// 2^21 vertices: 8 bytes each.  This kernel gathers the wire blob — [external keys][vertices][triangles], one
+// 64-bit word each — in DEVICE memory (no SM waits on PCIe, unlike packMeshKernel); the copy engine moves it and
+// the worker thread expands it into the HostKeyMesh blob the sink expects (unpack.cpp), redoing latticeEmitKernel's
+// four fused multiply-adds per vertex: bit-identical.  CTR_PACKED tells the host whether the block qualified.
+constexpr uint32_t kWireIndexBits = 21;
+__global__ void __launch_bounds__(256) compactMeshKernel(uint32_t *__restrict__ counters, const uint64_t *__restrict__ keys,
+                                                         const uint64_t *__restrict__ keysFlagged, const uint2 *__restrict__ compact,
+                                                         const uint2 *__restrict__ compactFlagged, const uint32_t *__restrict__ indices,
+                                                         uint64_t *__restrict__ wire, uint64_t capacityWords, uint32_t vertexSpace,
+                                                         uint32_t indexSpace)
+{
+    const uint32_t nV = counters[CTR_WELDED], nI = counters[CTR_INDICES], nInt = counters[CTR_FIRST_EXTERNAL], nU = counters[CTR_UNFLAGGED];
+    const bool overflow = counters[CTR_OVERFLOW] || counters[CTR_VERTS] > vertexSpace || nI > indexSpace;
+    const uint64_t nExt = nV - nInt, nTop = nU - nInt, nT = nI / 3;
+    const uint64_t words = nExt + nV + nT;
+    const bool fits = !overflow && counters[CTR_VERTS] != 0 && nV <= (1u << kWireIndexBits) && words <= capacityWords;
+    if (!fits) return;   // CTR_PACKED stays 0 (the block's memset)
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CTR_PACKED] = 1;
+    const uint64_t e0 = nTop, e1 = nExt, e2 = nExt + nU, e3 = nExt + nV;
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride)
+    {
+        uint64_t v;
+        if (i < e0) v = keys[nInt + i];
+        else if (i < e1) v = keysFlagged[i - e0];
+        else if (i < e3)
+        {
+            const uint2 c = i < e2 ? compact[i - e1] : compactFlagged[i - e2];
+            v = (uint64_t) c.x | ((uint64_t) c.y << 32);
+        }
+        else
+        {
+            const uint32_t *t = indices + 3 * (i - e3);
+            v = (uint64_t) t[0] | ((uint64_t) t[1] << kWireIndexBits) | ((uint64_t) t[2] << (2 * kWireIndexBits));
+        }
+        wire[i] = v;
+    }
+}
+
+}  // namespace
+
+int readbackModeFromEnv()
+{
+    static const int mode = [] {
+        const char *e = getenv("MLSB_READBACK");
+        if (e == nullptr) return 0;
+        return strcmp(e, "pack") == 0 ? 1 : strcmp(e, "compact") == 0 ? 2 : 0;
+    }();
+    return mode;
+}
+
 int marchingTablesHost(uint8_t *count, uint16_t *start, uint8_t *data, uint32_t *key)
 {
     buildTables();
@@ -868,6 +946,7 @@ struct MarchSizes
     size_t latticeWords;
     size_t field, blockActive, latMask, latRecord, indices, welded, weldedKeys, counters, tileTotals, tileList, tables;
     size_t hostBlobWorst;
+    size_t compactVerts, wireBlob;   // 0 unless MLSB_READBACK=compact
 };
 
 MarchSizes marchSizes(const mlsb_worker_config &c)
@@ -895,6 +974,11 @@ MarchSizes marchSizes(const mlsb_worker_config &c)
     z.tables = sizeof(Tables);
     mlsb_mesh_sizes worst{z.vertexSpace, z.indexSpace / 3, 0};
     z.hostBlobWorst = mlsb_mesh_host_bytes(&worst) + 64;
+    if (readbackModeFromEnv() == 2)
+    {
+        z.compactVerts = (z.vertexSpace + 1) * sizeof(uint2);      // twice: unflagged and flagged
+        z.wireBlob = (2 * z.vertexSpace + z.indexSpace / 3 + 1) * sizeof(uint64_t);   // keys + vertices + triangles
+    }
     return z;
 }
 
@@ -918,7 +1002,7 @@ uint64_t marchingDeviceBytes(const mlsb_worker_config &c, uint64_t *maxAllocatio
 {
     const MarchSizes z = marchSizes(c);
     const size_t all[] = {z.field, z.blockActive, z.latMask, z.latRecord, z.indices, z.welded, z.welded, z.weldedKeys, z.weldedKeys,
-                          z.counters, z.tileTotals, z.tileList, z.tables};
+                          z.counters, z.tileTotals, z.tileList, z.tables, z.compactVerts, z.compactVerts, z.wireBlob};
     uint64_t total = 0, largest = 0;
     for (size_t b : all)
     {
@@ -926,7 +1010,8 @@ uint64_t marchingDeviceBytes(const mlsb_worker_config &c, uint64_t *maxAllocatio
         largest = std::max<uint64_t>(largest, b);
     }
     if (maxAllocation) *maxAllocation = largest;
-    if (pinnedHost) *pinnedHost = z.hostBlobWorst + CTR_COUNT * sizeof(uint32_t);   // the blob's upper bound: it grows on demand
+    // the blob's upper bound: it grows on demand (compact read-back: plus the landing buffer of the wire blob)
+    if (pinnedHost) *pinnedHost = z.hostBlobWorst + z.wireBlob + CTR_COUNT * sizeof(uint32_t);
     return total;
 }
 
@@ -958,6 +1043,14 @@ int marchingAlloc(mlsb_worker *w)
     MLSB_CUDA(cudaMalloc(&w->tileTotals, z.tileTotals));
     MLSB_CUDA(cudaMalloc(&w->tileList, z.tileList));
     MLSB_CUDA(cudaMalloc(&w->tables, z.tables));
+    if (z.wireBlob)
+    {
+        MLSB_CUDA(cudaMalloc(&w->compactVerts, z.compactVerts));
+        MLSB_CUDA(cudaMalloc(&w->compactVertsFlagged, z.compactVerts));
+        MLSB_CUDA(cudaMalloc(&w->wireBlob, z.wireBlob));
+        w->wireWords = z.wireBlob / sizeof(uint64_t);
+        w->compactReadback = true;
+    }
     MLSB_CUDA(cudaMemcpy(w->tables, &gTables.t, sizeof(Tables), cudaMemcpyHostToDevice));
     MLSB_TRY(ensureHostBlob(w, (size_t) 8 << 20));
     MLSB_CUDA(cudaMallocHost(&w->hostCounters, CTR_COUNT * sizeof(uint32_t)));
@@ -981,6 +1074,10 @@ void marchingFree(mlsb_worker *w)
     cudaFree(w->tileTotals);
     cudaFree(w->tileList);
     cudaFree(w->tables);
+    cudaFree(w->compactVerts);
+    cudaFree(w->compactVertsFlagged);
+    cudaFree(w->wireBlob);
+    cudaFreeHost(w->hostWire);
     cudaFreeHost(w->hostBlob);
     cudaFreeHost(w->hostCounters);
 }
@@ -1075,6 +1172,8 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
     L.weldedKeys = w->weldedKeys;
     L.weldedFlagged = w->weldedFlagged;
     L.weldedKeysFlagged = w->weldedKeysFlagged;
+    L.compact = w->compactVerts;          // null unless MLSB_READBACK=compact
+    L.compactFlagged = w->compactVertsFlagged;
     L.keyOffset = ((uint64_t) keyOffset[2] << (2 * kKeyAxisBits + 1)) | ((uint64_t) keyOffset[1] << (kKeyAxisBits + 1))
                   | ((uint64_t) keyOffset[0] << 1);
     L.scale = w->scale;
@@ -1130,10 +1229,20 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
         w->launches++;
     };
     const bool packed = !io.deviceSink && w->meshFilters.empty() && w->packReadback;
+    const bool compact = !io.deviceSink && w->meshFilters.empty() && w->compactReadback;
     if (packed)
         pack();
     else
     {
+        if (compact)
+        {
+            // the wire blob is gathered while the sizes travel: the host learns from CTR_PACKED whether to fetch it
+            ScopedStat st(w, "kernel.marching.readback.time");
+            compactMeshKernel<<<296, 256, 0, s>>>(w->marchCounters, w->weldedKeys, w->weldedKeysFlagged, w->compactVerts,
+                                                  w->compactVertsFlagged, w->indices, w->wireBlob, w->wireWords,
+                                                  (uint32_t) w->vertexSpace, (uint32_t) w->indexSpace);
+            w->launches++;
+        }
         ScopedStat st(w, "kernel.marching.readback.time", 0);
         MLSB_CUDA(cudaMemcpyAsync(w->hostCounters, w->marchCounters, CTR_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     }
@@ -1197,6 +1306,30 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
             MLSB_TRY(waitStream(w));
             MLSB_REQUIRE(w->hostCounters[CTR_PACKED], MLSB_ERR_STATE, "the mesh did not fit the grown read-back blob");
         }
+    }
+    else if (compact && hc[CTR_PACKED])
+    {
+        // one copy of 8 bytes per key, vertex and triangle; the worker thread expands it (unpack.cpp)
+        const size_t wireBytes = (size_t) (numExternal + sizes.numVertices + sizes.numTriangles) * sizeof(uint64_t);
+        if (wireBytes > w->hostWireBytes)
+        {
+            if (w->hostWire) MLSB_CUDA(cudaFreeHost(w->hostWire));
+            w->hostWire = nullptr;
+            w->hostWireBytes = 0;
+            const size_t want = std::max(wireBytes + wireBytes / 2, (size_t) 4 << 20);
+            MLSB_CUDA(cudaMallocHost(&w->hostWire, want));
+            w->hostWireBytes = want;
+        }
+        MLSB_CUDA(cudaMemcpyAsync(w->hostWire, w->wireBlob, wireBytes, cudaMemcpyDeviceToHost, s));
+        MLSB_TRY(waitStream(w));
+        WireParams wp;
+        wp.numVertices = sizes.numVertices;
+        wp.numTriangles = sizes.numTriangles;
+        wp.numInternalVertices = sizes.numInternalVertices;
+        wp.zFirst = zFirst;
+        for (int a = 0; a < 3; a++) wp.gridOffset[a] = keyOffset[a], wp.bias[a] = w->bias[a];
+        wp.scale = w->scale;
+        unpackWireMesh(static_cast<const uint64_t *>(w->hostWire), wp, w->hostBlob);
     }
     else
     {

@@ -1,8 +1,8 @@
 // Per-corner MLS field: MlsFunctor::enqueue (src/mls.cpp:101-135) and processCorners
 // (kernels/mls.cl:299-433), sphere and plane fits.
 //
-// One CTA per 8x8x8 block of corners, as in the reference, but 256 threads that each own TWO
-// corners sharing (y, z) (MLSB_MLS_SLOTS = 2):  dot3(p,p) = fma(px,px, fma(py,py, pz*pz))
+// One CTA per HALF of the reference's 8x8x8 block of corners (8 x 8 x 4, see MLSB_MLS_CTA_Z): 128 threads that each
+// own TWO corners sharing (y, z) (MLSB_MLS_SLOTS = 2):  dot3(p,p) = fma(px,px, fma(py,py, pz*pz))
 // (kernels/mls.cl:105-108), so the inner fma(py,py,pz*pz) — and py, pz themselves — are computed
 // once per splat per thread and reused by both corners, with bit-identical results.  Each warp owns
 // a 4x4x4 brick of the block, walks the block's command chain on its own, and pair-tests only the
@@ -36,8 +36,23 @@ namespace
 #define MLSB_MLS_MINBLOCKS 4
 #endif
 constexpr int kSlots = MLSB_MLS_SLOTS;                      // corners per thread (sharing y and z)
-constexpr int kThreads = 512 / kSlots;         // one CTA per 8x8x8 block of corners
+// Corners per CTA along y and z (x is always 8): the warps of a CTA walk the same chain but finish at different
+// times (a brick far from the surface keeps nothing), and a CTA holds its registers until its slowest warp is done —
+// smaller CTAs give the slots back sooner.  Measured on C2 (ms per 70-bin step alone / bench Msplats/s):
+// 8 x 8 x 8 = one octree block per CTA (8 warps) 19.40 / 365.8; 8 x 8 x 4 (4 warps, 8 CTAs per SM) 18.33 / 377.5;
+// 8 x 4 x 4 (2 warps) 20.07 / 352.9 — twice the CTAs to launch for the empty blocks, and each re-reads the chain head.
+#ifndef MLSB_MLS_CTA_Y
+#define MLSB_MLS_CTA_Y 8
+#endif
+#ifndef MLSB_MLS_CTA_Z
+#define MLSB_MLS_CTA_Z 4
+#endif
+constexpr int kCtaY = MLSB_MLS_CTA_Y, kCtaZ = MLSB_MLS_CTA_Z;
+static_assert((kCtaY == 4 || kCtaY == 8) && (kCtaZ == 4 || kCtaZ == 8), "a CTA is 8 x {4,8} x {4,8} corners");
 constexpr int kBrickX = 2 * kSlots;            // a warp covers a kBrickX x 4 x 4 brick
+constexpr int kFullThreads = 512 / kSlots;     // threads for a whole 8x8x8 block of corners
+constexpr int kThreads = kFullThreads * kCtaY * kCtaZ / 64;
+constexpr int kMinBlocks = MLSB_MLS_MINBLOCKS * (kFullThreads / kThreads);
 constexpr int kBatch = 32;           // splats fetched per warp per batch
 constexpr float kRadiusCutoff = 0.99f;   // kernels/mls.cl:36
 constexpr int kHitsCutoff = 4;           // kernels/mls.cl:37
@@ -147,7 +162,7 @@ template <int SHAPE> __device__ __forceinline__ float finish(const Accum &f, flo
 // PRE: the octree build left every splat's hit threshold in P.thresholds; otherwise (buffers bound by
 // mlsb_mls_set_buffers) the kernel derives it from 1/r^2 for every splat it keeps.
 template <int SHAPE, bool COUNT, bool PRE>
-__global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKernel(MlsParams P)
+__global__ void __launch_bounds__(kThreads, kMinBlocks) processCornersKernel(MlsParams P)
 {
     // per-warp staging buffers for the splats that survive the cull
     __shared__ float4 sPosT[kThreads / 32][kBatch];    // x, y, z, hit threshold on |p|^2
@@ -158,17 +173,18 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
     const uint32_t lane = tid & 31, quad = tid >> 5;
     // corner layout inside the block: the warp owns a kBrickX x 4 x 4 brick; a thread owns the
     // corners x = lx + 2j (j = slot), with y and z fixed
-    constexpr int kBricksX = 8 / kBrickX;
-    const int qx = kBrickX * (int) (quad % kBricksX), qy = 4 * (int) ((quad / kBricksX) & 1), qz = 4 * (int) (quad / (2 * kBricksX));
+    constexpr int kBricksX = 8 / kBrickX, kBricksY = kCtaY / 4;
+    const int qx = kBrickX * (int) (quad % kBricksX), qy = 4 * (int) ((quad / kBricksX) % kBricksY), qz = 4 * (int) (quad / (kBricksY * kBricksX));
     const int lx = qx + (int) (lane & 1);
     const int ly = qy + (int) ((lane >> 1) & 3);
     const int lz = qz + (int) ((lane >> 3) & 3);
-    const int wx = blockIdx.x * kMlsWgs, wy = blockIdx.y * kMlsWgs, wz = blockIdx.z * kMlsWgs + (int) P.zFirst;
+    const int wx = blockIdx.x * kMlsWgs, wy = blockIdx.y * kCtaY, wz = blockIdx.z * kCtaZ + (int) P.zFirst;
 
+    // (the code of any corner of the 8x8x8 block: the low three bits of each coordinate are shifted out)
     const uint32_t code = (spread3(wx) | (spread3(wy) << 1) | (spread3(wz) << 2)) >> P.startShift;
     int32_t pos = P.start[code];
     if (P.blockActive != nullptr && tid == 0)
-        P.blockActive[((size_t) (wz >> 3) * P.activeDimY + blockIdx.y) * P.activeDimX + blockIdx.x] = pos >= 0;
+        P.blockActive[((size_t) (wz >> 3) * P.activeDimY + (wy >> 3)) * P.activeDimX + blockIdx.x] = pos >= 0;
 
     float out[kSlots];
 #pragma unroll
@@ -411,6 +427,9 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersKe
 // the block's staging buffer.  Staging is double-buffered: two barriers per 256 chain entries, and the
 // next batch's global loads are in flight while the current one is processed.  Per-corner
 // accumulation order is still the chain order: the field is bit-identical.
+namespace blockcull
+{
+constexpr int kThreads = kFullThreads;   // this kernel always takes a whole 8x8x8 block
 constexpr int kStage = kThreads;   // chain entries per block batch
 template <int SHAPE, bool COUNT, bool PRE>
 __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersBlockCullKernel(MlsParams P)
@@ -641,6 +660,8 @@ __global__ void __launch_bounds__(kThreads, MLSB_MLS_MINBLOCKS) processCornersBl
     for (int j = 0; j < kSlots; j++) dst[2 * j] = out[j];
 }
 
+}  // namespace blockcull
+
 // Dependent-free FFMA stream: 8 independent accumulators per thread, every issue slot an FFMA.
 __global__ void __launch_bounds__(256) fp32PeakKernel(float *out, float a, float b, int iters)
 {
@@ -735,7 +756,9 @@ int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &
     P.work = w->mlsWork;
     P.blockActive = recordActive ? w->blockActive : nullptr;
     P.activeDimX = P.activeDimY = roundUp(w->fieldDim / kMlsWgs, 4u);   // rows are read as 32-bit words
-    dim3 grid(width / kMlsWgs, height / kMlsWgs, divUp(sw.zLast - sw.zFirst + 1, (uint32_t) kMlsWgs));
+    const uint32_t blocksZ = divUp(sw.zLast - sw.zFirst + 1, (uint32_t) kMlsWgs);
+    dim3 grid(width / kMlsWgs, height / kCtaY, blocksZ * (kMlsWgs / kCtaZ));
+    dim3 fullGrid(width / kMlsWgs, height / kMlsWgs, blocksZ);
     ScopedStat st(w, "kernel.mls.processCorners.time", 1, 1);
     const bool count = w->countWork;
     cudaStream_t s = w->stream;
@@ -755,10 +778,10 @@ int mlsCorners(mlsb_worker *w, float *field, uint32_t pitch, const mlsb_swathe &
     do {                                                                                                    \
         if (blockCull)                                                                                      \
         {                                                                                                   \
-            if (count && pre) processCornersBlockCullKernel<SHAPE, true, true><<<grid, kThreads, 0, s>>>(P);    \
-            else if (count) processCornersBlockCullKernel<SHAPE, true, false><<<grid, kThreads, 0, s>>>(P);     \
-            else if (pre) processCornersBlockCullKernel<SHAPE, false, true><<<grid, kThreads, 0, s>>>(P);       \
-            else processCornersBlockCullKernel<SHAPE, false, false><<<grid, kThreads, 0, s>>>(P);               \
+            if (count && pre) blockcull::processCornersBlockCullKernel<SHAPE, true, true><<<fullGrid, kFullThreads, 0, s>>>(P);    \
+            else if (count) blockcull::processCornersBlockCullKernel<SHAPE, true, false><<<fullGrid, kFullThreads, 0, s>>>(P);     \
+            else if (pre) blockcull::processCornersBlockCullKernel<SHAPE, false, true><<<fullGrid, kFullThreads, 0, s>>>(P);       \
+            else blockcull::processCornersBlockCullKernel<SHAPE, false, false><<<fullGrid, kFullThreads, 0, s>>>(P);               \
         }                                                                                                   \
         else if (count && pre) processCornersKernel<SHAPE, true, true><<<grid, kThreads, 0, s>>>(P);        \
         else if (count) processCornersKernel<SHAPE, true, false><<<grid, kThreads, 0, s>>>(P);              \

@@ -487,7 +487,12 @@ __global__ void __launch_bounds__(256) writeEntriesBucketedKernel(uint32_t *__re
 
 constexpr int kBucketThreads = 1024, kBucketWarps = kBucketThreads / 32;
 constexpr int kBucketChunk = 8 * kBucketThreads;
-__global__ void __launch_bounds__(kBucketThreads) bucketSortEmitKernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ ids,
+#ifdef MLSB_BUCKET_MINBLOCKS
+__global__ void __launch_bounds__(kBucketThreads, MLSB_BUCKET_MINBLOCKS) bucketSortEmitKernel(
+#else
+__global__ void __launch_bounds__(kBucketThreads) bucketSortEmitKernel(
+#endif
+    const uint32_t *__restrict__ keys, const uint32_t *__restrict__ ids,
                                                             const uint32_t *__restrict__ bucketSizes, uint32_t numStart,
                                                             const int32_t *__restrict__ start, int32_t *__restrict__ commands)
 {

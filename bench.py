@@ -192,6 +192,12 @@ class Runner:
     def all_workers(self):
         return self.workers + [self.single]
 
+    def blob_bytes_since_reset(self):
+        """HostKeyMesh bytes of every block shipped since the workers' statistics were reset (for the wire / blob ratio)."""
+        v = sum(w.marching_work()[4] for w in self.all_workers())       # welded vertices
+        i = sum(w.marching_work()[3] for w in self.all_workers())       # indices
+        return 12 * v + 4 * i    # external keys (8 bytes each, < 1 % of a block) are left out on both sides of the ratio
+
     def stat_sum(self, names):
         tot, cnt = 0.0, 0
         for w in self.all_workers():
@@ -375,6 +381,7 @@ def workload_config(wl, args):
     return {"workload": name,
             "splats": wl["num_splats"], "bins": len(wl["bins"]), "splat_instances": int(len(wl["splats"])),
             "device_threads": args.threads, "bin_order": args.order,
+            "readback": os.environ.get("MLSB_READBACK") or "copy",
             "l2": "inputs larger than L2: %.0f MB of splats and a 64 MiB field per bin cycle through a 126 MB L2"
                   % (len(wl["splats"]) * 32 / 1e6)}
 
@@ -491,6 +498,14 @@ def main():
     runner.step(True)   # warm the host path
     ms_e2e, wall_e2e, _ = timed(True, args.steps, profile=False)
     d2h = runner.mesh_bytes // args.steps
+    readback = os.environ.get("MLSB_READBACK") or "copy"
+    if readback == "compact":
+        # what crossed PCIe is the wire blob (8 bytes per key, vertex and triangle), not the HostKeyMesh blob the
+        # sink receives: the workers count it (statistic readback.bytes); same blocks in every pass, so the share
+        # of the e2e steps is the share of all blocks since the statistics were reset
+        wire, blocks = runner.stat_sum(["readback.bytes"])
+        if blocks:
+            d2h = int(d2h * wire / max(1.0, float(runner.blob_bytes_since_reset())))
     h2d = int(len(wl["splats"]) * 32)
     if world > 1 and not args.replicas:
         t = torch.tensor([float(d2h), float(h2d)], device="cuda", dtype=torch.float64)

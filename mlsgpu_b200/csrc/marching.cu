@@ -1322,6 +1322,7 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
         }
         MLSB_CUDA(cudaMemcpyAsync(w->hostWire, w->wireBlob, wireBytes, cudaMemcpyDeviceToHost, s));
         MLSB_TRY(waitStream(w));
+        addSample(w, "readback.bytes", (double) wireBytes);
         WireParams wp;
         wp.numVertices = sizes.numVertices;
         wp.numTriangles = sizes.numTriangles;
@@ -1351,6 +1352,8 @@ int shipBlock(mlsb_worker *w, bool useActive, uint32_t pitch, uint32_t zStride, 
             MLSB_CUDA(cudaMemcpyAsync(hVerts, w->welded, numUnflagged * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
         MLSB_TRY(waitStream(w));
     }
+    // what crossed PCIe for this block (statistic readback.bytes): the blob, unless the compact wire format was used
+    if (!(compact && hc[CTR_PACKED])) addSample(w, "readback.bytes", (double) mlsb_mesh_host_bytes(&sizes));
     const uint8_t *blob = static_cast<const uint8_t *>(w->hostBlob);
     if (io.sink) io.sink(&sizes, blob, io.user);
     return MLSB_OK;

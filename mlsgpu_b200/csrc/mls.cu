@@ -52,7 +52,11 @@ static_assert((kCtaY == 4 || kCtaY == 8) && (kCtaZ == 4 || kCtaZ == 8), "a CTA i
 constexpr int kBrickX = 2 * kSlots;            // a warp covers a kBrickX x 4 x 4 brick
 constexpr int kFullThreads = 512 / kSlots;     // threads for a whole 8x8x8 block of corners
 constexpr int kThreads = kFullThreads * kCtaY * kCtaZ / 64;
+#ifdef MLSB_MLS_CTAS   // A/B builds: CTAs per SM at the actual CTA size
+constexpr int kMinBlocks = MLSB_MLS_CTAS;
+#else
 constexpr int kMinBlocks = MLSB_MLS_MINBLOCKS * (kFullThreads / kThreads);
+#endif
 constexpr int kBatch = 32;           // splats fetched per warp per batch
 constexpr float kRadiusCutoff = 0.99f;   // kernels/mls.cl:36
 constexpr int kHitsCutoff = 4;           // kernels/mls.cl:37

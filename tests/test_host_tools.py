@@ -524,6 +524,13 @@ def test_statistics_registry_known_answers():
     assert r.returncode == 0 and r.stdout.strip() == "statistics_test: ok", r.stdout + r.stderr
 
 
+def test_compact_readback_unpack_known_answers():
+    """csrc/unpack.cpp (host half of MLSB_READBACK=compact) against a scalar restatement of the device's vertex
+    arithmetic on random wire blobs: bit for bit, subnormal / -0 / huge t included, nothing written past the blob."""
+    r = subprocess.run([build("unpack_test")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("unpack_test: ok"), r.stdout + r.stderr
+
+
 def test_parse_statistics_formats():
     text = ("mlsgpu version: x\ncounter: 100\nstat0: [0]\nstat1: 1 : 1 [1]\nstat3: 12 : 4 +/- 2 [3]\n"
             "splats/s end-to-end: 2.5e+07 : 2.5e+07 [1]\n")

@@ -133,6 +133,20 @@ static int validateConfig(const mlsb_worker_config *c)
     return MLSB_OK;
 }
 
+// Copy of device-resident splats into a worker's buffer (mlsb_splats_upload_async): 16 bytes per thread and
+// iteration, four independent loads in flight.
+__global__ void __launch_bounds__(256) copyWordsKernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint32_t words)
+{
+    const uint32_t base = blockIdx.x * 1024 + threadIdx.x;
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (base + k * 256 < words) v[k] = src[base + k * 256];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (base + k * 256 < words) dst[base + k * 256] = v[k];
+}
+
 }  // namespace mlsb
 
 using namespace mlsb;
@@ -332,8 +346,26 @@ int mlsb_splats_upload_async(mlsb_worker *w, const mlsb_splat *host, uint32_t ds
     MLSB_REQUIRE((uint64_t) dstFirst + n <= w->cfg.maxSplats, MLSB_ERR_LENGTH, "more splats than the worker's buffer holds");
     MLSB_CUDA(cudaSetDevice(w->device));
     if (n)
-        MLSB_CUDA(cudaMemcpyAsync(w->splats + dstFirst, host, (size_t) n * sizeof(mlsb_splat), cudaMemcpyDefault,
-                                  w->copyStream));
+    {
+        // A source that already lives in device memory is copied by a kernel: a device-to-device cudaMemcpyAsync
+        // may be queued on the copy engine that is busy with other workers' mesh read-backs at PCIe speed (the
+        // HBM-resident bench pass was SLOWER than the pass from pinned host memory: 33.2 against 26.8 ms per step
+        // on two GPUs), while the host-to-device engine is otherwise idle.
+        cudaPointerAttributes attr;
+        const bool onDevice = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+        if (!onDevice) (void) cudaGetLastError();   // unregistered host memory may report an error: not one of ours
+        if (onDevice && (reinterpret_cast<uintptr_t>(host) & 15) == 0)
+        {
+            const uint32_t words = n * (uint32_t) (sizeof(mlsb_splat) / sizeof(uint4));
+            copyWordsKernel<<<(words + 1023) / 1024, 256, 0, w->copyStream>>>(reinterpret_cast<uint4 *>(w->splats + dstFirst),
+                                                                              reinterpret_cast<const uint4 *>(host), words);
+            w->launches++;
+            MLSB_CUDA(cudaGetLastError());
+        }
+        else
+            MLSB_CUDA(cudaMemcpyAsync(w->splats + dstFirst, host, (size_t) n * sizeof(mlsb_splat), cudaMemcpyDefault,
+                                      w->copyStream));
+    }
     MLSB_CUDA(cudaEventRecord(w->copyEvent, w->copyStream));
     w->copyPending = true;
     return MLSB_OK;

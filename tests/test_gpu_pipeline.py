@@ -153,3 +153,26 @@ def test_c1_full_size_properties():
     assert np.abs(np.linalg.norm(v.astype(np.float64), axis=1) - 1.0).max() < 0.01
     assert len(v) > 100_000 and abs(len(t) - 2 * len(v)) < 0.01 * len(v)   # F ~ 2V: closed up to a few small holes
     assert is_manifold(len(v), t) == ""
+
+
+def test_upload_from_device_memory():
+    """mlsb_splats_upload_async with a source in DEVICE memory (copied by a kernel, not by the copy engine): the
+    worker's buffer holds the same bytes as after an upload from the host, at an offset on both sides, for a
+    16-byte-aligned source and for one that is not (the cudaMemcpyAsync fall-back)."""
+    import mlsgpu_b200 as m
+    from mlsgpu_b200 import capi, host
+    s = host.sphere_splats(5003, seed=3, radius=0.02, noise=0.004)
+    dev = capi.DeviceBuffer.from_array(s)
+    raw = np.concatenate([np.zeros(4, np.uint8), s.view(np.uint8)])        # the splats start 4 bytes into this one
+    odd = capi.DeviceBuffer.from_array(raw)
+    with m.Worker(max_splats=6000, max_cells=31) as w:
+        launches = w.launch_count
+        w.upload_splats_from_device(dev, 7, 4990, dst_first=11)
+        assert w.launch_count == launches + 1
+        np.testing.assert_array_equal(w.download_splats(11, 4990).view(np.uint8), s[7:4997].view(np.uint8))
+        from mlsgpu_b200.capi import lib, _check
+        _check(lib().mlsb_splats_upload_async(w.h, odd.ptr.value + 4, 0, len(s)))
+        assert w.launch_count == launches + 1                               # not 16-byte aligned: the copy engine took it
+        np.testing.assert_array_equal(w.download_splats(0, len(s)).view(np.uint8), s.view(np.uint8))
+    dev.free()
+    odd.free()

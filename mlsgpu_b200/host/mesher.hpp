@@ -9,9 +9,13 @@
 //    vertex (updateClumpKeyMap, :280-306);
 //  * at write time components (root clumps) with fewer than floor(fit-prune x total vertices)
 //    vertices are dropped and the rest are compacted (getStatistics :491-513, write :763-852).
-// The reference streams blocks through temporary files to bound memory; this version keeps the
-// mesh in host memory, one piece per block, and only the seam bookkeeping (external vertices) is
-// serialised: the per-block work runs concurrently on the device workers' threads.
+// The reference streams blocks through temporary files to bound memory.  Here the mesh stays in host
+// memory by default, one piece per block, and only the seam bookkeeping (external vertices) is
+// serialised: the per-block work runs concurrently on the device workers' threads.  With
+// enableSpill() (--tmp-dir) the mesher is out of core like the reference's (src/mesher.cpp:343-445):
+// a completed block's vertices, clump labels and triangles go to ONE temporary file at once (pwrite
+// from the worker's thread), host memory keeps the key maps, the clumps and a few counters per block,
+// and stream() prunes, compacts and writes the output file by reading the blocks back in parallel.
 //
 // --split (src/mesher.h:169-179, testChunk in test/test_mesher.cpp:924-993): every block belongs
 // to an output chunk; vertices are welded within a chunk only (a vertex on a chunk boundary is
@@ -21,6 +25,8 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <cerrno>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -32,6 +38,9 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+
+#include <fcntl.h>
+#include <unistd.h>
 
 #include "../../include/mlsb200.h"
 
@@ -47,6 +56,45 @@ public:
 
     /// split = true: blocks of different chunks share components but not vertices.
     explicit Mesher(bool split = false) : split(split) {}
+    ~Mesher()
+    {
+        if (spillFd >= 0) ::close(spillFd);
+    }
+    Mesher(const Mesher &) = delete;
+    Mesher &operator=(const Mesher &) = delete;
+    Mesher(Mesher &&other) noexcept { *this = std::move(other); }
+    Mesher &operator=(Mesher &&other) noexcept
+    {
+        if (this == &other) return *this;
+        if (spillFd >= 0) ::close(spillFd);
+        split = other.split;
+        chunkIndex = std::move(other.chunkIndex);
+        chunks = std::move(other.chunks);
+        clumps = std::move(other.clumps);
+        globalKeyClump = std::move(other.globalKeyClump);
+        totalVertices = other.totalVertices;
+        totalTriangles = other.totalTriangles;
+        spillFd = other.spillFd;
+        spillSize.store(other.spillSize.load());
+        other.spillFd = -1;
+        return *this;
+    }
+
+    /// Out-of-core mode (--tmp-dir): from now on spill() moves completed blocks into an unnamed
+    /// temporary file in `dir`.  Call before the first block.
+    void enableSpill(const std::string &dir)
+    {
+        if (totalVertices != 0 || spillFd >= 0) throw std::logic_error("enableSpill() comes before the first block");
+        std::string path = (dir.empty() ? std::string(".") : dir) + "/mlsgpu-mesher-XXXXXX";
+        std::vector<char> name(path.begin(), path.end());
+        name.push_back('\0');
+        spillFd = ::mkstemp(name.data());
+        if (spillFd < 0) throw std::runtime_error("cannot create a temporary file in " + dir + ": " + std::strerror(errno));
+        ::unlink(name.data());   // the file lives as long as the descriptor
+    }
+    bool spilling() const { return spillFd >= 0; }
+    /// Bytes written to the temporary file so far.
+    std::uint64_t spilledBytes() const { return spillSize.load(); }
 
     /// One shipped-out block (HostKeyMesh layout, src/mesh.cpp:51-60) on its way into the mesh.
     /// The blob pointers are only used by prepare/commit/complete, i.e. inside the sink call.
@@ -68,6 +116,12 @@ public:
         std::vector<vertex_type> vertices;
         std::vector<std::uint32_t> vertexClump;
         std::vector<triangle_type> triangles;
+        // per local clump: kept vertices (above) and triangles of this block — what pruning needs to
+        // size the output without looking at the arrays
+        std::vector<std::uint32_t> clumpKept, clumpTriangles;
+        // out-of-core mode: where [vertices][vertexClump][triangles] went, and how many there are
+        std::int64_t spillOffset = -1;
+        std::size_t numKept = 0;
     };
 
     /// Step 1, thread-safe: local components and a private copy of the internal vertices.
@@ -111,6 +165,10 @@ public:
         b.vertices.assign(b.verts, b.verts + ni);
         b.vertexClump.reserve(nv);
         b.vertexClump.assign(b.clumpOfLocal.begin(), b.clumpOfLocal.begin() + ni);
+        b.clumpKept.assign(b.clumpVertices.size(), 0);
+        b.clumpTriangles.assign(b.clumpVertices.size(), 0);
+        for (std::size_t i = 0; i < ni; i++) b.clumpKept[b.clumpOfLocal[i]]++;
+        for (std::size_t i = 0; i < nt; i++) b.clumpTriangles[b.clumpOfLocal[b.tris[i][0]]]++;   // a triangle lies in one clump
         return block;
     }
 
@@ -151,6 +209,7 @@ public:
             {
                 b.vertices.push_back(b.verts[i]);
                 b.vertexClump.push_back(b.clumpOfLocal[i]);
+                b.clumpKept[b.clumpOfLocal[i]]++;
                 if (split)
                 {
                     // new to this chunk's file, but another chunk may hold the same vertex
@@ -167,6 +226,7 @@ public:
             }
             b.remapExternal[i - ni] = added.first->second.vertex;
         }
+        b.numKept = b.vertices.size();
         chunk.totalVertices += b.vertices.size();
         chunk.totalTriangles += b.nt;
         totalVertices += b.vertices.size();
@@ -193,8 +253,29 @@ public:
         b.tris = nullptr;
     }
 
-    /// All three steps, for a single-threaded consumer.
-    void add(const mlsb_mesh_sizes &sizes, const void *blob) { complete(commit(prepare(sizes, blob))); }
+    /// Step 4, out-of-core mode only, thread-safe: the completed block's arrays move to the temporary
+    /// file (one reservation of the file's tail, then positioned writes).
+    void spill(Block &b)
+    {
+        if (spillFd < 0) return;
+        const std::size_t bytesV = b.vertices.size() * sizeof(vertex_type), bytesC = b.vertexClump.size() * sizeof(std::uint32_t);
+        const std::size_t bytesT = b.triangles.size() * sizeof(triangle_type);
+        b.spillOffset = (std::int64_t) spillSize.fetch_add(bytesV + bytesC + bytesT);
+        writeAt(b.vertices.data(), bytesV, b.spillOffset);
+        writeAt(b.vertexClump.data(), bytesC, b.spillOffset + (std::int64_t) bytesV);
+        writeAt(b.triangles.data(), bytesT, b.spillOffset + (std::int64_t) (bytesV + bytesC));
+        std::vector<vertex_type>().swap(b.vertices);
+        std::vector<std::uint32_t>().swap(b.vertexClump);
+        std::vector<triangle_type>().swap(b.triangles);
+    }
+
+    /// All steps, for a single-threaded consumer.
+    void add(const mlsb_mesh_sizes &sizes, const void *blob)
+    {
+        Block &b = commit(prepare(sizes, blob));
+        complete(b);
+        spill(b);
+    }
 
     std::size_t numVertices() const { return totalVertices; }
     std::size_t numTriangles() const { return totalTriangles; }
@@ -205,6 +286,7 @@ public:
     /// can run later, possibly with another --fit-prune.  Call after the last block has completed.
     void save(std::ostream &out) const
     {
+        if (spilling()) throw std::logic_error("--checkpoint keeps the mesh in one file already: not with --tmp-dir");
         out.write(checkpointMagic(), 8);
         put<std::uint64_t>(out, split);
         put<std::uint64_t>(out, totalVertices);
@@ -269,6 +351,7 @@ public:
                 getVector(in, b->vertexClump);
                 getVector(in, b->triangles);
                 b->nt = b->triangles.size();
+                b->numKept = b->vertices.size();
             }
         }
         if (!in) throw std::runtime_error("truncated mesher checkpoint");
@@ -303,6 +386,7 @@ public:
     /// (fraction of all welded vertices, counted over the whole mesh).
     std::vector<Result> finishChunks(double pruneThreshold)
     {
+        if (spilling()) throw std::logic_error("an out-of-core mesher is finished with stream()");
         Result counts;
         std::vector<char> keepClump;
         countComponents(pruneThreshold, counts, &keepClump);
@@ -317,8 +401,157 @@ public:
         return out;
     }
 
+    /// Prune, compact and WRITE, chunk by chunk, without holding a chunk in memory (works in core as
+    /// well).  `open(chunk, numVertices, numTriangles)` returns a writer with thread-safe
+    /// `vertices(first, data, count)` and `triangles(first, data, count)` (PlyStreamWriter), or a null
+    /// pointer to skip the chunk (--split writes only chunks with triangles); the Results carry the
+    /// counts only.  OOCMesher::write, src/mesher.cpp:763-852.
+    template <typename Open>
+    std::vector<Result> stream(double pruneThreshold, Open open)
+    {
+        Result counts;
+        std::vector<char> keepClump;
+        countComponents(pruneThreshold, counts, &keepClump);
+        const bool prune = counts.keptComponents != counts.totalComponents;
+        std::vector<Result> out;
+        for (const auto &entry : chunkIndex)
+        {
+            Result r = counts;
+            r.chunk = entry.first;
+            Chunk &chunk = *chunks[entry.second];
+            const std::int64_t numBlocks = (std::int64_t) chunk.blocks.size();
+            // kept vertices and triangles per block, from the per-clump counters
+            std::vector<std::size_t> firstV(chunk.blocks.size() + 1, 0), firstT(chunk.blocks.size() + 1, 0);
+            for (std::int64_t i = 0; i < numBlocks; i++)
+            {
+                const Block &b = *chunk.blocks[i];
+                std::size_t kv = b.numKept, kt = b.nt;
+                if (prune)
+                {
+                    kv = kt = 0;
+                    for (std::size_t c = 0; c < b.clumpKept.size(); c++)
+                        if (keepClump[b.firstClump + c]) kv += b.clumpKept[c], kt += b.clumpTriangles[c];
+                }
+                firstV[i + 1] = firstV[i] + kv;
+                firstT[i + 1] = firstT[i] + kt;
+            }
+            r.numVertices = firstV.back();
+            r.numTriangles = firstT.back();
+            auto writer = open(r.chunk, r.numVertices, r.numTriangles);
+            if (writer)
+            {
+                std::vector<std::uint32_t> newIndex;
+                if (prune) newIndex.assign(chunk.totalVertices, UINT32_MAX);
+                std::string failure;
+#pragma omp parallel
+                {
+                    std::vector<vertex_type> verts;
+                    std::vector<std::uint32_t> labels;
+                    std::vector<triangle_type> tris;
+                    try
+                    {
+#pragma omp for schedule(dynamic, 1)
+                        for (std::int64_t i = 0; i < numBlocks; i++)
+                        {
+                            const Block &b = *chunk.blocks[i];
+                            const vertex_type *v = fetch(b, 0, b.numKept, b.vertices, verts);
+                            if (!prune)
+                            {
+                                writer->vertices(firstV[i], v, b.numKept);
+                                continue;
+                            }
+                            const std::uint32_t *l = fetch(b, b.numKept * sizeof(vertex_type), b.numKept, b.vertexClump, labels);
+                            std::size_t n = 0;
+                            if (v != verts.data())
+                            {
+                                verts.assign(v, v + b.numKept);   // in core: compact a copy, the block stays intact
+                                v = verts.data();
+                            }
+                            for (std::size_t k = 0; k < b.numKept; k++)
+                                if (keepClump[b.firstClump + l[k]])
+                                {
+                                    newIndex[b.firstVertex + k] = (std::uint32_t) (firstV[i] + n);
+                                    verts[n++] = v[k];
+                                }
+                            writer->vertices(firstV[i], verts.data(), n);
+                        }
+                        // (the implicit barrier: every newIndex is final before a triangle reads it)
+#pragma omp for schedule(dynamic, 1)
+                        for (std::int64_t i = 0; i < numBlocks; i++)
+                        {
+                            const Block &b = *chunk.blocks[i];
+                            const triangle_type *t = fetch(b, b.numKept * (sizeof(vertex_type) + sizeof(std::uint32_t)), b.nt, b.triangles, tris);
+                            if (!prune)
+                            {
+                                writer->triangles(firstT[i], t, b.nt);
+                                continue;
+                            }
+                            if (t != tris.data())
+                            {
+                                tris.assign(t, t + b.nt);
+                                t = tris.data();
+                            }
+                            std::size_t n = 0;
+                            for (std::size_t k = 0; k < b.nt; k++)
+                                if (newIndex[t[k][0]] != UINT32_MAX)   // a triangle's vertices share one component
+                                    tris[n++] = triangle_type{{newIndex[t[k][0]], newIndex[t[k][1]], newIndex[t[k][2]]}};
+                            writer->triangles(firstT[i], tris.data(), n);
+                        }
+                    }
+                    catch (const std::exception &e)
+                    {
+#pragma omp critical
+                        if (failure.empty()) failure = e.what();
+                    }
+                }
+                if (!failure.empty()) throw std::runtime_error(failure);
+                writer->close();
+            }
+            out.push_back(std::move(r));
+        }
+        if (out.empty()) out.push_back(counts);
+        return out;
+    }
+
 private:
     static const char *checkpointMagic() { return "MLSBCKP1"; }
+    // positioned I/O on the temporary file
+    void writeAt(const void *data, std::size_t bytes, std::int64_t offset) const
+    {
+        const char *p = static_cast<const char *>(data);
+        while (bytes > 0)
+        {
+            const ssize_t n = ::pwrite(spillFd, p, bytes, (off_t) offset);
+            if (n < 0 && errno == EINTR) continue;
+            if (n <= 0) throw std::runtime_error(std::string("error writing the mesher's temporary file: ") + std::strerror(errno));
+            p += n;
+            offset += n;
+            bytes -= (std::size_t) n;
+        }
+    }
+    void readAt(void *data, std::size_t bytes, std::int64_t offset) const
+    {
+        char *p = static_cast<char *>(data);
+        while (bytes > 0)
+        {
+            const ssize_t n = ::pread(spillFd, p, bytes, (off_t) offset);
+            if (n < 0 && errno == EINTR) continue;
+            if (n <= 0) throw std::runtime_error("error reading the mesher's temporary file");
+            p += n;
+            offset += n;
+            bytes -= (std::size_t) n;
+        }
+    }
+    /// `count` elements of a block's array: the array itself in core, else read from the temporary
+    /// file (at `skip` bytes into the block's record) into `scratch`.
+    template <typename T>
+    const T *fetch(const Block &b, std::size_t skip, std::size_t count, const std::vector<T> &inCore, std::vector<T> &scratch) const
+    {
+        if (b.spillOffset < 0) return inCore.data();
+        scratch.resize(count);
+        if (count) readAt(scratch.data(), count * sizeof(T), b.spillOffset + (std::int64_t) skip);
+        return scratch.data();
+    }
     template <typename T> static void put(std::ostream &out, T value) { out.write(reinterpret_cast<const char *>(&value), sizeof(T)); }
     template <typename T> static T get(std::istream &in)
     {
@@ -477,6 +710,8 @@ private:
     std::vector<Clump> clumps;
     std::unordered_map<std::uint64_t, std::uint32_t> globalKeyClump;   // split only: key -> clump where first seen
     std::size_t totalVertices = 0, totalTriangles = 0;
+    int spillFd = -1;                          // out-of-core mode: the temporary file
+    std::atomic<std::uint64_t> spillSize{0};   // its length (blocks reserve their place with a fetch_add)
 };
 
 /// ChunkNamer (src/mesher.cpp:88-96): base_XXXX_YYYY_ZZZZ.ply, at least four digits per coordinate.

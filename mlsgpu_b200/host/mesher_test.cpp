@@ -46,9 +46,16 @@ int main(int argc, char **argv)
     const bool split = numBlocks > 0 && std::fread(chunkIds.data(), 12, numBlocks, f) == numBlocks;
     std::fclose(f);
     if (split) mesher = mlsb::Mesher(true);
+    // MLSB_MESHER_TMP=dir: the out-of-core mesher (blocks spilled to a temporary file there, output streamed)
+    const char *tmpDir = std::getenv("MLSB_MESHER_TMP");
+    if (tmpDir && argc != 6) mesher.enableSpill(tmpDir);
     if (threads <= 1)
         for (std::uint64_t b = 0; b < numBlocks; b++)
-            mlsb::Mesher::complete(mesher.commit(mlsb::Mesher::prepare(sizes[b], blobs[b].data()), chunkIds[b]));
+        {
+            mlsb::Mesher::Block &block = mesher.commit(mlsb::Mesher::prepare(sizes[b], blobs[b].data()), chunkIds[b]);
+            mlsb::Mesher::complete(block);
+            mesher.spill(block);
+        }
     else
     {
         std::mutex mutex;
@@ -64,6 +71,7 @@ int main(int argc, char **argv)
                         block = &mesher.commit(std::move(prepared), chunkIds[b]);
                     }
                     mlsb::Mesher::complete(*block);
+                    mesher.spill(*block);
                 }
             });
         for (std::thread &t : pool) t.join();
@@ -82,6 +90,26 @@ int main(int argc, char **argv)
     }
     mlsb::PlyWriter writer;
     writer.addComment("mesher_test");
+    if (mesher.spilling())
+    {
+        const std::size_t nv = mesher.numVertices(), nt = mesher.numTriangles();
+        std::vector<std::string> names;
+        const std::vector<mlsb::Mesher::Result> all = mesher.stream(std::atof(argv[2]),
+            [&](const mlsb::Mesher::chunk_type &chunk, std::size_t numV, std::size_t numT) {
+                if (split && numT == 0) return std::unique_ptr<mlsb::PlyStreamWriter>();
+                names.push_back(split ? mlsb::chunkName(argv[3], chunk) : std::string(argv[3]));
+                return writer.openStream(names.back(), numV, numT);
+            });
+        if (!split && names.empty()) writer.write(argv[3], std::vector<mlsb::PlyWriter::vertex_type>(), std::vector<mlsb::PlyWriter::triangle_type>());
+        std::cout << nv << " " << nt << " " << all[0].totalComponents << " " << all[0].keptComponents << " " << all[0].thresholdVertices << "\n";
+        if (split)
+        {
+            std::size_t k = 0;
+            for (const mlsb::Mesher::Result &r : all)
+                if (r.numTriangles != 0) std::cout << names[k++] << " " << r.numVertices << " " << r.numTriangles << "\n";
+        }
+        return 0;
+    }
     if (!split)
     {
         mlsb::Mesher::Result r = mesher.finish(std::atof(argv[2]));

@@ -5,8 +5,10 @@
 //   marching on the GPU) -> host mesher (seam weld, prune) -> PLY
 //
 // Option names, defaults and validation follow the reference; options that configure parts of the
-// reference that do not exist here (out-of-core readers/writers, temporary files, checkpoints,
-// MPI) are accepted and ignored so that existing command lines keep working.
+// reference that do not exist here (its reader / writer classes, reorder and gather buffers, MPI) are
+// accepted and ignored so that existing command lines keep working.  Inputs larger than
+// --mem-load-splats are streamed (stream.hpp); with --tmp-dir the mesher is out of core as well
+// (mesher.hpp), so that neither the input nor the output has to fit in host memory.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -14,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <csignal>
+#include <sys/resource.h>
 #include <dirent.h>
 #include <execinfo.h>
 #include <fstream>
@@ -60,6 +63,7 @@ struct Options
     // is sized for the hosts B200s sit in.  Pass the reference's value to get its behaviour.
     std::uint64_t memLoadSplats = 16ull << 30;
     std::uint64_t memMesh = 512ull << 20;
+    std::string tmpDir;              // not empty: the mesher spills finished blocks to a temporary file there
     std::vector<int> devices;        // CUDA ordinals; empty = every device found (the reference's default, src/clh.cpp:180-240)
     bool quiet = false, statistics = false, statisticsCL = false, split = false;
     std::uint64_t splitSize = 100ull << 20;   // src/mlsgpu_core.cpp:162
@@ -89,7 +93,9 @@ void usage()
         "  --mem-bucket-splats SIZE    device memory for splats of one bin, K/M/G suffix (64M)\n"
         "  --mem-load-splats SIZE      host memory for splats loaded at once; larger inputs are streamed from\n"
         "                              disk in several passes (16G; the reference's default is 256M)\n"
-        "                              NOTE: the output mesh is always held in host memory until it is written\n"
+        "  --tmp-dir DIR               keep the mesh out of core: finished blocks go to a temporary file in DIR and\n"
+        "                              the output is streamed from it (without it the mesh is held in host memory\n"
+        "                              until it is written: ~38 bytes per output vertex)\n"
         "  --mem-mesh SIZE             device memory for raw mesh data (512M)\n"
         "  --device N[,N...]|all       CUDA devices to use, one worker group each (replaces --cl-device; default: all)\n"
         "  --cl-gpu                    use every GPU (the default)\n"
@@ -121,7 +127,7 @@ Options parse(int argc, char **argv)
     Options o;
     // accepted for compatibility, value ignored
     static const std::map<std::string, bool> ignored = {
-        {"--response-file", true}, {"--tmp-dir", true},
+        {"--response-file", true},
         {"--max-split", true}, {"--reader", true}, {"--writer", true}, {"--omp-threads", true},
         {"--decache", false},
         {"--mem-host-splats", true}, {"--mem-reorder", true}, {"--mem-gather", true},
@@ -176,6 +182,7 @@ Options parse(int argc, char **argv)
         else if (a == "--statistics-file") { o.statisticsFile = value(); o.statistics = true; }
         else if (a == "--statistics-cl") o.statisticsCL = true;
         else if (a == "--timeplot") o.timeplot = value();
+        else if (a == "--tmp-dir") o.tmpDir = value();
         else if (a == "--checkpoint") o.checkpoint = value();
         else if (a == "--resume") o.resume = value();
         else if (a == "--split") o.split = true;
@@ -199,6 +206,8 @@ Options parse(int argc, char **argv)
     if (o.memBucketSplats < sizeof(mlsb_splat)) throw std::invalid_argument("Value of --mem-bucket-splats is too small.");
     if (o.memLoadSplats < o.memBucketSplats)   // src/mlsgpu_core.cpp:436-440
         throw std::invalid_argument("Value of --mem-load-splats must be at least that of --mem-bucket-splats.");
+    if (!o.tmpDir.empty() && !o.checkpoint.empty())
+        throw std::invalid_argument("--checkpoint keeps the whole mesh in one file already: it cannot be combined with --tmp-dir.");
     return o;
 }
 
@@ -244,6 +253,30 @@ struct Written
 Written writeMesh(mlsb::Mesher &mesher, bool split, const std::string &output, double fitPrune, const mlsb::PlyWriter &writer)
 {
     Written w;
+    if (mesher.spilling())
+    {
+        // out of core: pruned, compacted and written block by block from the temporary file
+        const std::vector<mlsb::Mesher::Result> chunks = mesher.stream(fitPrune,
+            [&](const mlsb::Mesher::chunk_type &chunk, std::size_t numVertices, std::size_t numTriangles) {
+                if (split && numTriangles == 0) return std::unique_ptr<mlsb::PlyStreamWriter>();
+                w.files++;
+                return writer.openStream(split ? mlsb::chunkName(output, chunk) : output, numVertices, numTriangles);
+            });
+        for (const mlsb::Mesher::Result &c : chunks)
+        {
+            w.totals.totalComponents = c.totalComponents;
+            w.totals.keptComponents = c.keptComponents;
+            w.totals.thresholdVertices = c.thresholdVertices;
+            w.totals.numVertices += c.numVertices;
+            w.totals.numTriangles += c.numTriangles;
+        }
+        if (!split && w.files == 0)   // no block at all: still an (empty) output file
+        {
+            writer.write(output, std::vector<mlsb::PlyWriter::vertex_type>(), std::vector<mlsb::PlyWriter::triangle_type>());
+            w.files = 1;
+        }
+        return w;
+    }
     if (!split)
     {
         mlsb::Mesher::Result mesh = mesher.finish(fitPrune);
@@ -358,6 +391,7 @@ void meshSink(std::uint64_t tag, const mlsb_mesh_sizes *sizes, const void *blob,
     }
     const double t3 = now();
     mlsb::Mesher::complete(*block);
+    st->mesher.spill(*block);   // out-of-core mode (--tmp-dir): the block's arrays leave host memory now
     const double local = (t1 - t0) + (now() - t3);
     {
         std::lock_guard<std::mutex> lock(st->mutex);
@@ -473,6 +507,7 @@ int main(int argc, char **argv)
             st::getStatistic<st::Peak>("mem.pinned") += (std::int64_t) (usage.pinnedHostBytes * (std::uint64_t) o.deviceThreads);
         }
         SinkState state(o.split);
+        if (!o.tmpDir.empty()) state.mesher.enableSpill(o.tmpDir);
         state.timeplot.enabled = !o.timeplot.empty();
         const double tp0 = mlsb_timeplot_now();
         std::vector<mlsb_splat> splats;
@@ -767,6 +802,12 @@ int main(int argc, char **argv)
             st::getStatistic<st::Variable>("device.gather.time").add(tGather);
             st::getStatistic<st::Variable>("mesher.prepare.time").add(state.prepareSeconds);
             st::getStatistic<st::Variable>("mesher.commit.time").add(state.commitSeconds);
+            if (state.mesher.spilling()) st::getStatistic<st::Counter>("mesher.tmp.bytes").add(state.mesher.spilledBytes());
+            {
+                // the process's high-water mark of resident memory (pinned buffers and page tables included)
+                struct rusage usage;
+                if (getrusage(RUSAGE_SELF, &usage) == 0) st::getStatistic<st::Peak>("mem.rss") = (std::int64_t) usage.ru_maxrss * 1024;
+            }
             if (streaming)
             {
                 st::getStatistic<st::Counter>("stream.batches").add(batches.size());

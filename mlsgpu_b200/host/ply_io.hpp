@@ -15,7 +15,9 @@
 #include <cstdio>
 #include <cstring>
 #include <fcntl.h>
+#include <cerrno>
 #include <limits>
+#include <memory>
 #include <map>
 #include <sstream>
 #include <stdexcept>
@@ -231,10 +233,91 @@ private:
 };
 
 /// FastPly::Writer, src/fast_ply.cpp:398-564.
+/// An output file of known size that is filled in pieces, from any thread, at any position: what the
+/// out-of-core mesher writes into (Mesher::stream).  Made by PlyWriter::openStream.
+class PlyStreamWriter
+{
+public:
+    typedef std::array<float, 3> vertex_type;
+    typedef std::array<std::uint32_t, 3> triangle_type;
+
+    PlyStreamWriter(const std::string &path, const std::string &header, std::size_t numVertices, std::size_t numTriangles)
+        : path(path), vertexOffset(header.size()), faceOffset(header.size() + 12 * numVertices)
+    {
+        fd = ::open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
+        if (fd < 0) throw std::runtime_error("cannot create " + path);
+        if (::ftruncate(fd, (off_t) (faceOffset + faceBytes * numTriangles)) != 0)
+        {
+            ::close(fd);
+            throw std::runtime_error("cannot size " + path);
+        }
+        put(header.data(), header.size(), 0);
+    }
+    ~PlyStreamWriter()
+    {
+        if (fd >= 0) ::close(fd);
+    }
+    PlyStreamWriter(const PlyStreamWriter &) = delete;
+    PlyStreamWriter &operator=(const PlyStreamWriter &) = delete;
+
+    /// Vertices first .. first + count of the file.  Thread-safe.
+    void vertices(std::size_t first, const vertex_type *data, std::size_t count)
+    {
+        put(data, 12 * count, vertexOffset + 12 * first);
+    }
+    /// Faces first .. first + count of the file.  Thread-safe.
+    void triangles(std::size_t first, const triangle_type *data, std::size_t count)
+    {
+        const std::size_t slice = 1 << 16;
+        std::vector<unsigned char> packed(faceBytes * std::min(slice, count));
+        for (std::size_t done = 0; done < count; done += slice)
+        {
+            const std::size_t n = std::min(slice, count - done);
+            for (std::size_t i = 0; i < n; i++)
+            {
+                packed[faceBytes * i] = 3;
+                std::memcpy(packed.data() + faceBytes * i + 1, data[done + i].data(), 12);
+            }
+            put(packed.data(), faceBytes * n, faceOffset + faceBytes * (first + done));
+        }
+    }
+    void close()
+    {
+        const int rc = ::close(fd);
+        fd = -1;
+        if (rc != 0) throw std::runtime_error("error writing " + path);
+    }
+
+private:
+    static const std::size_t faceBytes = 13;   // uint8 count + 3 x uint32
+    void put(const void *data, std::size_t bytes, std::size_t offset)
+    {
+        const char *p = static_cast<const char *>(data);
+        while (bytes > 0)
+        {
+            const ssize_t n = ::pwrite(fd, p, bytes, (off_t) offset);
+            if (n < 0 && errno == EINTR) continue;
+            if (n <= 0) throw std::runtime_error("error writing " + path);
+            p += n;
+            offset += (std::size_t) n;
+            bytes -= (std::size_t) n;
+        }
+    }
+    std::string path;
+    std::size_t vertexOffset, faceOffset;
+    int fd = -1;
+};
+
 class PlyWriter
 {
 public:
     void addComment(const std::string &c) { comments.push_back(c); }
+
+    /// The same file as write() would make for these counts, to be filled piece by piece.
+    std::unique_ptr<PlyStreamWriter> openStream(const std::string &path, std::size_t numVertices, std::size_t numTriangles) const
+    {
+        return std::unique_ptr<PlyStreamWriter>(new PlyStreamWriter(path, makeHeader(numVertices, numTriangles), numVertices, numTriangles));
+    }
 
     typedef std::array<float, 3> vertex_type;
     typedef std::array<std::uint32_t, 3> triangle_type;

@@ -26,6 +26,18 @@ def tetra(offset, keys=None):
     return dict(vertices=v, triangles=t, keys=keys, num_internal=4 - len(keys))
 
 
+@pytest.fixture(params=["core", "spill"])
+def mesher_mode(request, tmp_path, monkeypatch):
+    """core: the mesh stays in memory (finish / finishChunks); spill: the out-of-core mesher (--tmp-dir): blocks go
+    to a temporary file as they complete and the output is streamed from it (Mesher::enableSpill / spill / stream).
+    Every mesher fixture must come out the same either way."""
+    if request.param == "spill":
+        monkeypatch.setenv("MLSB_MESHER_TMP", str(tmp_path))
+    else:
+        monkeypatch.delenv("MLSB_MESHER_TMP", raising=False)
+    return request.param
+
+
 def write_blocks(path, blocks, chunks=None):
     """chunks: one (x, y, z) output chunk per block -> the harness runs the mesher in --split mode."""
     with open(path, "wb") as f:
@@ -37,7 +49,7 @@ def write_blocks(path, blocks, chunks=None):
             f.write(np.asarray(chunks, np.uint32).reshape(len(blocks), 3).tobytes())
 
 
-def test_mesher_welds_by_key_and_prunes(tmp_path):
+def test_mesher_welds_by_key_and_prunes(tmp_path, mesher_mode):
     exe = build("mesher_test")
     # two big strips sharing two external vertices (keys 7 and 9) + one isolated small component
     big1 = tetra((0, 0, 0), keys=[7, 9])
@@ -280,6 +292,42 @@ def check_isomorphic(expected_vertices, expected_indices, verts, tris):
     assert canon(ev, expected_indices) == canon(av, tris)
 
 
+def test_out_of_core_mesher_writes_the_same_bytes(tmp_path, monkeypatch):
+    """The out-of-core mesher against the in-core one on a few hundred welded blocks, with and without pruning,
+    one file and --split: the output files are the same bytes (same vertex order, same triangle order)."""
+    rng = np.random.default_rng(11)
+    blocks, chunks = [], []
+    for i in range(240):
+        # chains of tetrahedra welded through keys, of random length, plus loose ones (pruned at 2 %)
+        keys = [1000 + i, 1001 + i] if i % 40 != 39 else []
+        b = tetra((3 * i, float(rng.integers(0, 5)), 0), keys=keys)
+        blocks.append(b)
+        chunks.append((i // 60, 0, 0))
+    exe = build("mesher_test")
+
+    def run(mode, prune, split):
+        if mode == "spill":
+            monkeypatch.setenv("MLSB_MESHER_TMP", str(tmp_path))
+        else:
+            monkeypatch.delenv("MLSB_MESHER_TMP", raising=False)
+        d = tmp_path / ("%s_%s_%d" % (mode, prune, split))
+        d.mkdir()
+        write_blocks(d / "blocks.bin", blocks, chunks if split else None)
+        r = subprocess.run([exe, str(d / "blocks.bin"), prune, str(d / "out"), "1"], check=True, capture_output=True, text=True)
+        files = {f.name: f.read_bytes() for f in sorted(d.iterdir()) if f.name != "blocks.bin"}
+        return r.stdout.replace(str(d), ""), files
+
+    for prune in ("0", "0.02", "0.1", "0.3"):        # 0.3: everything is pruned
+        for split in (0, 1):
+            core, spill = run("core", prune, split), run("spill", prune, split)
+            assert core[0] == spill[0], (prune, split, core[0], spill[0])
+            assert sorted(core[1]) == sorted(spill[1]) and (len(core[1]) >= 1 or prune == "0.3")
+            for name in core[1]:
+                assert core[1][name] == spill[1][name], (prune, split, name)
+    # nothing is left behind in the temporary directory
+    assert not [f for f in tmp_path.iterdir() if f.name.startswith("mlsgpu-mesher-")]
+
+
 # threads > 1: the blocks go through Mesher::prepare/commit/complete concurrently, as the CLI's sink does
 THREADS = pytest.mark.parametrize("threads", [1, 3])
 
@@ -294,7 +342,7 @@ def run_mesher(tmp_path, blocks, prune, threads=1):
 
 
 @THREADS
-def test_mesher_reference_weld_fixture(tmp_path, threads):
+def test_mesher_reference_weld_fixture(tmp_path, threads, mesher_mode):
     b0 = blk([(0, 0, 1), (0, 0, 2), (0, 0, 3), (0, 0, 4), (0, 0, 5)], [], [], [0, 1, 3, 1, 2, 3, 3, 4, 0])
     b1 = blk([], [(1, 0, 1), (1, 0, 2), (1, 0, 3), (1, 0, 4)], [0, 0x8000000000000000, 1, 0x8000000000000001],
              [0, 1, 3, 1, 2, 3, 2, 0, 3])
@@ -321,7 +369,7 @@ WELD_BLOCKS = [
 
 
 @pytest.mark.parametrize("order", [(0, 1, 2), (2, 1, 0)])
-def test_mesher_reference_simple_fixture(tmp_path, order):
+def test_mesher_reference_simple_fixture(tmp_path, order, mesher_mode):
     """testSimple, test/test_mesher.cpp:462-544: three blocks without shared keys, in either order."""
     expected_vertices = [(0, 0, 1), (0, 0, 2), (0, 0, 3), (0, 0, 4), (0, 0, 5), (1, 0, 1), (1, 0, 2), (1, 0, 3), (1, 0, 4),
                          (0, 1, 0), (0, 2, 0), (0, 3, 0), (2, 0, 1), (2, 0, 2)]
@@ -331,7 +379,7 @@ def test_mesher_reference_simple_fixture(tmp_path, order):
     check_isomorphic(expected_vertices, expected_indices, verts, tris)
 
 
-def test_mesher_reference_no_internal_and_no_external_fixtures(tmp_path):
+def test_mesher_reference_no_internal_and_no_external_fixtures(tmp_path, mesher_mode):
     """testNoInternal / testNoExternal, test/test_mesher.cpp:546-650 (degenerate triangles included)."""
     b1 = WELD_BLOCKS[1]
     b2 = blk([], [(2, 0, 1), (2, 0, 2)], [0x1234567812345678, 0x12345678], [0, 1, 1, 0, 0, 1])
@@ -346,7 +394,7 @@ def test_mesher_reference_no_internal_and_no_external_fixtures(tmp_path):
 
 
 @THREADS
-def test_mesher_on_oracle_blocks(tmp_path, threads):
+def test_mesher_on_oracle_blocks(tmp_path, threads, mesher_mode):
     """A real surface shipped out in four blocks (the oracle's marching over four z ranges of the
     reference's truncated-sphere volume): the mesher's weld equals the key weld of the test suite and
     `plymanifold` accepts it — the role of testRandom, test/test_mesher.cpp:1010-1100."""
@@ -385,7 +433,7 @@ def run_split(tmp_path, blocks, chunks, prune, threads=1, base="chunk"):
 
 
 @THREADS
-def test_mesher_reference_chunk_fixture(tmp_path, threads):
+def test_mesher_reference_chunk_fixture(tmp_path, threads, mesher_mode):
     """testChunk, test/test_mesher.cpp:924-993: the blocks of the weld fixture, each in a chunk of its
     own: every file holds its block's vertices, external ones included (no welding across files)."""
     chunks = [(i, i * i, 1) for i in range(4)]
@@ -397,7 +445,7 @@ def test_mesher_reference_chunk_fixture(tmp_path, threads):
         check_isomorphic(b["vertices"], b["triangles"].ravel(), verts, tris)
 
 
-def test_mesher_split_names_and_global_components(tmp_path):
+def test_mesher_split_names_and_global_components(tmp_path, mesher_mode):
     """ChunkNamer (testSimple / testBig, test/test_mesher.cpp:101-122) and what --split keeps global:
     components and pruning span the chunk files, vertices do not."""
     # a chain of tetrahedra welded through keys, laid over three chunks, plus a small island in a fourth
@@ -464,7 +512,7 @@ def test_checkpoint_and_resume(tmp_path):
 
 
 @THREADS
-def test_mesher_reference_prune_fixture(tmp_path, threads):
+def test_mesher_reference_prune_fixture(tmp_path, threads, mesher_mode):
     b0 = blk([(0, 0, 0), (1, 0, 0), (2, 0, 0), (3, 0, 0), (4, 0, 0)], [(0, 3, 0), (1, 3, 0), (2, 3, 0)], [0x30, 0x31, 0x32],
              [0, 4, 1, 1, 4, 2, 2, 4, 3, 5, 7, 6])
     b1 = blk([(0, 1, 0), (1, 1, 0), (2, 1, 0), (3, 1, 0), (4, 1, 0), (5, 1, 0), (0, 2, 0), (3, 2, 0)],
@@ -482,7 +530,7 @@ def test_mesher_reference_prune_fixture(tmp_path, threads):
 
 
 @THREADS
-def test_mesher_reference_empty_fixture(tmp_path, threads):
+def test_mesher_reference_empty_fixture(tmp_path, threads, mesher_mode):
     # TestMesherBase::testEmpty: no blocks (or empty blocks) give an empty, well-formed PLY
     verts, tris = run_mesher(tmp_path, [], 0.0, threads)
     assert len(verts) == 0 and len(tris) == 0
@@ -561,6 +609,17 @@ def test_cli_streamed_run_equals_in_core_run(tmp_path):
     assert sb["bucket.loader.load"]["n"] == sb["stream.batches"] == sb["bucket.loader.compute"]["n"]
     assert sb["mem.splats"] < host.parse_statistics(a.stdout)["mem.splats"] / 2
     d = subprocess.run([build("meshdiff"), str(tmp_path / "core.ply"), str(tmp_path / "stream.ply")], capture_output=True, text=True)
+    assert d.returncode == 0, d.stdout + d.stderr
+    # out of core at both ends: streamed input AND the mesher spilling finished blocks to --tmp-dir; pruning active
+    spill_dir = tmp_path / "tmp"
+    spill_dir.mkdir()
+    c = subprocess.run(common + ["-o", str(tmp_path / "ooc.ply"), "--mem-load-splats", "8M", "--mem-bucket-splats", "4M",
+                                 "--tmp-dir", str(spill_dir)] + files, capture_output=True, text=True)
+    assert c.returncode == 0, c.stderr
+    sc = host.parse_statistics(c.stdout)
+    assert sc["mesher.tmp.bytes"] >= 28 * sc["output.vertices"] and list(spill_dir.iterdir()) == []
+    assert sc["output.vertices"] == sb["output.vertices"] and sc["output.triangles"] == sb["output.triangles"]
+    d = subprocess.run([build("meshdiff"), str(tmp_path / "core.ply"), str(tmp_path / "ooc.ply")], capture_output=True, text=True)
     assert d.returncode == 0, d.stdout + d.stderr
 
 

@@ -124,11 +124,43 @@ public:
         std::size_t numKept = 0;
     };
 
+    /// Arrays whose storage is handed from block to block on a thread instead of going back to the
+    /// allocator: a block's scratch arrays always (complete() returns them), and in out-of-core mode
+    /// the kept arrays as well (spill() returns them) — a fresh 3 MB vector per block costs more in
+    /// page faults than filling it does.
+    struct Pool
+    {
+        std::vector<std::uint32_t> clumpOfLocal, remapExternal, vertexClump;
+        std::vector<vertex_type> vertices;
+        std::vector<triangle_type> triangles;
+    };
+    static Pool &pool()
+    {
+        static thread_local Pool p;
+        return p;
+    }
+    template <typename T> static void take(std::vector<T> &dst, std::vector<T> &pooled)
+    {
+        dst.swap(pooled);
+        dst.clear();
+    }
+    template <typename T> static void give(std::vector<T> &src, std::vector<T> &pooled)
+    {
+        src.clear();
+        if (src.capacity() > pooled.capacity()) pooled.swap(src);
+        std::vector<T>().swap(src);
+    }
+
     /// Step 1, thread-safe: local components and a private copy of the internal vertices.
     static std::unique_ptr<Block> prepare(const mlsb_mesh_sizes &sizes, const void *blob)
     {
         std::unique_ptr<Block> block(new Block);
         Block &b = *block;
+        take(b.clumpOfLocal, pool().clumpOfLocal);
+        take(b.remapExternal, pool().remapExternal);
+        take(b.vertices, pool().vertices);
+        take(b.vertexClump, pool().vertexClump);
+        take(b.triangles, pool().triangles);
         const std::size_t nv = b.nv = sizes.numVertices, nt = b.nt = sizes.numTriangles;
         const std::size_t ni = b.ni = sizes.numInternalVertices;
         b.keys = static_cast<const std::uint64_t *>(blob);
@@ -139,11 +171,14 @@ public:
         static thread_local std::vector<std::int32_t> local;
         local.resize(nv);
         for (std::size_t i = 0; i < nv; i++) local[i] = (std::int32_t) i;
-        for (std::size_t i = 0; i < nt; i++)
         {
-            // two edges are enough: the third is redundant (src/mesher.cpp:230-234)
-            mergeLocal(local, b.tris[i][0], b.tris[i][1]);
-            mergeLocal(local, b.tris[i][1], b.tris[i][2]);
+            std::int32_t *const parent = local.data();
+            for (std::size_t i = 0; i < nt; i++)
+            {
+                // two edges are enough: the third is redundant (src/mesher.cpp:230-234)
+                uniteLocal(parent, (std::int32_t) b.tris[i][0], (std::int32_t) b.tris[i][1]);
+                uniteLocal(parent, (std::int32_t) b.tris[i][1], (std::int32_t) b.tris[i][2]);
+            }
         }
         // ---- one clump per local component ----
         b.clumpOfLocal.resize(nv);
@@ -155,11 +190,24 @@ public:
             }
         // a root is the smallest index of its component, so its entry is final before any of its
         // members reads it
-        for (std::size_t i = 0; i < nv; i++)
+        // (counters are kept in a register over runs of the same clump: one component per block is the
+        // common case, and a read-modify-write of the same counter per element serialises on it)
         {
-            const std::uint32_t c = b.clumpOfLocal[findLocal(local, (std::int32_t) i)];
-            b.clumpOfLocal[i] = c;
-            b.clumpVertices[c]++;
+            std::uint32_t last = 0;
+            std::uint64_t run = 0;
+            for (std::size_t i = 0; i < nv; i++)
+            {
+                const std::uint32_t c = b.clumpOfLocal[findLocal(local, (std::int32_t) i)];
+                b.clumpOfLocal[i] = c;
+                if (c != last)
+                {
+                    b.clumpVertices[last] += run;
+                    last = c;
+                    run = 0;
+                }
+                run++;
+            }
+            if (run) b.clumpVertices[last] += run;
         }
         b.vertices.reserve(nv);
         b.vertices.assign(b.verts, b.verts + ni);
@@ -167,8 +215,8 @@ public:
         b.vertexClump.assign(b.clumpOfLocal.begin(), b.clumpOfLocal.begin() + ni);
         b.clumpKept.assign(b.clumpVertices.size(), 0);
         b.clumpTriangles.assign(b.clumpVertices.size(), 0);
-        for (std::size_t i = 0; i < ni; i++) b.clumpKept[b.clumpOfLocal[i]]++;
-        for (std::size_t i = 0; i < nt; i++) b.clumpTriangles[b.clumpOfLocal[b.tris[i][0]]]++;   // a triangle lies in one clump
+        countRuns(b.clumpKept, ni, [&](std::size_t i) { return b.clumpOfLocal[i]; });
+        countRuns(b.clumpTriangles, nt, [&](std::size_t i) { return b.clumpOfLocal[b.tris[i][0]]; });   // a triangle lies in one clump
         return block;
     }
 
@@ -242,12 +290,15 @@ public:
         const std::uint32_t firstVertex = b.firstVertex;
         const std::uint32_t *ext = b.remapExternal.data();
         auto remap = [=](std::uint32_t v) { return v < ni ? firstVertex + v : ext[v - ni]; };
+        // (resize + indexed stores: reserve + push_back avoids writing the array twice but measured twice as slow)
         b.triangles.resize(b.nt);
+        triangle_type *const out = b.triangles.data();
+        const triangle_type *const in = b.tris;
         for (std::size_t i = 0; i < b.nt; i++)
-            b.triangles[i] = {remap(b.tris[i][0]), remap(b.tris[i][1]), remap(b.tris[i][2])};
+            out[i] = triangle_type{{remap(in[i][0]), remap(in[i][1]), remap(in[i][2])}};
         // scratch that is not needed any more
-        std::vector<std::uint32_t>().swap(b.clumpOfLocal);
-        std::vector<std::uint32_t>().swap(b.remapExternal);
+        give(b.clumpOfLocal, pool().clumpOfLocal);
+        give(b.remapExternal, pool().remapExternal);
         b.keys = nullptr;
         b.verts = nullptr;
         b.tris = nullptr;
@@ -264,9 +315,9 @@ public:
         writeAt(b.vertices.data(), bytesV, b.spillOffset);
         writeAt(b.vertexClump.data(), bytesC, b.spillOffset + (std::int64_t) bytesV);
         writeAt(b.triangles.data(), bytesT, b.spillOffset + (std::int64_t) (bytesV + bytesC));
-        std::vector<vertex_type>().swap(b.vertices);
-        std::vector<std::uint32_t>().swap(b.vertexClump);
-        std::vector<triangle_type>().swap(b.triangles);
+        give(b.vertices, pool().vertices);
+        give(b.vertexClump, pool().vertexClump);
+        give(b.triangles, pool().triangles);
     }
 
     /// All steps, for a single-threaded consumer.
@@ -679,10 +730,40 @@ private:
         }
         return x;
     }
-    static void mergeLocal(std::vector<std::int32_t> &local, std::uint32_t a, std::uint32_t b)
+    /// Union by Rem's algorithm (interleaved finds with splicing): parents always have the smaller
+    /// index, so a root is the smallest vertex of its component, as prepare() relies on.
+    static void uniteLocal(std::int32_t *parent, std::int32_t x, std::int32_t y)
     {
-        const std::int32_t ra = findLocal(local, (std::int32_t) a), rb = findLocal(local, (std::int32_t) b);
-        if (ra != rb) local[std::max(ra, rb)] = std::min(ra, rb);
+        while (parent[x] != parent[y])
+        {
+            if (parent[x] < parent[y]) std::swap(x, y);
+            if (x == parent[x])
+            {
+                parent[x] = parent[y];
+                return;
+            }
+            const std::int32_t z = parent[x];
+            parent[x] = parent[y];
+            x = z;
+        }
+    }
+    /// counts[label(i)]++ for i < n, with the counter of the current run of equal labels in a register.
+    template <typename Label>
+    static void countRuns(std::vector<std::uint32_t> &counts, std::size_t n, Label label)
+    {
+        std::uint32_t last = 0, run = 0;
+        for (std::size_t i = 0; i < n; i++)
+        {
+            const std::uint32_t c = label(i);
+            if (c != last)
+            {
+                counts[last] += run;
+                last = c;
+                run = 0;
+            }
+            run++;
+        }
+        if (run) counts[last] += run;
     }
     std::uint32_t findClump(std::uint32_t x)
     {

@@ -597,7 +597,7 @@ def test_cli_streamed_run_equals_in_core_run(tmp_path):
     files, fit_grid = synth(tmp_path, "C3", 1_500_000)
     exe = build("mlsgpu")
     common = [exe, "--fit-grid", repr(fit_grid), "--device", "0", "--device-threads", "3", "--statistics"]
-    a = subprocess.run(common + ["-o", str(tmp_path / "core.ply")] + files, capture_output=True, text=True)
+    a = subprocess.run(common + ["-o", str(tmp_path / "core.ply"), "--in-core"] + files, capture_output=True, text=True)
     b = subprocess.run(common + ["-o", str(tmp_path / "stream.ply"), "--mem-load-splats", "8M", "--mem-bucket-splats", "4M"] + files,
                        capture_output=True, text=True)
     assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
@@ -610,6 +610,7 @@ def test_cli_streamed_run_equals_in_core_run(tmp_path):
     assert sb["mem.splats"] < host.parse_statistics(a.stdout)["mem.splats"] / 2
     d = subprocess.run([build("meshdiff"), str(tmp_path / "core.ply"), str(tmp_path / "stream.ply")], capture_output=True, text=True)
     assert d.returncode == 0, d.stdout + d.stderr
+    assert "mesher.tmp.bytes" not in a.stdout and sb["mesher.tmp.bytes"] > 0      # --in-core; the default is out of core
     # out of core at both ends: streamed input AND the mesher spilling finished blocks to --tmp-dir; pruning active
     spill_dir = tmp_path / "tmp"
     spill_dir.mkdir()

@@ -76,14 +76,19 @@ public:
         totalTriangles = other.totalTriangles;
         spillFd = other.spillFd;
         spillSize.store(other.spillSize.load());
+        keepInCore = other.keepInCore;
+        inCoreBytes.store(other.inCoreBytes.load());
         other.spillFd = -1;
         return *this;
     }
 
     /// Out-of-core mode (--tmp-dir): from now on spill() moves completed blocks into an unnamed
     /// temporary file in `dir`.  Call before the first block.
-    void enableSpill(const std::string &dir)
+    /// keepBytes: blocks stay in host memory until that much is held; only the ones after that go to the
+    /// file (0: every block does).  A mesh that fits is then never written twice.
+    void enableSpill(const std::string &dir, std::uint64_t keepBytes = 0)
     {
+        keepInCore = keepBytes;
         if (totalVertices != 0 || spillFd >= 0) throw std::logic_error("enableSpill() comes before the first block");
         std::string path = (dir.empty() ? std::string(".") : dir) + "/mlsgpu-mesher-XXXXXX";
         std::vector<char> name(path.begin(), path.end());
@@ -311,6 +316,11 @@ public:
         if (spillFd < 0) return;
         const std::size_t bytesV = b.vertices.size() * sizeof(vertex_type), bytesC = b.vertexClump.size() * sizeof(std::uint32_t);
         const std::size_t bytesT = b.triangles.size() * sizeof(triangle_type);
+        if (inCoreBytes.load() + bytesV + bytesC + bytesT <= keepInCore)
+        {
+            inCoreBytes.fetch_add(bytesV + bytesC + bytesT);   // within the budget: the block keeps its arrays
+            return;
+        }
         b.spillOffset = (std::int64_t) spillSize.fetch_add(bytesV + bytesC + bytesT);
         writeAt(b.vertices.data(), bytesV, b.spillOffset);
         writeAt(b.vertexClump.data(), bytesC, b.spillOffset + (std::int64_t) bytesV);
@@ -793,6 +803,8 @@ private:
     std::size_t totalVertices = 0, totalTriangles = 0;
     int spillFd = -1;                          // out-of-core mode: the temporary file
     std::atomic<std::uint64_t> spillSize{0};   // its length (blocks reserve their place with a fetch_add)
+    std::uint64_t keepInCore = 0;              // bytes of block arrays that may stay in host memory before blocks spill
+    std::atomic<std::uint64_t> inCoreBytes{0};
 };
 
 /// ChunkNamer (src/mesher.cpp:88-96): base_XXXX_YYYY_ZZZZ.ply, at least four digits per coordinate.

@@ -48,7 +48,9 @@ int main(int argc, char **argv)
     if (split) mesher = mlsb::Mesher(true);
     // MLSB_MESHER_TMP=dir: the out-of-core mesher (blocks spilled to a temporary file there, output streamed)
     const char *tmpDir = std::getenv("MLSB_MESHER_TMP");
-    if (tmpDir && argc != 6) mesher.enableSpill(tmpDir);
+    // MLSB_MESHER_KEEP=bytes: blocks stay in memory up to that many bytes, the rest is spilled
+    const char *keep = std::getenv("MLSB_MESHER_KEEP");
+    if (tmpDir && argc != 6) mesher.enableSpill(tmpDir, keep ? std::strtoull(keep, nullptr, 10) : 0);
     if (threads <= 1)
         for (std::uint64_t b = 0; b < numBlocks; b++)
         {

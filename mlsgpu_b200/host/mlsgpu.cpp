@@ -63,11 +63,15 @@ struct Options
     // is sized for the hosts B200s sit in.  Pass the reference's value to get its behaviour.
     std::uint64_t memLoadSplats = 16ull << 30;
     std::uint64_t memMesh = 512ull << 20;
-    // The mesher is out of core like the reference's (src/mesher.cpp:343-445): finished blocks go to a temporary
-    // file in tmpDir (the reference's default is the system's temporary directory too).  Measured on C3 (100 M
-    // splats): faster than holding the mesh in memory (11.8 against 14.7 s) at 5.7 instead of 38.4 GB resident.
+    // The mesher can work out of core like the reference's (src/mesher.cpp:343-445): finished blocks go to a
+    // temporary file in tmpDir (the reference's default is the system's temporary directory too) once memHostMesh
+    // bytes of mesh are held in memory.  Measured on C3 (100 M splats, 16 GB of mesh) with EVERYTHING going through
+    // the file: 5.7 instead of 38.4 GB resident; 11.8 against 14.7 s on one box and 15.4 against 11.0 s on another —
+    // the mesh is written twice, so it follows the temporary directory's disk.  Hence the budget: a mesh that fits
+    // stays in memory, one that does not still gets done.
     std::string tmpDir;
     bool inCore = false;
+    std::int64_t memHostMesh = -1;   // < 0: a quarter of the physical memory
     std::vector<int> devices;        // CUDA ordinals; empty = every device found (the reference's default, src/clh.cpp:180-240)
     bool quiet = false, statistics = false, statisticsCL = false, split = false;
     std::uint64_t splitSize = 100ull << 20;   // src/mlsgpu_core.cpp:162
@@ -97,10 +101,11 @@ void usage()
         "  --mem-bucket-splats SIZE    device memory for splats of one bin, K/M/G suffix (64M)\n"
         "  --mem-load-splats SIZE      host memory for splats loaded at once; larger inputs are streamed from\n"
         "                              disk in several passes (16G; the reference's default is 256M)\n"
-        "  --tmp-dir DIR               directory for the mesher's temporary file ($TMPDIR, else /tmp): finished blocks\n"
-        "                              go there (40 bytes per vertex) and the output is streamed from it\n"
-        "  --in-core                   keep the mesh in host memory instead (~38 bytes per output vertex plus allocator\n"
-        "                              slack; implied by --checkpoint)\n"
+        "  --mem-host-mesh SIZE        host memory for the mesh (a quarter of the physical memory): finished blocks stay\n"
+        "                              in memory up to that size, the ones after that go to a temporary file (40 bytes\n"
+        "                              per vertex) and the output is streamed from both; 0 = everything goes to the file\n"
+        "  --tmp-dir DIR               directory for that temporary file ($TMPDIR, else /tmp)\n"
+        "  --in-core                   never use a temporary file (implied by --checkpoint)\n"
         "  --mem-mesh SIZE             device memory for raw mesh data (512M)\n"
         "  --device N[,N...]|all       CUDA devices to use, one worker group each (replaces --cl-device; default: all)\n"
         "  --cl-gpu                    use every GPU (the default)\n"
@@ -189,6 +194,7 @@ Options parse(int argc, char **argv)
         else if (a == "--timeplot") o.timeplot = value();
         else if (a == "--tmp-dir") o.tmpDir = value();
         else if (a == "--in-core") o.inCore = true;
+        else if (a == "--mem-host-mesh") o.memHostMesh = (std::int64_t) parseCapacity(value());
         else if (a == "--checkpoint") o.checkpoint = value();
         else if (a == "--resume") o.resume = value();
         else if (a == "--split") o.split = true;
@@ -217,6 +223,11 @@ Options parse(int argc, char **argv)
     {
         const char *env = std::getenv("TMPDIR");
         o.tmpDir = env && *env ? env : "/tmp";
+    }
+    if (o.memHostMesh < 0)
+    {
+        const long pages = sysconf(_SC_PHYS_PAGES), pageSize = sysconf(_SC_PAGE_SIZE);
+        o.memHostMesh = pages > 0 && pageSize > 0 ? (std::int64_t) pages / 4 * pageSize : (std::int64_t) 8 << 30;
     }
     return o;
 }
@@ -517,7 +528,7 @@ int main(int argc, char **argv)
             st::getStatistic<st::Peak>("mem.pinned") += (std::int64_t) (usage.pinnedHostBytes * (std::uint64_t) o.deviceThreads);
         }
         SinkState state(o.split);
-        if (!o.inCore) state.mesher.enableSpill(o.tmpDir);
+        if (!o.inCore) state.mesher.enableSpill(o.tmpDir, (std::uint64_t) o.memHostMesh);
         state.timeplot.enabled = !o.timeplot.empty();
         const double tp0 = mlsb_timeplot_now();
         std::vector<mlsb_splat> splats;

@@ -306,8 +306,11 @@ def test_out_of_core_mesher_writes_the_same_bytes(tmp_path, monkeypatch):
     exe = build("mesher_test")
 
     def run(mode, prune, split):
-        if mode == "spill":
+        monkeypatch.delenv("MLSB_MESHER_KEEP", raising=False)
+        if mode in ("spill", "mixed"):
             monkeypatch.setenv("MLSB_MESHER_TMP", str(tmp_path))
+            if mode == "mixed":       # a budget that about a third of the blocks fit in: the rest goes to the file
+                monkeypatch.setenv("MLSB_MESHER_KEEP", str(80 * (4 * 12 + 4 * 4 + 4 * 12)))
         else:
             monkeypatch.delenv("MLSB_MESHER_TMP", raising=False)
         d = tmp_path / ("%s_%s_%d" % (mode, prune, split))
@@ -319,11 +322,13 @@ def test_out_of_core_mesher_writes_the_same_bytes(tmp_path, monkeypatch):
 
     for prune in ("0", "0.02", "0.1", "0.3"):        # 0.3: everything is pruned
         for split in (0, 1):
-            core, spill = run("core", prune, split), run("spill", prune, split)
-            assert core[0] == spill[0], (prune, split, core[0], spill[0])
-            assert sorted(core[1]) == sorted(spill[1]) and (len(core[1]) >= 1 or prune == "0.3")
-            for name in core[1]:
-                assert core[1][name] == spill[1][name], (prune, split, name)
+            core = run("core", prune, split)
+            for mode in ("spill", "mixed"):
+                other = run(mode, prune, split)
+                assert core[0] == other[0], (mode, prune, split, core[0], other[0])
+                assert sorted(core[1]) == sorted(other[1]) and (len(core[1]) >= 1 or prune == "0.3")
+                for name in core[1]:
+                    assert core[1][name] == other[1][name], (mode, prune, split, name)
     # nothing is left behind in the temporary directory
     assert not [f for f in tmp_path.iterdir() if f.name.startswith("mlsgpu-mesher-")]
 
@@ -610,15 +615,16 @@ def test_cli_streamed_run_equals_in_core_run(tmp_path):
     assert sb["mem.splats"] < host.parse_statistics(a.stdout)["mem.splats"] / 2
     d = subprocess.run([build("meshdiff"), str(tmp_path / "core.ply"), str(tmp_path / "stream.ply")], capture_output=True, text=True)
     assert d.returncode == 0, d.stdout + d.stderr
-    assert "mesher.tmp.bytes" not in a.stdout and sb["mesher.tmp.bytes"] > 0      # --in-core; the default is out of core
-    # out of core at both ends: streamed input AND the mesher spilling finished blocks to --tmp-dir; pruning active
+    # --in-core never opens a temporary file; by default there is one, unused while the mesh fits --mem-host-mesh
+    assert "mesher.tmp.bytes" not in a.stdout and sb["mesher.tmp.bytes"] == 0
+    # out of core at both ends: streamed input AND the mesher spilling all but 4 MB of finished blocks to --tmp-dir
     spill_dir = tmp_path / "tmp"
     spill_dir.mkdir()
     c = subprocess.run(common + ["-o", str(tmp_path / "ooc.ply"), "--mem-load-splats", "8M", "--mem-bucket-splats", "4M",
-                                 "--tmp-dir", str(spill_dir)] + files, capture_output=True, text=True)
+                                 "--tmp-dir", str(spill_dir), "--mem-host-mesh", "4M"] + files, capture_output=True, text=True)
     assert c.returncode == 0, c.stderr
     sc = host.parse_statistics(c.stdout)
-    assert sc["mesher.tmp.bytes"] >= 28 * sc["output.vertices"] and list(spill_dir.iterdir()) == []
+    assert sc["mesher.tmp.bytes"] >= 28 * sc["output.vertices"] - (6 << 20) and list(spill_dir.iterdir()) == []
     assert sc["output.vertices"] == sb["output.vertices"] and sc["output.triangles"] == sb["output.triangles"]
     d = subprocess.run([build("meshdiff"), str(tmp_path / "core.ply"), str(tmp_path / "ooc.ply")], capture_output=True, text=True)
     assert d.returncode == 0, d.stdout + d.stderr

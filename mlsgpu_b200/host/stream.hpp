@@ -37,6 +37,7 @@ struct InputChunk
     std::size_t finite = 0;             // splats that survive the non-finite filter
     double mn[3], mx[3];                // world bounds of position -+ radius over them
     std::int64_t blockFirst[3], blockLast[3];   // blocks they reach (pass 2); empty if blockFirst[0] > blockLast[0]
+    std::vector<std::uint32_t> blocks;          // exactly which ones (sorted indices): a handful for a coherent chunk
 };
 
 class SplatStream
@@ -119,6 +120,7 @@ public:
         {
             std::vector<mlsb_splat> buf(kChunkVertices);
             std::vector<char> scratch;
+            std::vector<std::pair<std::size_t, std::uint64_t>> local;   // (block, instances) of the chunk in hand
 #pragma omp for schedule(dynamic, 4)
             for (std::int64_t ci = 0; ci < (std::int64_t) chunks.size(); ci++)
             {
@@ -126,6 +128,11 @@ public:
                 for (int a = 0; a < 3; a++) c.blockFirst[a] = INT64_MAX, c.blockLast[a] = INT64_MIN;
                 if (c.finite == 0) continue;
                 readers[c.file]->readRange(c.first, c.count, buf.data(), scratch);
+                // instances per block of this chunk first (consecutive splats mostly reach the same block),
+                // then one atomic add per block the chunk reaches
+                c.blocks.clear();
+                local.clear();
+                std::size_t lastIndex = SIZE_MAX, lastSlot = 0;
                 for (std::size_t i = 0; i < c.count; i++)
                 {
                     mlsb_splat s = buf[i];
@@ -143,10 +150,23 @@ public:
                         for (std::int64_t by = first[1]; by <= last[1]; by++)
                             for (std::int64_t bx = first[0]; bx <= last[0]; bx++)
                             {
-                                std::uint64_t &slot = counts[layout.index(bx, by, bz)];
-#pragma omp atomic
-                                slot++;
+                                const std::size_t index = layout.index(bx, by, bz);
+                                if (index != lastIndex)
+                                {
+                                    lastIndex = index;
+                                    for (lastSlot = 0; lastSlot < local.size() && local[lastSlot].first != index; lastSlot++) {}
+                                    if (lastSlot == local.size()) local.push_back(std::make_pair(index, (std::uint64_t) 0));
+                                }
+                                local[lastSlot].second++;
                             }
+                }
+                std::sort(local.begin(), local.end());
+                for (const std::pair<std::size_t, std::uint64_t> &e : local)
+                {
+                    c.blocks.push_back((std::uint32_t) e.first);
+                    std::uint64_t &slot = counts[e.first];
+#pragma omp atomic
+                    slot += e.second;
                 }
             }
         }
@@ -181,11 +201,10 @@ public:
         for (std::size_t ci = 0; ci < chunks.size(); ci++)
         {
             const InputChunk &c = chunks[ci];
-            if (c.finite == 0 || c.blockFirst[0] > c.blockLast[0]) continue;
-            // block indices are z-major: the chunk's lie within [index(first), index(last)]
-            const std::size_t lo = layout.index(c.blockFirst[0], c.blockFirst[1], c.blockFirst[2]);
-            const std::size_t hi = layout.index(c.blockLast[0], c.blockLast[1], c.blockLast[2]);
-            if (hi >= begin && lo < end) wanted.push_back(ci);
+            if (c.finite == 0 || c.blocks.empty()) continue;
+            // the chunk is read again only if one of the blocks it reaches belongs to the batch
+            const std::vector<std::uint32_t>::const_iterator it = std::lower_bound(c.blocks.begin(), c.blocks.end(), (std::uint32_t) begin);
+            if (it != c.blocks.end() && *it < end) wanted.push_back(ci);
         }
         std::vector<std::vector<mlsb_splat>> parts(wanted.size());
 #pragma omp parallel

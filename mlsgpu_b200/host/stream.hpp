@@ -35,8 +35,8 @@ struct InputChunk
 {
     std::size_t file, first, count;     // vertices [first, first + count) of readers[file]
     std::size_t finite = 0;             // splats that survive the non-finite filter
-    double mn[3], mx[3];                // world bounds of position -+ radius over them
-    std::int64_t blockFirst[3], blockLast[3];   // blocks they reach (pass 2); empty if blockFirst[0] > blockLast[0]
+    double mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};   // world bounds of position -+ radius over them
+    std::int64_t blockFirst[3] = {0, 0, 0}, blockLast[3] = {-1, -1, -1};   // blocks they reach (pass 2); empty if blockFirst[0] > blockLast[0]
     std::vector<std::uint32_t> blocks;          // exactly which ones (sorted indices): a handful for a coherent chunk
 };
 

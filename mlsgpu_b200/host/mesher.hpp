@@ -30,6 +30,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <istream>
 #include <map>
 #include <memory>
@@ -503,23 +504,37 @@ public:
             {
                 std::vector<std::uint32_t> newIndex;
                 if (prune) newIndex.assign(chunk.totalVertices, UINT32_MAX);
+                // (an exception must not leave a worksharing loop: every iteration catches its own, notes the
+                // first message and lets the remaining iterations fall through)
                 std::string failure;
+                std::atomic<bool> failed(false);
+                auto guarded = [&](const std::function<void()> &body) {
+                    if (failed.load()) return;
+                    try
+                    {
+                        body();
+                    }
+                    catch (const std::exception &e)
+                    {
+                        failed.store(true);
+#pragma omp critical(mlsb_mesher_stream_failure)
+                        if (failure.empty()) failure = e.what();
+                    }
+                };
 #pragma omp parallel
                 {
                     std::vector<vertex_type> verts;
                     std::vector<std::uint32_t> labels;
                     std::vector<triangle_type> tris;
-                    try
-                    {
 #pragma omp for schedule(dynamic, 1)
-                        for (std::int64_t i = 0; i < numBlocks; i++)
-                        {
+                    for (std::int64_t i = 0; i < numBlocks; i++)
+                        guarded([&] {
                             const Block &b = *chunk.blocks[i];
                             const vertex_type *v = fetch(b, 0, b.numKept, b.vertices, verts);
                             if (!prune)
                             {
                                 writer->vertices(firstV[i], v, b.numKept);
-                                continue;
+                                return;
                             }
                             const std::uint32_t *l = fetch(b, b.numKept * sizeof(vertex_type), b.numKept, b.vertexClump, labels);
                             std::size_t n = 0;
@@ -535,17 +550,17 @@ public:
                                     verts[n++] = v[k];
                                 }
                             writer->vertices(firstV[i], verts.data(), n);
-                        }
-                        // (the implicit barrier: every newIndex is final before a triangle reads it)
+                        });
+                    // (the loop's implicit barrier: every newIndex is final before a triangle reads it)
 #pragma omp for schedule(dynamic, 1)
-                        for (std::int64_t i = 0; i < numBlocks; i++)
-                        {
+                    for (std::int64_t i = 0; i < numBlocks; i++)
+                        guarded([&] {
                             const Block &b = *chunk.blocks[i];
                             const triangle_type *t = fetch(b, b.numKept * (sizeof(vertex_type) + sizeof(std::uint32_t)), b.nt, b.triangles, tris);
                             if (!prune)
                             {
                                 writer->triangles(firstT[i], t, b.nt);
-                                continue;
+                                return;
                             }
                             if (t != tris.data())
                             {
@@ -557,13 +572,7 @@ public:
                                 if (newIndex[t[k][0]] != UINT32_MAX)   // a triangle's vertices share one component
                                     tris[n++] = triangle_type{{newIndex[t[k][0]], newIndex[t[k][1]], newIndex[t[k][2]]}};
                             writer->triangles(firstT[i], tris.data(), n);
-                        }
-                    }
-                    catch (const std::exception &e)
-                    {
-#pragma omp critical
-                        if (failure.empty()) failure = e.what();
-                    }
+                        });
                 }
                 if (!failure.empty()) throw std::runtime_error(failure);
                 writer->close();
